@@ -1,0 +1,59 @@
+# Build everything in-tree (the .so files travel to the GPU box with the snapshot).
+#   make            -> gpu library, host mirror, oracle, C++ test binaries
+#   make gpu|host|oracle
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: the reference's f64 arithmetic has no fused multiply-add; the
+# device must round exactly like the oracle (BASELINE.json north_star).
+NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v -Iinclude
+CXXFLAGS  := -std=c++20 -O2 -ffp-contract=off -fPIC -Wall -Wextra -Iinclude
+CFLAGS    := -std=c11 -O2 -ffp-contract=off -fPIC -Wall -Wextra -Iinclude
+
+PKG       := portrayer_b200
+GPU_LIB   := $(PKG)/lib/libportrayer_gpu.so
+HOST_LIB  := $(PKG)/lib/libportrayer_host.so
+ORACLE_LIB:= oracle/liboracle.so
+HOST_TEST := tests/cpp/test_host
+EXAMPLE_BIN := $(PKG)/lib/portrayer_example
+
+GPU_SRC   := $(wildcard $(PKG)/csrc/*.cu)
+GPU_HDR   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/portrayer_gpu.h
+HOST_SRC  := $(wildcard $(PKG)/host/*.cpp) $(wildcard $(PKG)/host/examples/*.cpp)
+HOST_HDR  := $(wildcard $(PKG)/host/*.hpp) $(wildcard $(PKG)/host/*.h) $(wildcard $(PKG)/host/examples/*.hpp) include/portrayer_gpu.h
+
+all: gpu host oracle hosttest example
+gpu: $(GPU_LIB)
+host: $(HOST_LIB)
+oracle: $(ORACLE_LIB)
+hosttest: $(HOST_TEST)
+example: $(EXAMPLE_BIN)
+
+$(PKG)/lib:
+	mkdir -p $@
+
+build/scene_blob.o: $(PKG)/csrc/scene_blob.c include/portrayer_gpu.h
+	mkdir -p build
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(GPU_LIB): $(GPU_SRC) $(GPU_HDR) build/scene_blob.o | $(PKG)/lib
+	$(NVCC) $(NVFLAGS) -shared $(GPU_SRC) build/scene_blob.o -o $@ 2> build/ptxas_gpu.log || (cat build/ptxas_gpu.log; false)
+	@grep -E "error|warning" build/ptxas_gpu.log || true
+
+$(HOST_LIB): $(HOST_SRC) $(HOST_HDR) $(GPU_LIB) | $(PKG)/lib
+	$(CXX) $(CXXFLAGS) -shared $(HOST_SRC) -o $@ -L$(PKG)/lib -lportrayer_gpu -Wl,-rpath,'$$ORIGIN'
+
+$(ORACLE_LIB): oracle/oracle.c oracle/oracle.h include/portrayer_gpu.h
+	$(CC) $(CFLAGS) -shared oracle/oracle.c -o $@ -lm -lpthread
+
+$(HOST_TEST): tests/cpp/test_host.cpp $(HOST_LIB)
+	$(CXX) $(CXXFLAGS) -I$(PKG)/host $< -o $@ -L$(PKG)/lib -lportrayer_host -lportrayer_gpu -Wl,-rpath,'$$ORIGIN/../../$(PKG)/lib'
+
+$(EXAMPLE_BIN): $(PKG)/host/tools/example_main.cpp $(HOST_LIB)
+	$(CXX) $(CXXFLAGS) -I$(PKG)/host $< -o $@ -L$(PKG)/lib -lportrayer_host -lportrayer_gpu -Wl,-rpath,'$$ORIGIN'
+
+clean:
+	rm -rf build $(PKG)/lib $(ORACLE_LIB) $(HOST_TEST)
+
+.PHONY: all gpu host oracle hosttest example clean

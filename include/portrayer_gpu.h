@@ -1,0 +1,351 @@
+/*
+ * portrayer_gpu.h — C ABI of the B200 render-loop library (libportrayer_gpu.so).
+ *
+ * This is the drop-in boundary for portrayer's per-pixel render loop.  The
+ * reference (sunjay/portrayer, pure Rust) has NO FFI today; the cut line is
+ * between "scene prepared" and the rayon pixel loop:
+ *
+ *     src/render.rs:124-126   FlatScene::from + KDTreeScene::from   (host, stays)
+ *     src/render.rs:127-150   par_chunks_mut pixel loop              (REPLACED)
+ *
+ * Everything the replaced loop reads is passed here as plain pointers + sizes:
+ * the flattened scene (src/flat_scene.rs:50-61), the kd-tree over it
+ * (src/kdtree/node.rs:13-25, src/kdtree/leaf.rs:70-78), per-mesh kd-trees
+ * (src/kdtree/kdmesh.rs:19-24), triangle soups (src/primitive/mesh.rs:22-34,
+ * src/primitive/triangle.rs:9-19), materials (src/material.rs:51-86), lights
+ * (src/light.rs:74-85), textures (src/texture.rs:78-80), the prepared camera
+ * (src/camera.rs:17-32) and the per-pixel background colour
+ * (src/render.rs:31-34).  The output is the RGB8 buffer of
+ * src/render.rs:143-147, written only inside the slice (src/render.rs:136-138).
+ *
+ * No torch / C++ types appear in any signature.  All functions return 0 on
+ * success or a negative PtError; pt_last_error() gives the message (the
+ * reference's panic text where the reference would have panicked).
+ */
+#ifndef PORTRAYER_GPU_H
+#define PORTRAYER_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Constants of the reference that are part of the contract                    */
+/* ------------------------------------------------------------------------- */
+#define PT_EPSILON 0.00001            /* src/math.rs:15 */
+#define PT_GAMMA 2.2                  /* src/math.rs:20 */
+#define PT_MAX_RECURSION_DEPTH 10u    /* src/material.rs:12 */
+#define PT_DEFAULT_SAMPLES 100u       /* src/render.rs:113 */
+
+#define PT_MAX_KD_STACK 48            /* deepest kd-tree (KD_DEPTH / KD_MESH_DEPTH) the device walks */
+#define PT_MAX_LIGHTS 32
+
+/* ------------------------------------------------------------------------- */
+/* Errors                                                                      */
+/* ------------------------------------------------------------------------- */
+typedef enum PtError {
+    PT_OK = 0,
+    PT_ERR_INVALID = -1,          /* bad argument / malformed blob */
+    PT_ERR_CUDA = -2,             /* CUDA runtime failure (no device, OOM, launch error) */
+    PT_ERR_NO_TEXCOORD_NORMALMAP = -3, /* "Normal/Texture mapping is not supported for this primitive!" material.rs:133 */
+    PT_ERR_NO_TEXCOORD_TEXTURE = -4,   /* "Texture mapping is not supported for this primitive!" material.rs:141 */
+    PT_ERR_KD_PLANE_MISS = -5,    /* "bug: ray should definitely hit infinite plane" kdtree/node.rs:147,178 */
+    PT_ERR_TIR_INSIDE = -6,       /* "bug: should not have total internal reflection when casting inside surface" material.rs:258 */
+    PT_ERR_KD_TOO_DEEP = -7,      /* kd depth > PT_MAX_KD_STACK */
+    PT_ERR_OVERFLOW = -8          /* ray-tree node pool exhausted even at the minimum batch size */
+} PtError;
+
+/* bits of the device-side error word (PtStats.device_error_bits) */
+#define PT_DEVERR_NORMALMAP 1u
+#define PT_DEVERR_TEXTURE 2u
+#define PT_DEVERR_KD_PLANE 4u
+#define PT_DEVERR_TIR 8u
+#define PT_DEVERR_OVERFLOW 16u
+
+/* ------------------------------------------------------------------------- */
+/* Scene records (all little-endian, f64 unless stated)                        */
+/* ------------------------------------------------------------------------- */
+
+/* Primitive enum, src/primitive.rs:67-81 */
+typedef enum PtPrimType {
+    PT_PRIM_SPHERE = 0,   /* src/primitive/sphere.rs */
+    PT_PRIM_TRIANGLE = 1, /* src/primitive/triangle.rs as a top-level primitive (mesh record, no bbox gate) */
+    PT_PRIM_MESH = 2,     /* src/primitive/mesh.rs: bbox gate + linear scan */
+    PT_PRIM_KDMESH = 3,   /* src/kdtree/kdmesh.rs: bbox gate + kd walk */
+    PT_PRIM_PLANE = 4,    /* src/primitive/plane.rs */
+    PT_PRIM_CUBE = 5,     /* src/primitive/cube.rs */
+    PT_PRIM_CYLINDER = 6, /* src/primitive/cylinder.rs */
+    PT_PRIM_CONE = 7      /* src/primitive/cone.rs */
+} PtPrimType;
+
+/* One kd-tree node, 16 bytes.  Replaces KDTreeNode::{Split,Leaf}
+ * (src/kdtree/node.rs:13-25); the per-node BoundingBox is dropped because the
+ * traversal (node.rs:66-203) only ever reads the ROOT's extent.
+ *   split node: a = axis(0|1|2) | front_child << 2 ; b = back_child ; split = plane coordinate
+ *   leaf  node: a = 3 | first_item << 2            ; b = item_count ; split unused
+ * child / item indices are relative to the tree's own node / item base. */
+typedef struct PtKdNode {
+    double split;
+    uint32_t a;
+    uint32_t b;
+} PtKdNode;
+
+/* What an intersection test needs for one flat instance
+ * (FlatSceneNode, src/flat_scene.rs:50-61).  128 bytes, one cache line. */
+typedef struct PtInstance {
+    double invtrans[12]; /* rows 0..2 of the world->object Mat4, row-major 3x4 */
+    uint32_t prim;       /* PtPrimType */
+    uint32_t mesh;       /* index into meshes for TRIANGLE/MESH/KDMESH, else 0xFFFFFFFF */
+    uint32_t material;   /* index into materials */
+    uint32_t reserved;
+    double pad[2];
+} PtInstance;
+
+/* object->world rows 0..2 (flat_scene.rs:87); normal_trans = invtrans^T is
+ * derived from PtInstance.invtrans (flat_scene.rs:105). 96 bytes. */
+typedef struct PtInstanceTrans {
+    double trans[12];
+} PtInstanceTrans;
+
+#define PT_MESH_LINEAR 0u   /* Mesh */
+#define PT_MESH_KD 1u       /* KDMesh */
+#define PT_MESH_TRIANGLE 2u /* single Triangle primitive, no bbox gate */
+#define PT_MESH_FLAG_NORMALS 1u /* Shading::Smooth: per-corner normals present */
+#define PT_MESH_FLAG_UVS 2u     /* per-corner texture coordinates present */
+
+/* Per-mesh record. bbox_invtrans is BoundingBox.invtrans
+ * (src/bounding_box.rs:57-82), extent is BoundingBox::extent of the kd root
+ * (src/bounding_box.rs:95-99, squared diagonal).  160 bytes. */
+typedef struct PtMesh {
+    double bbox_invtrans[12];
+    double extent;
+    uint32_t kind;
+    uint32_t flags;
+    uint32_t tri_first;  /* first triangle in tri_pos (and tri_normals/tri_uvs via *_first below) */
+    uint32_t tri_count;
+    uint32_t node_first; /* KD: first node in blas_nodes */
+    uint32_t node_count;
+    uint32_t item_first; /* KD: base of this tree's leaf items in blas_items (values are triangle indices relative to tri_first) */
+    uint32_t item_count;
+    uint32_t nrm_first;  /* first record in tri_normals or 0xFFFFFFFF */
+    uint32_t uv_first;   /* first record in tri_uvs or 0xFFFFFFFF */
+    uint32_t kd_depth;
+    uint32_t reserved;
+    double pad;
+} PtMesh;
+
+typedef struct PtTriPos { double a[3], b[3], c[3]; } PtTriPos;       /* 72 B, triangle.rs:10-12 */
+typedef struct PtTriNormals { double na[3], nb[3], nc[3]; } PtTriNormals; /* 72 B, triangle.rs:15 */
+typedef struct PtTriUvs { double uva[2], uvb[2], uvc[2]; } PtTriUvs; /* 48 B, triangle.rs:18 */
+
+/* src/material.rs:51-86. texture / normals are indices into textures or -1. 160 bytes. */
+typedef struct PtMaterial {
+    double diffuse[3];
+    double specular[3];
+    double shininess;
+    double reflectivity;
+    double glossy_side_length;
+    double refraction_index;
+    double uv_trans[9]; /* row-major 3x3 */
+    int32_t texture;
+    int32_t normals;
+} PtMaterial;
+
+/* src/light.rs:74-85 (+ Falloff :11-15, Parallelogram :41-46). 128 bytes. */
+typedef struct PtLight {
+    double position[3];
+    double color[3];
+    double falloff[3]; /* c0, c1, c2 */
+    double area_a[3];
+    double area_b[3];
+    double pad;
+} PtLight;
+
+/* RGB8 row-major image in the texel pool (RgbImageBuffer, src/texture.rs:78-80). */
+typedef struct PtTexture {
+    uint32_t width;
+    uint32_t height;
+    uint64_t offset; /* byte offset into the texel pool */
+} PtTexture;
+
+/* Pointer form of a prepared scene: what the Rust glue fills from KDTreeScene. */
+typedef struct PtSceneDesc {
+    double ambient[3];  /* Scene.ambient, src/scene.rs:17 */
+    double tlas_extent; /* extent() of the scene kd root, node.rs:29 */
+    uint32_t tlas_depth;
+    uint32_t n_tlas_nodes;  const PtKdNode* tlas_nodes;
+    uint32_t n_tlas_items;  const uint32_t* tlas_items; /* instance indices */
+    uint32_t n_instances;   const PtInstance* instances; const PtInstanceTrans* instance_trans;
+    uint32_t n_meshes;      const PtMesh* meshes;
+    uint32_t n_blas_nodes;  const PtKdNode* blas_nodes;
+    uint32_t n_blas_items;  const uint32_t* blas_items;
+    uint32_t n_triangles;   const PtTriPos* tri_pos;
+    uint32_t n_tri_normals; const PtTriNormals* tri_normals;
+    uint32_t n_tri_uvs;     const PtTriUvs* tri_uvs;
+    uint32_t n_materials;   const PtMaterial* materials;
+    uint32_t n_lights;      const PtLight* lights;
+    uint32_t n_textures;    const PtTexture* textures;
+    uint64_t n_texel_bytes; const uint8_t* texels;
+} PtSceneDesc;
+
+/* Pointer-free form of the same thing: one contiguous blob, every section
+ * 128-byte aligned, offsets from the start of the blob.  This is what crosses
+ * NVLink verbatim when the scene is broadcast to the other ranks. */
+#define PT_BLOB_MAGIC 0x43535450u /* "PTSC" */
+#define PT_BLOB_VERSION 2u
+
+typedef struct PtBlobHeader {
+    uint32_t magic;
+    uint32_t version;
+    uint64_t total_bytes;
+    double ambient[3];
+    double tlas_extent;
+    uint32_t tlas_depth;
+    uint32_t blas_max_depth;
+    uint32_t n_tlas_nodes, n_tlas_items, n_instances, n_meshes;
+    uint32_t n_blas_nodes, n_blas_items, n_triangles, n_tri_normals;
+    uint32_t n_tri_uvs, n_materials, n_lights, n_textures;
+    uint64_t n_texel_bytes;
+    uint64_t off_tlas_nodes, off_tlas_items, off_instances, off_instance_trans;
+    uint64_t off_meshes, off_blas_nodes, off_blas_items, off_tri_pos;
+    uint64_t off_tri_normals, off_tri_uvs, off_materials, off_lights;
+    uint64_t off_textures, off_texels;
+} PtBlobHeader;
+
+/* Prepared camera, src/camera.rs:17-32 (Camera::new stays on the host). */
+typedef struct PtCamera {
+    double eye[3];
+    double view_to_world[16]; /* row-major Mat4 */
+    double fov_factor;
+    double aspect_ratio;
+    double width;
+    double height;
+} PtCamera;
+
+/* Deterministic replacement for thread_rng() (render.rs:38, material.rs:106):
+ *   FIXED : every draw is 0.5  -> pixel-centre rays, area lights sampled at
+ *           their centre, glossy offset exactly 0.
+ *   HASH  : draw(pixel, sample, path, dim) =
+ *             (mix(mix(seed ^ (pixel * 0x9E3779B97F4A7C15 + sample)) + (path << 8 | dim)) >> 11) * 2^-53
+ *           with mix = splitmix64 finaliser
+ *             z ^= z >> 30; z *= 0xBF58476D1CE4E5B9; z ^= z >> 27; z *= 0x94D049BB133111EB; z ^= z >> 31.
+ *   pixel = y * width + x (global, independent of slices, tiles and ranks),
+ *   path  = 1 for the primary ray; child = parent << 1 | (0 reflected, 1 refracted),
+ *   dim   = 0,1 pixel jitter (render.rs:39, root only); then per shaded node
+ *           2+2l, 3+2l for light l (light.rs:66-67) and 2+2L, 3+2L for the
+ *           glossy square (material.rs:235-236). */
+#define PT_RNG_FIXED 0u
+#define PT_RNG_HASH 1u
+
+#define PT_BG_PER_PIXEL 0u /* background[W*H*3], row-major: background.at(x/w, y/h) at integer x,y (render.rs:31-34) */
+#define PT_BG_PER_ROW 1u   /* background[H*3]: the closure depends on v only */
+#define PT_BG_CONSTANT 2u  /* background[3] */
+
+typedef struct PtRenderParams {
+    uint32_t width, height;   /* full image */
+    uint32_t x1, y1, x2, y2;  /* inclusive slice, render.rs:116-119 */
+    uint32_t samples;         /* SAMPLES, render.rs:107-113 */
+    uint32_t rng_mode;
+    uint64_t seed;
+    uint32_t bg_mode;
+    uint32_t max_depth;       /* 0 -> PT_MAX_RECURSION_DEPTH */
+    /* multi-GPU tile ownership: tile k (row-major over the image's tile grid)
+     * is rendered iff k % world == rank.  world = 0 or 1 -> everything. */
+    uint32_t tile_w, tile_h;  /* 0 -> 32 */
+    uint32_t rank, world;
+    /* tuning (0 = defaults) */
+    uint64_t max_batch_paths;
+    uint64_t node_pool_capacity;
+    uint32_t flags;           /* PT_RENDER_* */
+    uint32_t reserved;
+} PtRenderParams;
+
+#define PT_RENDER_COUNTERS 1u  /* run the counting variant of the traversal kernels (fills PtStats work counters) */
+#define PT_RENDER_LINEAR_TLAS 2u /* ignore the scene kd-tree: FlatScene linear scan, flat_scene.rs:71-99 + ray.rs:87-99 */
+
+typedef struct PtStats {
+    /* rays = every ray_cast issued against the scene root */
+    uint64_t rays_primary, rays_shadow, rays_reflect, rays_refract;
+    uint64_t rays_depth_cut;    /* depth-11 rays the reference casts but whose result is always bg (elided) */
+    /* work counters (only with PT_RENDER_COUNTERS) */
+    uint64_t kd_splits, instance_tests, triangle_tests, bbox_gates;
+    uint64_t shaded_hits, texel_lookups;
+    uint64_t nodes_total;       /* ray-tree nodes allocated */
+    uint32_t batches, retries;
+    uint32_t max_level;         /* deepest recursion level that held a ray */
+    uint32_t device_error_bits;
+    uint32_t kernel_launches;   /* launches of this library's kernels inside the call */
+    uint32_t reserved;
+    double device_ms;           /* CUDA-event time of the kernels of the call */
+    double h2d_ms, d2h_ms;
+    uint64_t h2d_bytes, d2h_bytes;
+} PtStats;
+
+typedef struct PtScene PtScene; /* opaque, library-owned */
+typedef struct PtFrame PtFrame; /* opaque: device buffers of one render target */
+
+/* report_finished_pixels(n), src/reporter.rs:12 — called on the calling thread between batches */
+typedef void (*PtProgressFn)(void* user, uint64_t finished_pixels);
+
+/* ---- library ---- */
+int pt_init(int device);                 /* cudaSetDevice + stream; device < 0 -> current */
+void pt_shutdown(void);
+const char* pt_last_error(void);
+const char* pt_error_string(int code);   /* the reference's panic text for PT_ERR_* */
+int pt_device_count(void);
+
+/* ---- scene (replaces nothing in the reference: it is the glue's output) ---- */
+/* bytes needed to pack desc; pack it. Pure host code, works without a GPU. */
+uint64_t pt_scene_blob_size(const PtSceneDesc* desc);
+int pt_scene_pack(const PtSceneDesc* desc, void* blob_out, uint64_t capacity);
+/* validate a blob and view it as a desc (pointers into the blob). Host only. */
+int pt_scene_unpack(const void* blob, uint64_t bytes, PtSceneDesc* desc_out);
+
+int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out);        /* host blob -> device */
+int pt_scene_upload_device(const void* d_blob, uint64_t bytes, PtScene** out); /* blob already in HBM (after the NCCL broadcast) */
+void pt_scene_free(PtScene* scene);
+
+/* ---- render: replaces ImageSliceMut::render's pixel loop, render.rs:127-150 ---- */
+/* One blocking call with HOST buffers (the call the Rust shim makes).
+ * rgb_inout: W*H*3, only slice pixels owned by (rank, world) are written.
+ * hit_id_out (nullable): W*H*2 u32 = (instance, sub id) of the sample-0 primary ray; instance 0xFFFFFFFF = miss.
+ * hit_t_out (nullable): W*H f64 ray parameter of that hit (inf on miss). */
+int pt_render(PtScene* scene, const PtCamera* camera, const PtRenderParams* params,
+              const double* background, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out,
+              PtProgressFn progress, void* user, PtStats* stats);
+
+/* Ray::color(scene, background, 0) (src/ray.rs:139-148) for n explicit world-space rays — the
+ * per-ray evaluation of the reference's own mesh_equivalence test (src/kdtree/kdmesh.rs:155-163).
+ * origins/dirs: n*3; background3: the constant background colour; ray i draws its random numbers
+ * as pixel i, sample 0.  Outputs (nullable): color_out n*3 linear f64 (no gamma), hit_id_out n*2,
+ * hit_t_out n.  flags: PT_RENDER_COUNTERS. */
+int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const double* dirs, const double* background3,
+                  uint32_t rng_mode, uint64_t seed, uint32_t max_depth, uint32_t flags, double* color_out,
+                  uint32_t* hit_id_out, double* hit_t_out, PtStats* stats);
+
+/* The same path with device-resident inputs/outputs, for callers that keep the
+ * frame in HBM (multi-GPU gather, benchmarks). */
+int pt_frame_create(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, PtFrame** out);
+void pt_frame_free(PtFrame* frame);
+uint64_t pt_frame_owned_pixels(const PtFrame* frame);   /* pixels this rank renders */
+uint64_t pt_frame_background_doubles(const PtFrame* frame); /* doubles expected in the background buffer */
+int pt_frame_set_background(PtFrame* frame, const double* background);          /* host -> device */
+int pt_frame_set_background_device(PtFrame* frame, const double* d_background); /* device -> device */
+/* render every owned pixel; outputs stay in HBM. stream: cudaStream_t or NULL for the library stream. */
+int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* user, PtStats* stats);
+/* device pointers to the compact outputs, owned-pixel order (see pt_frame_pixel_index) */
+const uint8_t* pt_frame_rgb_device(const PtFrame* frame);     /* owned_pixels * 3 */
+const uint32_t* pt_frame_hit_id_device(const PtFrame* frame); /* owned_pixels * 2 */
+const double* pt_frame_hit_t_device(const PtFrame* frame);    /* owned_pixels */
+/* global pixel index (y * W + x) of every owned pixel, in output order (host array of owned_pixels u32) */
+int pt_frame_pixel_index(const PtFrame* frame, uint32_t* index_out);
+/* copy the compact outputs back and scatter them into full-size host images (any may be NULL) */
+int pt_frame_read(PtFrame* frame, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtStats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PORTRAYER_GPU_H */

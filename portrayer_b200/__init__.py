@@ -1,0 +1,15 @@
+"""portrayer_b200 — B200-native implementation of portrayer's per-pixel render loop.
+
+Only what the hot path needs lives here:
+
+* ``csrc/``  hand-written CUDA kernels for sm_100a + the C ABI (``include/portrayer_gpu.h``)
+* ``host/``  C++ mirror of the reference's scene API (stays Rust in the target design)
+* this Python layer: ctypes bindings, the ``Image.render`` entry point, multi-GPU plumbing.
+"""
+from ._ffi import (PT_RENDER_COUNTERS, PT_RNG_FIXED, PT_RNG_HASH, PortrayerError, PtCamera, PtRenderParams,  # noqa: F401
+                   PtStats)
+from .render import DeviceScene, Frame, Image, make_params, samples_from_env  # noqa: F401
+from .scene import Scene, example_names  # noqa: F401
+
+__all__ = ["Scene", "example_names", "Image", "DeviceScene", "Frame", "make_params", "samples_from_env", "PtStats",
+           "PtCamera", "PtRenderParams", "PortrayerError", "PT_RNG_FIXED", "PT_RNG_HASH", "PT_RENDER_COUNTERS"]

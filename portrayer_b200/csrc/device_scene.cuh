@@ -1,0 +1,86 @@
+// Device view of an uploaded scene blob and of one batch's ray-tree node pool.
+#pragma once
+#include <cstdint>
+
+#include "device_math.cuh"
+#include "portrayer_gpu.h"
+
+namespace ptd {
+
+// Pointers into the blob as it lies in HBM (the blob is uploaded verbatim, so
+// an NCCL-broadcast copy is usable as is).
+struct DScene {
+    const PtKdNode* tlas_nodes;
+    const uint32_t* tlas_items;
+    const PtInstance* instances;
+    const PtInstanceTrans* instance_trans;
+    const PtMesh* meshes;
+    const PtKdNode* blas_nodes;
+    const uint32_t* blas_items;
+    const PtTriPos* tri_pos;
+    const PtTriNormals* tri_normals;
+    const PtTriUvs* tri_uvs;
+    const PtMaterial* materials;
+    const PtLight* lights;
+    const PtTexture* textures;
+    const uint8_t* texels;
+    double ambient[3];
+    double tlas_extent;
+    uint32_t n_lights;
+    uint32_t n_instances;
+    uint32_t n_tlas_nodes;
+    uint32_t n_tlas_items;
+};
+
+// child / node sentinels
+constexpr uint32_t kChildNone = 0xFFFFFFFFu;  // no such child
+constexpr uint32_t kChildBg = 0xFFFFFFFEu;    // child's colour is the pixel background (depth cut-off, material.rs:102-104)
+
+// how a node combines its children (material.rs:280,307-309,315)
+constexpr uint8_t kModeLeaf = 0;        // colour = local
+constexpr uint8_t kModeReflect = 1;     // colour = local + refl * C(child0)            (mirror, and total internal reflection)
+constexpr uint8_t kModeDielectric = 2;  // colour = local + refl * (F*C(child0) + (1-F)*C(child1))
+
+// One batch's ray tree, structure-of-arrays, `capacity` nodes.  Level d of the
+// recursion occupies the contiguous index range [level_start[d], level_start[d+1]);
+// level 0 is the batch's primary rays, node index == path index.
+struct NodePool {
+    double *ox, *oy, *oz, *dx, *dy, *dz;  // ray (world space; direction not necessarily unit, material.rs:238-242)
+    double* t;                            // closest hit parameter
+    uint32_t* inst;                       // flat instance index or kNone
+    uint32_t* sub;                        // triangle / face / part id
+    uint32_t* root;                       // path index (-> pixel, sample)
+    uint32_t* pathid;                     // 1 for the primary ray; child = parent << 1 | (0 reflected, 1 refracted)
+    double *cr, *cg, *cb;                 // local colour (ambient + unshadowed lights), later the subtree colour of roots
+    double* refl;                         // material.reflectivity
+    double* fres;                         // Schlick reflectivity of dielectrics
+    uint32_t *child0, *child1;
+    uint8_t* mode;
+    uint8_t* occl;                        // [light][capacity]: 1 = the shadow ray of that light found an occluder
+    uint32_t capacity;
+};
+
+// device-side control block of a batch
+struct BatchCtl {
+    uint32_t level_start[16];  // PT_MAX_RECURSION_DEPTH + 2 used
+    uint32_t pool_count;       // bump allocator of the node pool
+    uint32_t error_bits;       // PT_DEVERR_*
+    uint32_t blocks_done[16];  // per level "last block" tickets of the shade kernel
+    unsigned long long rays_shadow, rays_reflect, rays_refract, rays_depth_cut, shaded_hits, texel_lookups;
+    unsigned long long kd_splits, instance_tests, triangle_tests, bbox_gates;
+};
+
+// per-frame constants
+struct FrameParams {
+    PtCamera cam;
+    const uint32_t* pixel_index;  // owned slot -> global pixel (y*W+x)
+    const double* background;
+    uint32_t bg_mode;
+    uint32_t width, height;
+    uint32_t samples;
+    uint32_t rng_mode;
+    uint64_t seed;
+    uint32_t max_depth;
+};
+
+}  // namespace ptd

@@ -1,0 +1,600 @@
+// The wavefront pipeline that replaces the rayon pixel loop of
+// src/render.rs:127-150.  One batch of paths is a forest of ray trees stored
+// level by level in a node pool (device_scene.cuh):
+//
+//   camera_kernel        render.rs:36-40 + camera.rs:48-84     primary rays -> level 0
+//   per level d = 0..10:
+//     extend_kernel      ray.rs:140-141                        closest hit of every ray of the level
+//     shadow_kernel      material.rs:150-179                   one any-hit walk per (hit, light)
+//     shade_kernel       material.rs:91-320                    local colour; children appended to level d+1
+//   tree_eval_kernel     material.rs:280,307-309,315           bottom-up colour of each path, reference order
+//   resolve_kernel       render.rs:43-50,143-147               sum over samples, gamma, clamp, truncate to u8
+//
+// No atomics touch colours: every node's colour is computed by one thread in
+// the reference's own expression order, so the result is deterministic and
+// independent of batch size, tile ownership and GPU count.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "shade.cuh"
+#include "traverse.cuh"
+
+namespace ptd {
+
+namespace {
+
+constexpr int kBlock = 128;
+
+PT_D void background_of(const FrameParams& fp, uint32_t pixel, double* bg) {
+    const double* src = fp.bg_mode == PT_BG_PER_PIXEL ? fp.background + (size_t)pixel * 3
+                        : fp.bg_mode == PT_BG_PER_ROW ? fp.background + (size_t)(pixel / fp.width) * 3
+                                                      : fp.background;
+    bg[0] = __ldg(src);
+    bg[1] = __ldg(src + 1);
+    bg[2] = __ldg(src + 2);
+}
+
+// warp-aggregated add of per-thread work counters into the batch control block
+PT_D void flush_counters(BatchCtl* ctl, const WorkCounters& wc) {
+    unsigned long long v[4] = {wc.kd_splits, wc.instance_tests, wc.triangle_tests, wc.bbox_gates};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xFFFFFFFFu, v[k], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (v[0]) atomicAdd(&ctl->kd_splits, v[0]);
+        if (v[1]) atomicAdd(&ctl->instance_tests, v[1]);
+        if (v[2]) atomicAdd(&ctl->triangle_tests, v[2]);
+        if (v[3]) atomicAdd(&ctl->bbox_gates, v[3]);
+    }
+}
+
+// ------------------------------------------------------------------ camera
+// path p of the batch = (owned pixel slot, sample); Camera::ray_at, camera.rs:48-84
+__global__ void __launch_bounds__(kBlock) camera_kernel(FrameParams fp, NodePool pool, uint32_t first_slot, uint32_t n_paths) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_paths) return;
+    const uint32_t slot = first_slot + p / fp.samples;
+    const uint32_t sample = p % fp.samples;
+    const uint32_t pixel = __ldg(fp.pixel_index + slot);
+    const uint32_t px = pixel % fp.width, py = pixel / fp.width;
+    // Choose a random point in the pixel square, render.rs:38-39
+    const double x = (double)px + draw(fp.rng_mode, fp.seed, pixel, sample, 1, 0);
+    const double y = (double)py + draw(fp.rng_mode, fp.seed, pixel, sample, 1, 1);
+
+    const PtCamera& cam = fp.cam;
+    const double pixel_ndc_y = y / cam.height;
+    const double pixel_view_y = (1.0 - 2.0 * pixel_ndc_y) * cam.fov_factor;
+    const double pixel_ndc_x = x / cam.width;
+    const double pixel_view_x = (2.0 * pixel_ndc_x - 1.0) * cam.aspect_ratio * cam.fov_factor;
+    const V3 pixel_view = v3(pixel_view_x, pixel_view_y, -1.0);
+    const V3 pixel_world = xf_point(cam.view_to_world, pixel_view);
+    const V3 eye = v3(cam.eye[0], cam.eye[1], cam.eye[2]);
+    const V3 dir = normalized(pixel_world - eye);
+
+    pool.ox[p] = eye.x; pool.oy[p] = eye.y; pool.oz[p] = eye.z;
+    pool.dx[p] = dir.x; pool.dy[p] = dir.y; pool.dz[p] = dir.z;
+    pool.root[p] = p;
+    pool.pathid[p] = 1u;
+}
+
+// explicit rays instead of camera rays (pt_trace_rays): ray i is "pixel" i, sample 0
+__global__ void __launch_bounds__(kBlock) load_rays_kernel(const double* __restrict__ origins, const double* __restrict__ dirs,
+                                                         NodePool pool, uint32_t first, uint32_t n_paths) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_paths) return;
+    const size_t i = (size_t)(first + p) * 3;
+    pool.ox[p] = origins[i]; pool.oy[p] = origins[i + 1]; pool.oz[p] = origins[i + 2];
+    pool.dx[p] = dirs[i]; pool.dy[p] = dirs[i + 1]; pool.dz[p] = dirs[i + 2];
+    pool.root[p] = p;
+    pool.pathid[p] = 1u;
+}
+
+// ------------------------------------------------------------------ extend (closest hit)
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) extend_kernel(DScene sc, NodePool pool, BatchCtl* ctl, int level) {
+    const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
+    KdStack tlas_stack, blas_stack;
+    WorkCounters wc;
+    uint32_t err = 0;
+    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+        const V3 o = v3(pool.ox[i], pool.oy[i], pool.oz[i]);
+        const V3 d = v3(pool.dx[i], pool.dy[i], pool.dz[i]);
+        Hit hit{(double)INFINITY, kNone, 0};
+        const bool found = scene_cast<false>(sc, o, d, hit, tlas_stack, blas_stack, err, wc);
+        pool.t[i] = found ? hit.t : (double)INFINITY;
+        pool.inst[i] = found ? hit.inst : kNone;
+        pool.sub[i] = found ? hit.sub : 0u;
+    }
+    if (err) atomicOr(&ctl->error_bits, err);
+    if (COUNT) flush_counters(ctl, wc);
+}
+
+// ------------------------------------------------------------------ shadow (any hit), light-major
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) shadow_kernel(DScene sc, FrameParams fp, NodePool pool, BatchCtl* ctl, int level,
+                                                       uint32_t first_slot) {
+    const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
+    const uint32_t n = end - begin;
+    const unsigned long long total = (unsigned long long)n * sc.n_lights;
+    KdStack tlas_stack, blas_stack;
+    WorkCounters wc;
+    uint32_t err = 0;
+    unsigned long long cast = 0;
+    for (unsigned long long j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t l = (uint32_t)(j / n);
+        const uint32_t i = begin + (uint32_t)(j % n);
+        const uint32_t inst = pool.inst[i];
+        if (inst == kNone) continue;
+        const V3 o = v3(pool.ox[i], pool.oy[i], pool.oz[i]);
+        const V3 d = v3(pool.dx[i], pool.dy[i], pool.dz[i]);
+        const V3 hit_point = world_hit_point(sc, inst, o, d, pool.t[i], nullptr, nullptr, nullptr);
+        const uint32_t root = pool.root[i];
+        const uint32_t pixel = fp.pixel_index ? __ldg(fp.pixel_index + first_slot + root / fp.samples) : first_slot + root;
+        const uint32_t sample = root % fp.samples;
+        const V3 light_pos = light_sample_position(sc.lights + l, l, fp.rng_mode, fp.seed, pixel, sample, pool.pathid[i]);
+        // material.rs:156-179
+        const V3 hit_to_light = light_pos - hit_point;
+        const double light_dist = magnitude(hit_to_light);
+        const V3 light_dir = hit_to_light / light_dist;
+        Hit hit{(double)INFINITY, kNone, 0};
+        const bool occluded = scene_cast<true>(sc, hit_point, light_dir, hit, tlas_stack, blas_stack, err, wc);
+        pool.occl[(size_t)l * pool.capacity + i] = occluded ? 1 : 0;
+        ++cast;
+    }
+    if (err) atomicOr(&ctl->error_bits, err);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cast += __shfl_down_sync(0xFFFFFFFFu, cast, off);
+    if ((threadIdx.x & 31) == 0 && cast) atomicAdd(&ctl->rays_shadow, cast);
+    if (COUNT) flush_counters(ctl, wc);
+}
+
+// ------------------------------------------------------------------ shade
+// Allocate one node per lane that wants one: one atomicAdd per warp
+// (__ballot_sync/__popc), lanes get consecutive slots.
+PT_D uint32_t warp_alloc(BatchCtl* ctl, bool want) {
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
+    if (mask == 0) return kNone;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&ctl->pool_count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return want ? base + (uint32_t)__popc(mask & ((1u << lane) - 1u)) : kNone;
+}
+
+__global__ void __launch_bounds__(kBlock) shade_kernel(DScene sc, FrameParams fp, NodePool pool, BatchCtl* ctl, int level,
+                                                      uint32_t first_slot) {
+    const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
+    const uint32_t n = end - begin;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (n + stride - 1) / stride;  // every lane runs the same number of rounds (warp_alloc is collective)
+    uint32_t err = 0;
+    unsigned long long n_shaded = 0, n_reflect = 0, n_refract = 0, n_cut = 0, n_texel = 0;
+
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t i = begin + r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = i < end;
+        bool want0 = false, want1 = false;  // children to trace
+        V3 hit_point = v3(0, 0, 0), dir0 = v3(0, 0, 0), dir1 = v3(0, 0, 0);
+        uint32_t root = 0, pathid = 0;
+
+        if (active) {
+            root = pool.root[i];
+            pathid = pool.pathid[i];
+            const uint32_t pixel = fp.pixel_index ? __ldg(fp.pixel_index + first_slot + root / fp.samples) : first_slot + root;
+            const uint32_t sample = root % fp.samples;
+            const uint32_t inst = pool.inst[i];
+            double color[3];
+            uint8_t mode = kModeLeaf;
+            uint32_t c0 = kChildNone, c1 = kChildNone;
+            double refl = 0.0, fres = 0.0;
+
+            if (inst == kNone) {
+                background_of(fp, pixel, color);  // ray.rs:146
+            } else {
+                ++n_shaded;
+                const V3 o = v3(pool.ox[i], pool.oy[i], pool.oz[i]);
+                const V3 ray_dir = v3(pool.dx[i], pool.dy[i], pool.dz[i]);
+                const PtMaterial* mat = sc.materials + __ldg(&sc.instances[inst].material);
+                const int tex_id = __ldg(&mat->texture), nrm_id = __ldg(&mat->normals);
+                SurfaceHit sh;
+                reconstruct_hit(sc, inst, pool.sub[i], o, ray_dir, pool.t[i], tex_id >= 0 || nrm_id >= 0, sh);
+                hit_point = sh.hit_point;
+                const V3 view = -ray_dir;
+
+                // uv' = uv_trans * (u, v, 1), material.rs:114-117
+                double tu = 0.0, tv = 0.0;
+                if (sh.has_uv) {
+                    const double* m = mat->uv_trans;
+                    tu = __ldg(m + 0) * sh.u + __ldg(m + 1) * sh.v + __ldg(m + 2) * 1.0;
+                    tv = __ldg(m + 3) * sh.u + __ldg(m + 4) * sh.v + __ldg(m + 5) * 1.0;
+                }
+                V3 normal;
+                bool ok = true;
+                if (nrm_id < 0) {
+                    normal = normalized(sh.normal);
+                } else if (sh.has_uv && sh.has_nmt) {
+                    double c[3];
+                    texture_at(sc, nrm_id, tu, tv, c);
+                    ++n_texel;
+                    // NormalMap::normal_at: (nx, ny, nz) -> (nx, -nz, -ny), texture.rs:203-220
+                    const V3 norm = v3(2.0 * c[0] - 1.0, 2.0 * c[1] - 1.0, -(2.0 * c[2] - 1.0));
+                    const V3 tn = normalized(v3(norm.x, -norm.z, -norm.y));
+                    const double* m = sh.nmt;
+                    normal = v3(m[0] * tn.x + m[1] * tn.y + m[2] * tn.z, m[3] * tn.x + m[4] * tn.y + m[5] * tn.z,
+                                m[6] * tn.x + m[7] * tn.y + m[8] * tn.z);
+                } else {
+                    err |= PT_DEVERR_NORMALMAP;  // material.rs:133
+                    normal = v3(0, 0, 0);
+                    ok = false;
+                }
+                double kd[3] = {0, 0, 0};
+                if (tex_id < 0) {
+                    kd[0] = __ldg(&mat->diffuse[0]); kd[1] = __ldg(&mat->diffuse[1]); kd[2] = __ldg(&mat->diffuse[2]);
+                } else if (sh.has_uv) {
+                    texture_at(sc, tex_id, tu, tv, kd);
+                    ++n_texel;
+                    kd[0] = pow(kd[0], PT_GAMMA); kd[1] = pow(kd[1], PT_GAMMA); kd[2] = pow(kd[2], PT_GAMMA);  // texture.rs:166
+                } else {
+                    err |= PT_DEVERR_TEXTURE;  // material.rs:141
+                    ok = false;
+                }
+
+                color[0] = sc.ambient[0] * kd[0]; color[1] = sc.ambient[1] * kd[1]; color[2] = sc.ambient[2] * kd[2];
+                if (ok) {
+                    const double spec[3] = {__ldg(&mat->specular[0]), __ldg(&mat->specular[1]), __ldg(&mat->specular[2])};
+                    const bool has_spec = spec[0] > kEps || spec[1] > kEps || spec[2] > kEps;
+                    const double shininess = __ldg(&mat->shininess);
+                    for (uint32_t l = 0; l < sc.n_lights; ++l) {  // material.rs:149-212
+                        if (pool.occl[(size_t)l * pool.capacity + i]) continue;
+                        const PtLight* light = sc.lights + l;
+                        const V3 light_pos = light_sample_position(light, l, fp.rng_mode, fp.seed, pixel, sample, pathid);
+                        const V3 hit_to_light = light_pos - hit_point;
+                        const double light_dist = magnitude(hit_to_light);
+                        const V3 light_dir = hit_to_light / light_dist;
+                        const double f0 = __ldg(&light->falloff[0]), f1 = __ldg(&light->falloff[1]), f2 = __ldg(&light->falloff[2]);
+                        const double attenuation = f0 + f1 * light_dist + f2 * light_dist * light_dist;
+                        const double lc[3] = {__ldg(&light->color[0]), __ldg(&light->color[1]), __ldg(&light->color[2])};
+                        const double normal_light = fmax(dot(normal, light_dir), 0.0);
+                        double specular[3] = {0.0, 0.0, 0.0};
+                        if (has_spec) {
+                            const V3 half = normalized(view + light_dir);
+                            const double normal_half_shiny = pow(fmax(dot(normal, half), 0.0), 4.0 * shininess);
+                            specular[0] = spec[0] * lc[0] * normal_half_shiny;
+                            specular[1] = spec[1] * lc[1] * normal_half_shiny;
+                            specular[2] = spec[2] * lc[2] * normal_half_shiny;
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const double diffuse = kd[ch] * lc[ch] * normal_light;
+                            color[ch] += (diffuse + specular[ch]) / attenuation;
+                        }
+                    }
+
+                    refl = __ldg(&mat->reflectivity);
+                    if (refl > 0.0) {  // material.rs:216-317
+                        V3 reflect_dir = ray_dir - (normal * 2.0) * dot(ray_dir, normal);
+                        const double g = __ldg(&mat->glossy_side_length);
+                        if (g > 0.0) {  // material.rs:220-239; the result is NOT renormalised
+                            const V3 offset_vector = (fabs(reflect_dir.x) < kEps && fabs(reflect_dir.y) < kEps)
+                                                         ? reflect_dir + v3(0.0, 0.1, 0.0)
+                                                         : reflect_dir + v3(0.0, 0.0, 0.1);
+                            const V3 u_basis = cross(reflect_dir, offset_vector);
+                            const V3 v_basis = cross(reflect_dir, u_basis);
+                            const double u_coord = -g / 2.0 + draw(fp.rng_mode, fp.seed, pixel, sample, pathid, 2 + 2 * sc.n_lights) * g;
+                            const double v_coord = -g / 2.0 + draw(fp.rng_mode, fp.seed, pixel, sample, pathid, 3 + 2 * sc.n_lights) * g;
+                            reflect_dir = reflect_dir + (u_basis * u_coord + v_basis * v_coord);
+                        }
+                        dir0 = reflect_dir;
+                        want0 = true;
+                        mode = kModeReflect;
+                        const double ior = __ldg(&mat->refraction_index);
+                        if (ior > 0.0) {
+                            V3 refract_dir;
+                            double cos_incident = 0.0;
+                            bool have = false;
+                            if (dot(ray_dir, normal) < 0.0) {
+                                if (refracted_direction(ray_dir, normal, ior, refract_dir)) {
+                                    cos_incident = dot(-ray_dir, normal);
+                                    have = true;
+                                } else {
+                                    err |= PT_DEVERR_TIR;  // material.rs:258
+                                }
+                            } else if (refracted_direction(ray_dir, -normal, 1.0 / ior, refract_dir)) {
+                                cos_incident = dot(refract_dir, normal);
+                                have = true;
+                            }  // else: total internal reflection -> reflect-only combine (material.rs:277-284)
+                            if (have) {
+                                double r0 = (ior - 1.0) * (ior - 1.0);
+                                r0 = r0 / ((ior + 1.0) * (ior + 1.0));
+                                const double base = 1.0 - cos_incident;
+                                double p4 = base * base;  // powi(5) = base * (base^2)^2
+                                p4 = p4 * p4;
+                                fres = r0 + (1.0 - r0) * (base * p4);
+                                dir1 = refract_dir;
+                                want1 = true;
+                                mode = kModeDielectric;
+                            }
+                        }
+                    }
+                }
+            }
+
+            // depth cut-off: a child at depth > max_depth is bg whatever it hits (material.rs:102-104)
+            if ((uint32_t)level + 1 > fp.max_depth) {
+                if (want0) { c0 = kChildBg; ++n_cut; want0 = false; }
+                if (want1) { c1 = kChildBg; ++n_cut; want1 = false; }
+            }
+            pool.cr[i] = color[0]; pool.cg[i] = color[1]; pool.cb[i] = color[2];
+            pool.mode[i] = mode;
+            pool.refl[i] = refl;
+            pool.fres[i] = fres;
+            pool.child0[i] = c0;
+            pool.child1[i] = c1;
+        }
+
+        // children: reflected ray first, then refracted (material.rs:243 before :303)
+        const uint32_t n0 = warp_alloc(ctl, want0);
+        const uint32_t n1 = warp_alloc(ctl, want1);
+        if (want0) {
+            if (n0 < pool.capacity) {
+                pool.ox[n0] = hit_point.x; pool.oy[n0] = hit_point.y; pool.oz[n0] = hit_point.z;
+                pool.dx[n0] = dir0.x; pool.dy[n0] = dir0.y; pool.dz[n0] = dir0.z;
+                pool.root[n0] = root;
+                pool.pathid[n0] = pathid << 1;
+                pool.child0[i] = n0;
+                ++n_reflect;
+            } else {
+                err |= PT_DEVERR_OVERFLOW;
+                pool.child0[i] = kChildBg;
+            }
+        }
+        if (want1) {
+            if (n1 < pool.capacity) {
+                pool.ox[n1] = hit_point.x; pool.oy[n1] = hit_point.y; pool.oz[n1] = hit_point.z;
+                pool.dx[n1] = dir1.x; pool.dy[n1] = dir1.y; pool.dz[n1] = dir1.z;
+                pool.root[n1] = root;
+                pool.pathid[n1] = (pathid << 1) | 1u;
+                pool.child1[i] = n1;
+                ++n_refract;
+            } else {
+                err |= PT_DEVERR_OVERFLOW;
+                pool.child1[i] = kChildBg;
+            }
+        }
+    }
+
+    if (err) atomicOr(&ctl->error_bits, err);
+    unsigned long long v[5] = {n_shaded, n_reflect, n_refract, n_cut, n_texel};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xFFFFFFFFu, v[k], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (v[0]) atomicAdd(&ctl->shaded_hits, v[0]);
+        if (v[1]) atomicAdd(&ctl->rays_reflect, v[1]);
+        if (v[2]) atomicAdd(&ctl->rays_refract, v[2]);
+        if (v[3]) atomicAdd(&ctl->rays_depth_cut, v[3]);
+        if (v[4]) atomicAdd(&ctl->texel_lookups, v[4]);
+    }
+
+    // the last block to finish publishes where the next level ends
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t ticket = atomicAdd(&ctl->blocks_done[level], 1u);
+        if (ticket == gridDim.x - 1) {
+            const uint32_t count = atomicAdd(&ctl->pool_count, 0u);
+            ctl->level_start[level + 2] = count < pool.capacity ? count : pool.capacity;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ tree evaluation
+// Colour of one path = post-order walk of its ray tree with the reference's own
+// expressions (material.rs:280,307-309,315); writes the result over the root's local colour.
+__global__ void __launch_bounds__(kBlock) tree_eval_kernel(FrameParams fp, NodePool pool, uint32_t first_slot, uint32_t n_paths) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_paths) return;
+    if (pool.mode[p] == kModeLeaf) return;  // colour already final
+
+    const uint32_t pixel = fp.pixel_index ? __ldg(fp.pixel_index + first_slot + p / fp.samples) : first_slot + p;
+    double bg[3];
+    background_of(fp, pixel, bg);
+
+    constexpr int kMaxFrames = PT_MAX_RECURSION_DEPTH + 2;
+    uint32_t f_node[kMaxFrames];
+    uint8_t f_stage[kMaxFrames];
+    double f_refl[kMaxFrames][3];  // reflected_color once child0 is done
+    int sp = 0;
+    f_node[0] = p;
+    f_stage[0] = 0;
+    double ret[3] = {0, 0, 0};  // colour returned by the frame that just finished
+    for (;;) {
+        const uint32_t node = f_node[sp];
+        const uint8_t mode = pool.mode[node];
+        const uint8_t stage = f_stage[sp];
+        if (stage == 0) {
+            if (mode == kModeLeaf) {
+                ret[0] = pool.cr[node]; ret[1] = pool.cg[node]; ret[2] = pool.cb[node];
+            } else {
+                const uint32_t c0 = pool.child0[node];
+                f_stage[sp] = 1;
+                if (c0 == kChildBg) {
+                    ret[0] = bg[0]; ret[1] = bg[1]; ret[2] = bg[2];
+                } else {
+                    ++sp;
+                    f_node[sp] = c0;
+                    f_stage[sp] = 0;
+                }
+                continue;
+            }
+        } else if (stage == 1) {  // ret = reflected_color
+            if (mode == kModeReflect) {
+                const double refl = pool.refl[node];
+                ret[0] = pool.cr[node] + refl * ret[0];
+                ret[1] = pool.cg[node] + refl * ret[1];
+                ret[2] = pool.cb[node] + refl * ret[2];
+            } else {
+                f_refl[sp][0] = ret[0]; f_refl[sp][1] = ret[1]; f_refl[sp][2] = ret[2];
+                const uint32_t c1 = pool.child1[node];
+                f_stage[sp] = 2;
+                if (c1 == kChildBg) {
+                    ret[0] = bg[0]; ret[1] = bg[1]; ret[2] = bg[2];
+                } else {
+                    ++sp;
+                    f_node[sp] = c1;
+                    f_stage[sp] = 0;
+                }
+                continue;
+            }
+        } else {  // stage 2: ret = refracted_color, material.rs:292-309
+            const double refl = pool.refl[node];
+            const double reflectivity = pool.fres[node];
+            const double transmittance = 1.0 - reflectivity;
+            const double local[3] = {pool.cr[node], pool.cg[node], pool.cb[node]};
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const double total_color = reflectivity * f_refl[sp][ch] + transmittance * ret[ch];
+                ret[ch] = local[ch] + refl * total_color;
+            }
+        }
+        // frame finished with `ret`
+        if (sp == 0) break;
+        --sp;
+    }
+    pool.cr[p] = ret[0]; pool.cg[p] = ret[1]; pool.cb[p] = ret[2];
+}
+
+// ------------------------------------------------------------------ resolve
+PT_D uint8_t to_u8(double c) {  // Rust `as u8`: truncate, saturate, NaN -> 0. render.rs:143-147
+    const double v = c * 255.0;
+    if (!(v > 0.0)) return 0;
+    if (v >= 255.0) return 255;
+    return (uint8_t)v;
+}
+PT_D double clamp01(double v) {
+    const double lo = v >= 0.0 ? v : 0.0;
+    return lo <= 1.0 ? lo : 1.0;
+}
+
+// one thread per owned pixel of the batch: render.rs:43-50,143-147
+__global__ void __launch_bounds__(kBlock) resolve_kernel(FrameParams fp, NodePool pool, uint32_t first_slot, uint32_t n_slots,
+                                                        uint8_t* __restrict__ rgb, uint32_t* __restrict__ hit_id,
+                                                        double* __restrict__ hit_t) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_slots) return;
+    const uint32_t p0 = k * fp.samples;
+    double total[3] = {0.0, 0.0, 0.0};
+    for (uint32_t s = 0; s < fp.samples; ++s) {
+        total[0] = total[0] + pool.cr[p0 + s];
+        total[1] = total[1] + pool.cg[p0 + s];
+        total[2] = total[2] + pool.cb[p0 + s];
+    }
+    const size_t slot = (size_t)first_slot + k;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        double c = total[ch] / (double)fp.samples;
+        c = pow(c, 1.0 / PT_GAMMA);
+        rgb[slot * 3 + ch] = to_u8(clamp01(c));
+    }
+    hit_id[slot * 2] = pool.inst[p0];
+    hit_id[slot * 2 + 1] = pool.sub[p0];
+    hit_t[slot] = pool.t[p0];
+}
+
+// pt_trace_rays: linear colour of each explicit ray, no gamma
+__global__ void __launch_bounds__(kBlock) export_rays_kernel(NodePool pool, uint32_t first, uint32_t n_paths,
+                                                            double* __restrict__ color, uint32_t* __restrict__ hit_id,
+                                                            double* __restrict__ hit_t) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_paths) return;
+    const size_t i = (size_t)first + p;
+    color[i * 3] = pool.cr[p]; color[i * 3 + 1] = pool.cg[p]; color[i * 3 + 2] = pool.cb[p];
+    hit_id[i * 2] = pool.inst[p];
+    hit_id[i * 2 + 1] = pool.sub[p];
+    hit_t[i] = pool.t[p];
+}
+
+__global__ void begin_batch_kernel(BatchCtl* ctl, uint32_t n_paths) {
+    if (threadIdx.x < 16) {
+        ctl->level_start[threadIdx.x] = threadIdx.x == 0 ? 0u : n_paths;
+        ctl->blocks_done[threadIdx.x] = 0u;
+    }
+    if (threadIdx.x == 0) ctl->pool_count = n_paths;
+}
+
+int g_grid_extend[2] = {0, 0}, g_grid_shadow[2] = {0, 0}, g_grid_shade = 0;
+
+template <class K>
+int persistent_grid(K kernel) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0);
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launch wrappers
+void kernels_init() {
+    g_grid_extend[0] = persistent_grid(extend_kernel<false>);
+    g_grid_extend[1] = persistent_grid(extend_kernel<true>);
+    g_grid_shadow[0] = persistent_grid(shadow_kernel<false>);
+    g_grid_shadow[1] = persistent_grid(shadow_kernel<true>);
+    g_grid_shade = persistent_grid(shade_kernel);
+}
+
+static inline uint32_t blocks_for(uint32_t n) { return (n + kBlock - 1) / kBlock; }
+
+void launch_begin_batch(BatchCtl* ctl, uint32_t n_paths, cudaStream_t st) { begin_batch_kernel<<<1, 32, 0, st>>>(ctl, n_paths); }
+
+void launch_camera(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_paths, cudaStream_t st) {
+    camera_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(fp, pool, first_slot, n_paths);
+}
+void launch_load_rays(const double* origins, const double* dirs, const NodePool& pool, uint32_t first, uint32_t n_paths,
+                      cudaStream_t st) {
+    load_rays_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(origins, dirs, pool, first, n_paths);
+}
+// A level can never hold more rays than `max_items`; the persistent grid is capped to it.
+void launch_extend(const DScene& sc, const NodePool& pool, BatchCtl* ctl, int level, uint32_t max_items, bool count,
+                   cudaStream_t st) {
+    int grid = g_grid_extend[count ? 1 : 0];
+    if ((uint32_t)grid > blocks_for(max_items)) grid = (int)blocks_for(max_items);
+    if (count) extend_kernel<true><<<grid, kBlock, 0, st>>>(sc, pool, ctl, level);
+    else extend_kernel<false><<<grid, kBlock, 0, st>>>(sc, pool, ctl, level);
+}
+void launch_shadow(const DScene& sc, const FrameParams& fp, const NodePool& pool, BatchCtl* ctl, int level,
+                   uint32_t first_slot, uint32_t max_items, bool count, cudaStream_t st) {
+    if (sc.n_lights == 0) return;
+    int grid = g_grid_shadow[count ? 1 : 0];
+    const unsigned long long items = (unsigned long long)max_items * sc.n_lights;
+    const unsigned long long need = (items + kBlock - 1) / kBlock;
+    if ((unsigned long long)grid > need) grid = (int)need;
+    if (count) shadow_kernel<true><<<grid, kBlock, 0, st>>>(sc, fp, pool, ctl, level, first_slot);
+    else shadow_kernel<false><<<grid, kBlock, 0, st>>>(sc, fp, pool, ctl, level, first_slot);
+}
+void launch_shade(const DScene& sc, const FrameParams& fp, const NodePool& pool, BatchCtl* ctl, int level,
+                  uint32_t first_slot, uint32_t max_items, cudaStream_t st) {
+    int grid = g_grid_shade;
+    if ((uint32_t)grid > blocks_for(max_items)) grid = (int)blocks_for(max_items);
+    shade_kernel<<<grid, kBlock, 0, st>>>(sc, fp, pool, ctl, level, first_slot);
+}
+void launch_tree_eval(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_paths, cudaStream_t st) {
+    tree_eval_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(fp, pool, first_slot, n_paths);
+}
+void launch_resolve(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_slots, uint8_t* rgb,
+                    uint32_t* hit_id, double* hit_t, cudaStream_t st) {
+    resolve_kernel<<<blocks_for(n_slots), kBlock, 0, st>>>(fp, pool, first_slot, n_slots, rgb, hit_id, hit_t);
+}
+void launch_export_rays(const NodePool& pool, uint32_t first, uint32_t n_paths, double* color, uint32_t* hit_id,
+                        double* hit_t, cudaStream_t st) {
+    export_rays_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(pool, first, n_paths, color, hit_id, hit_t);
+}
+
+}  // namespace ptd

@@ -1,0 +1,401 @@
+// Ray casting on the device: the reference's kd-tree walk with all of its
+// quirks (SURVEY §8 quirk list 12-14, Appendix A.1/A.2), per-instance object
+// space intersection, and the `t`-only forms of every primitive's ray_hit.
+// Hit attributes (normal, uv, normal-map basis) are NOT computed here: they are
+// pure functions of (instance, sub id, t) and are rebuilt once in the shade
+// kernel for the final hit (Appendix A.3).
+//
+//   KDTreeNode::ray_cast_impl   src/kdtree/node.rs:66-203
+//   [T]::ray_cast / ray_hit     src/ray.rs:50-63,87-99
+//   FlatSceneNode::ray_cast     src/flat_scene.rs:71-99
+//   KDMesh::ray_hit             src/kdtree/kdmesh.rs:62-74
+//   Mesh::ray_hit               src/primitive/mesh.rs:145-168
+//   BoundingBox::test_hit       src/bounding_box.rs:104-116
+//   Sphere/Cube/Plane/Cylinder/Cone/Triangle/InfinitePlane::ray_hit   src/primitive/*.rs
+//   Quadratic::solve            src/math.rs:107-114 -> roots::find_roots_quadratic
+#pragma once
+#include "device_scene.cuh"
+
+namespace ptd {
+
+struct WorkCounters {
+    uint32_t kd_splits = 0, instance_tests = 0, triangle_tests = 0, bbox_gates = 0;
+};
+
+struct Hit {
+    double t;
+    uint32_t inst;
+    uint32_t sub;
+};
+
+// ------------------------------------------------------------------ quadratic
+// roots 0.0.5 find_roots_quadratic: roots ascending, "do not use the smallest divisor"
+PT_D int solve_quadratic(double a2, double a1, double a0, double& x_lo, double& x_hi) {
+    if (a2 == 0.0) {
+        if (a1 == 0.0) {
+            if (a0 == 0.0) { x_lo = 0.0; return 1; }
+            return 0;
+        }
+        x_lo = -a0 / a1;
+        return 1;
+    }
+    const double discriminant = a1 * a1 - 4.0 * a2 * a0;
+    if (discriminant < 0.0) return 0;
+    const double a2x2 = 2.0 * a2;
+    if (discriminant == 0.0) { x_lo = -a1 / a2x2; return 1; }
+    const double sq = sqrt(discriminant);
+    double same_sign, diff_sign;
+    if (a1 < 0.0) { same_sign = -a1 + sq; diff_sign = -a1 - sq; }
+    else { same_sign = -a1 - sq; diff_sign = -a1 + sq; }
+    double x1, x2;
+    if (fabs(same_sign) > fabs(a2x2)) {
+        const double a0x2 = 2.0 * a0;
+        if (fabs(diff_sign) > fabs(a2x2)) { x1 = a0x2 / same_sign; x2 = a0x2 / diff_sign; }
+        else { x1 = a0x2 / same_sign; x2 = same_sign / a2x2; }
+    } else { x1 = diff_sign / a2x2; x2 = same_sign / a2x2; }
+    if (x1 < x2) { x_lo = x1; x_hi = x2; } else { x_lo = x2; x_hi = x1; }
+    return 2;
+}
+// Solutions::find_in_range: the smallest root inside [s, e)
+PT_D bool quadratic_in_range(double a, double b, double c, double s, double e, double& t) {
+    double r0 = 0.0, r1 = 0.0;
+    const int n = solve_quadratic(a, b, c, r0, r1);
+    if (n >= 1 && in_range(s, e, r0)) { t = r0; return true; }
+    if (n == 2 && in_range(s, e, r1)) { t = r1; return true; }
+    return false;
+}
+
+// ------------------------------------------------------------------ analytic primitives (t and sub id only)
+PT_D bool cube_contains(V3 p) {  // cube.rs:22-27
+    const double radius = 0.5 + kEps;
+    return -radius <= p.x && p.x <= radius && -radius <= p.y && p.y <= radius && -radius <= p.z && p.z <= radius;
+}
+
+// t of InfinitePlane::ray_hit for cube face f (infinite_plane.rs:46-79 with the
+// axis-unit normals and on-axis points of cube.rs:46-65; the dot products reduce
+// to one component, the other products are exact zeros)
+PT_D double cube_face_t(int f, V3 o, V3 d) {
+    switch (f) {
+        case 0: return -(o.x - 0.5) / d.x;    // Right  n=+x p=+0.5
+        case 1: return (o.x + 0.5) / (-d.x);  // Left   n=-x p=-0.5
+        case 2: return -(o.y - 0.5) / d.y;    // Top
+        case 3: return (o.y + 0.5) / (-d.y);  // Bottom
+        case 4: return -(o.z - 0.5) / d.z;    // Near
+        default: return (o.z + 0.5) / (-d.z); // Far
+    }
+}
+
+// Cube::ray_hit fold over the 6 faces, cube.rs:67-82. ANY: stop at the first accepted face.
+template <bool ANY>
+PT_D bool cube_t(V3 o, V3 d, double s, double e, double& t_out, uint32_t& face_out) {
+    bool found = false;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const double t = cube_face_t(f, o, d);
+        if (in_range(s, e, t) && cube_contains(ray_at(o, d, t))) {
+            e = t;
+            t_out = t;
+            face_out = (uint32_t)f;
+            found = true;
+            if (ANY) return true;
+        }
+    }
+    return found;
+}
+
+PT_D bool sphere_t(V3 o, V3 d, double s, double e, double& t) {  // sphere.rs:49-56
+    const double a = dot(d, d);
+    const double b = 2.0 * dot(o, d);
+    const double c = dot(o, o) - 1.0;
+    return quadratic_in_range(a, b, c, s, e, t);
+}
+
+PT_D bool plane_t(V3 o, V3 d, double s, double e, double& t_out) {  // plane.rs:35-52, infinite_plane.rs:63-69
+    const double t = -o.y / d.y;
+    if (!in_range(s, e, t)) return false;
+    const V3 p = ray_at(o, d, t);
+    const double radius = 0.5 + kEps;
+    if (!(-radius <= p.x && p.x <= radius && -radius <= p.z && p.z <= radius)) return false;
+    t_out = t;
+    return true;
+}
+
+PT_D bool cyl_cap_t(double height, V3 o, V3 d, double s, double e, double& t_out) {  // cylinder.rs:77-116, cone.rs:116-157
+    const double t = (height - o.y) / d.y;
+    if (!in_range(s, e, t)) return false;
+    const V3 p = ray_at(o, d, t);
+    if ((p.x * p.x + p.z * p.z) > 0.5 * 0.5) return false;
+    t_out = t;
+    return true;
+}
+
+template <bool ANY>
+PT_D bool cylinder_t(V3 o, V3 d, double s, double e, double& t_out, uint32_t& part) {  // cylinder.rs:28-74,118-153
+    bool found = false;
+    {
+        const double a = d.x * d.x + d.z * d.z;
+        const double b = 2.0 * o.x * d.x + 2.0 * o.z * d.z;
+        const double c = o.x * o.x + o.z * o.z - 0.5 * 0.5;
+        double t;
+        if (quadratic_in_range(a, b, c, s, e, t)) {
+            const V3 p = ray_at(o, d, t);
+            if (!(p.y > 0.5 || p.y < -0.5)) { e = t; t_out = t; part = 0; found = true; if (ANY) return true; }
+        }
+    }
+    double t;
+    if (cyl_cap_t(0.5, o, d, s, e, t)) { e = t; t_out = t; part = 1; found = true; if (ANY) return true; }
+    if (cyl_cap_t(-0.5, o, d, s, e, t)) { t_out = t; part = 2; found = true; }
+    return found;
+}
+
+template <bool ANY>
+PT_D bool cone_t(V3 o, V3 d, double s, double e, double& t_out, uint32_t& part) {  // cone.rs:28-113,159-186
+    bool found = false;
+    {
+        const double HEIGHT = 1.0, RADIUS = 0.5;
+        const double h_sqr = HEIGHT * HEIGHT;
+        const double r_sqr = RADIUS * RADIUS;
+        const double a = 4.0 * d.y * d.y * r_sqr - 4.0 * h_sqr * (d.x * d.x + d.z * d.z);
+        const double b = -8.0 * h_sqr * (d.x * o.x + d.z * o.z) - 4.0 * r_sqr * (d.y * HEIGHT - 2.0 * d.y * o.y);
+        const double c = -4.0 * h_sqr * (o.x * o.x + o.z * o.z) + r_sqr * (h_sqr - 4.0 * HEIGHT * o.y + 4.0 * o.y * o.y);
+        double t;
+        if (quadratic_in_range(a, b, c, s, e, t)) {
+            const V3 p = ray_at(o, d, t);
+            if (!(p.y > 0.5 || p.y < -0.5)) { e = t; t_out = t; part = 0; found = true; if (ANY) return true; }
+        }
+    }
+    double t;
+    if (cyl_cap_t(-0.5, o, d, s, e, t)) { t_out = t; part = 1; found = true; }
+    return found;
+}
+
+// Triangle::ray_hit up to the barycentric tests (triangle.rs:38-80)
+struct TriBary {
+    double beta, gamma;
+};
+PT_D bool triangle_t(const PtTriPos* __restrict__ tp, V3 o, V3 dir, double s, double e_, double& t_out, TriBary* bary) {
+    const double* v = reinterpret_cast<const double*>(tp);
+    const V3 A = v3(__ldg(v + 0), __ldg(v + 1), __ldg(v + 2));
+    const V3 B = v3(__ldg(v + 3), __ldg(v + 4), __ldg(v + 5));
+    const V3 C = v3(__ldg(v + 6), __ldg(v + 7), __ldg(v + 8));
+    const V3 ab = A - B, ac = A - C, ao = A - o;
+    const double a = ab.x, b = ab.y, c = ab.z;
+    const double d = ac.x, e = ac.y, f = ac.z;
+    const double g = dir.x, h = dir.y, i = dir.z;
+    const double j = ao.x, k = ao.y, l = ao.z;
+
+    const double ei_hf = e * i - h * f;
+    const double gf_di = g * f - d * i;
+    const double dh_eg = d * h - e * g;
+    const double m = a * ei_hf + b * gf_di + c * dh_eg;
+
+    const double ak_jb = a * k - j * b;
+    const double jc_al = j * c - a * l;
+    const double bl_ck = b * l - c * k;
+
+    const double t = -(f * ak_jb + e * jc_al + d * bl_ck) / m;
+    if (!in_range(s, e_, t)) return false;
+    const double gamma = (i * ak_jb + h * jc_al + g * bl_ck) / m;
+    if (gamma < 0.0 || gamma > 1.0) return false;
+    const double beta = (j * ei_hf + k * gf_di + l * dh_eg) / m;
+    if (beta < 0.0 || beta > 1.0 - gamma) return false;
+    t_out = t;
+    if (bary) { bary->beta = beta; bary->gamma = gamma; }
+    return true;
+}
+
+// BoundingBox::test_hit, bounding_box.rs:104-116: is_some() only
+PT_D bool bbox_gate(const PtMesh* __restrict__ mesh, V3 o, V3 d, double s, double e) {
+    double m[12];
+    load_doubles12(mesh->bbox_invtrans, m);
+    const V3 lo = xf_point(m, o), ld = xf_dir(m, d);
+    if (cube_contains(ray_at(lo, ld, s))) return true;
+    double t;
+    uint32_t face;
+    return cube_t<true>(lo, ld, s, e, t, face);
+}
+
+// ------------------------------------------------------------------ kd walk
+struct KdStack {
+    uint32_t node[PT_MAX_KD_STACK];
+    double s[PT_MAX_KD_STACK];
+    double e[PT_MAX_KD_STACK];
+};
+
+PT_D void load_kd_node(const PtKdNode* __restrict__ nodes, uint32_t i, double& split, uint32_t& a, uint32_t& b) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(nodes) + i);
+    split = __hiloint2double((int)w.y, (int)w.x);
+    a = w.z;
+    b = w.w;
+}
+
+// Iterative form of ray_cast_impl (node.rs:66-203). `leaf(first, count, s, e)`
+// returns true when the leaf's fold produced a hit inside [s, e); the first
+// leaf that does ends the walk.
+template <class LeafFn>
+PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d, double s, double e, KdStack& stack,
+                  LeafFn& leaf, uint32_t& err, uint32_t& n_splits) {
+    int sp = 0;
+    uint32_t node = 0;
+    for (;;) {
+        double split;
+        uint32_t a, b;
+        load_kd_node(nodes, node, split, a, b);
+        const uint32_t axis = a & 3u;
+        if (axis != 3u) {
+            ++n_splits;
+            // node.rs:119-127
+            double t_max = s + extent;
+            if (!in_range(s, e, t_max)) t_max = e - kEps;
+            const double t_min = s + kEps;
+            const double oa = axis == 0 ? o.x : (axis == 1 ? o.y : o.z);
+            const double da = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
+            const double p0 = oa + da * t_min;
+            const double p1 = oa + da * t_max;
+            const bool f0 = (p0 - split) >= 0.0;  // which_side, infinite_plane.rs:27-35
+            const bool f1 = (p1 - split) >= 0.0;
+            const uint32_t front = a >> 2, back = b;
+            if (f0 == f1) {  // node.rs:134-137
+                node = f0 ? front : back;
+                continue;
+            }
+            const double tp = (split - oa) / da;  // ray_hit_axis_aligned_plane, node.rs:90-110
+            if (in_range(s, e, tp)) {
+                // near child on [s, tp); if it misses, far child on [tp, e). node.rs:150-166
+                stack.node[sp] = f0 ? back : front;
+                stack.s[sp] = tp;
+                stack.e[sp] = e;
+                ++sp;
+                node = f0 ? front : back;
+                e = tp;
+                continue;
+            }
+            err |= PT_DEVERR_KD_PLANE;  // .expect("bug: ray should definitely hit infinite plane")
+        } else if (leaf(a >> 2, b, s, e)) {
+            return true;
+        }
+        if (sp == 0) return false;
+        --sp;
+        node = stack.node[sp];
+        s = stack.s[sp];
+        e = stack.e[sp];
+    }
+}
+
+// leaf of a KDMesh tree: RayHit for [Triangle] with a shrinking clone of the range (ray.rs:50-63)
+template <bool ANY>
+struct BlasLeaf {
+    const uint32_t* __restrict__ items;
+    const PtTriPos* __restrict__ tris;
+    V3 o, d;
+    double t;
+    uint32_t tri;
+    uint32_t n_tests;
+    PT_D bool operator()(uint32_t first, uint32_t count, double s, double e) {
+        bool found = false;
+        for (uint32_t k = 0; k < count; ++k) {
+            const uint32_t idx = __ldg(items + first + k);
+            ++n_tests;
+            double tt;
+            if (triangle_t(tris + idx, o, d, s, e, tt, nullptr)) {
+                e = tt;
+                t = tt;
+                tri = idx;
+                found = true;
+                if (ANY) return true;
+            }
+        }
+        return found;
+    }
+};
+
+// Primitive::ray_hit in object space (primitive.rs:55-61), t + sub id only
+template <bool ANY>
+PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V3 d, double s, double e, double& t,
+                      uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc) {
+    sub = 0;
+    switch (prim) {
+        case PT_PRIM_SPHERE: return sphere_t(o, d, s, e, t);
+        case PT_PRIM_CUBE: return cube_t<ANY>(o, d, s, e, t, sub);
+        case PT_PRIM_PLANE: return plane_t(o, d, s, e, t);
+        case PT_PRIM_CYLINDER: return cylinder_t<ANY>(o, d, s, e, t, sub);
+        case PT_PRIM_CONE: return cone_t<ANY>(o, d, s, e, t, sub);
+        default: break;
+    }
+    const PtMesh* mesh = sc.meshes + mesh_id;
+    const uint32_t tri_first = __ldg(&mesh->tri_first);
+    if (prim == PT_PRIM_TRIANGLE) {
+        ++wc.triangle_tests;
+        return triangle_t(sc.tri_pos + tri_first, o, d, s, e, t, nullptr);
+    }
+    ++wc.bbox_gates;
+    if (!bbox_gate(mesh, o, d, s, e)) return false;
+    if (prim == PT_PRIM_MESH) {  // linear fold over every triangle, mesh.rs:157-167
+        const uint32_t n = __ldg(&mesh->tri_count);
+        bool found = false;
+        for (uint32_t k = 0; k < n; ++k) {
+            ++wc.triangle_tests;
+            double tt;
+            if (triangle_t(sc.tri_pos + tri_first + k, o, d, s, e, tt, nullptr)) {
+                e = tt;
+                t = tt;
+                sub = k;
+                found = true;
+                if (ANY) return true;
+            }
+        }
+        return found;
+    }
+    // KDMesh: KDTreeNode<Triangle>::ray_hit on a clone of the range (node.rs:33-51)
+    BlasLeaf<ANY> leaf{sc.blas_items + __ldg(&mesh->item_first), sc.tri_pos + tri_first, o, d, 0.0, 0, 0};
+    const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), __ldg(&mesh->extent), o, d, s, e, blas_stack, leaf,
+                             err, wc.kd_splits);
+    wc.triangle_tests += leaf.n_tests;
+    if (hit) { t = leaf.t; sub = leaf.tri; }
+    return hit;
+}
+
+// leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99)
+template <bool ANY>
+struct TlasLeaf {
+    const DScene& sc;
+    V3 o, d;
+    KdStack& blas_stack;
+    Hit& hit;
+    uint32_t& err;
+    WorkCounters& wc;
+    PT_D bool operator()(uint32_t first, uint32_t count, double s, double e) {
+        bool found = false;
+        for (uint32_t k = 0; k < count; ++k) {
+            const uint32_t inst = __ldg(sc.tlas_items + first + k);
+            ++wc.instance_tests;
+            // FlatSceneNode::ray_cast: the ray in object space, direction NOT renormalised (flat_scene.rs:75, ray.rs:130-135)
+            const PtInstance* rec = sc.instances + inst;
+            double m[12];
+            load_doubles12(rec->invtrans, m);
+            const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&rec->prim));
+            const V3 lo = xf_point(m, o), ld = xf_dir(m, d);
+            double t;
+            uint32_t sub;
+            if (primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc)) {
+                e = t;  // flat_scene.rs:92
+                hit.t = t;
+                hit.inst = inst;
+                hit.sub = sub;
+                found = true;
+                if (ANY) return true;
+            }
+        }
+        return found;
+    }
+};
+
+// scene.root.ray_cast(ray, [EPSILON, inf)) — ray.rs:140-141, material.rs:174-179
+template <bool ANY>
+PT_D bool scene_cast(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& tlas_stack, KdStack& blas_stack, uint32_t& err,
+                     WorkCounters& wc) {
+    TlasLeaf<ANY> leaf{sc, o, d, blas_stack, hit, err, wc};
+    return kd_walk(sc.tlas_nodes, sc.tlas_extent, o, d, kEps, (double)INFINITY, tlas_stack, leaf, err, wc.kd_splits);
+}
+
+}  // namespace ptd

@@ -1,0 +1,155 @@
+#include "capi.h"
+
+#include <chrono>
+#include <cstring>
+#include <string>
+
+#include "assets.hpp"
+#include "examples/examples.hpp"
+#include "pack.hpp"
+#include "render.hpp"
+
+using namespace portrayer;
+
+struct PthScene {
+    ExampleScene example;
+    std::vector<uint8_t> blob;
+    double prepare_seconds = 0.0;
+};
+
+namespace {
+thread_local std::string g_error;
+
+PthScene* finish(ExampleScene ex, int64_t kd_depth, int linear_tlas) {
+    auto out = std::make_unique<PthScene>();
+    auto t0 = std::chrono::steady_clock::now();
+    if (ex.prebuilt) {
+        out->blob = pack_scene(*ex.prebuilt);
+    } else {
+        FlatScene flat = FlatScene::from(ex.scene);
+        if (linear_tlas) {
+            // one unpartitioned leaf: the flat_scene feature's linear fold (flat_scene.rs:71-99, ray.rs:87-99)
+            KDTreeScene kd = KDTreeScene::from(std::move(flat), 0);
+            out->blob = pack_scene(kd);
+        } else {
+            KDTreeScene kd = kd_depth < 0 ? KDTreeScene::from(std::move(flat))
+                                          : KDTreeScene::from(std::move(flat), static_cast<size_t>(kd_depth));
+            out->blob = pack_scene(kd);
+        }
+    }
+    out->prepare_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    out->example = std::move(ex);
+    return out.release();
+}
+
+template <class F>
+PthScene* guarded(F&& f) {
+    try {
+        return f();
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return nullptr;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char* pth_last_error(void) { return g_error.c_str(); }
+void pth_set_assets_dir(const char* dir) { set_assets_dir(dir); }
+void pth_register_texture(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb8) {
+    register_texture(path, width, height, rgb8);
+}
+
+void pth_set_baked_mesh_dir(const char* dir) { set_baked_mesh_dir(dir); }
+void pth_set_texture_loader(PthTextureLoader fn) { set_texture_loader(fn); }
+int pth_bake_obj(const char* obj_path, const char* out_path) {
+    try {
+        MeshData::load_obj(obj_path)->save_baked(out_path);
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+int64_t pth_mesh_info(const char* obj_path, uint64_t* n_positions, uint64_t* n_normals, uint64_t* n_uvs) {
+    try {
+        auto m = MeshData::load_obj(obj_path);
+        *n_positions = m->num_positions();
+        *n_normals = m->num_normals();
+        *n_uvs = m->has_tex_coords() ? m->num_positions() : 0;
+        return static_cast<int64_t>(m->num_triangles());
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+int pth_example_count(void) { return static_cast<int>(example_registry().size()); }
+const char* pth_example_name(int index) {
+    int i = 0;
+    for (const auto& kv : example_registry())
+        if (i++ == index) return kv.first.c_str();
+    return nullptr;
+}
+
+PthScene* pth_example_build(const char* name, int64_t kd_depth, int linear_tlas) {
+    return guarded([&]() -> PthScene* {
+        auto it = example_registry().find(name);
+        if (it == example_registry().end()) throw std::runtime_error(std::string("unknown example: ") + name);
+        return finish(it->second(), kd_depth, linear_tlas);
+    });
+}
+PthScene* pth_big_scene_build(uint64_t n, int64_t kd_depth, int linear_tlas) {
+    return guarded([&] { return finish(make_big_scene(n), kd_depth, linear_tlas); });
+}
+PthScene* pth_synthetic_instances_build(uint64_t n_instances, uint64_t seed, int64_t kd_depth) {
+    return guarded([&] { return finish(make_synthetic_instances(n_instances, seed), kd_depth, 0); });
+}
+PthScene* pth_synthetic_triangles_build(uint64_t n_triangles, uint64_t seed, int64_t kd_mesh_depth) {
+    return guarded([&] {
+        return finish(make_synthetic_triangles(n_triangles, seed, static_cast<size_t>(kd_mesh_depth)), -1, 0);
+    });
+}
+void pth_scene_free(PthScene* s) { delete s; }
+
+uint64_t pth_blob_size(const PthScene* s) { return s->blob.size(); }
+const void* pth_blob_data(const PthScene* s) { return s->blob.data(); }
+void pth_image_size(const PthScene* s, uint32_t* width, uint32_t* height) {
+    *width = static_cast<uint32_t>(s->example.width);
+    *height = static_cast<uint32_t>(s->example.height);
+}
+void pth_camera(const PthScene* s, double width, double height, PtCamera* out) {
+    *out = make_camera(s->example.cam, width, height);
+}
+void pth_background(const PthScene* s, uint32_t width, uint32_t height, double* out) {
+    for (uint32_t y = 0; y < height; ++y)
+        for (uint32_t x = 0; x < width; ++x) {
+            Rgb c = s->example.background(Uv{(double)x / (double)width, (double)y / (double)height});
+            double* p = out + (static_cast<size_t>(y) * width + x) * 3;
+            p[0] = c.r; p[1] = c.g; p[2] = c.b;
+        }
+}
+double pth_prepare_seconds(const PthScene* s) { return s->prepare_seconds; }
+
+int pth_image_render(const PthScene* s, uint32_t width, uint32_t height, uint32_t samples, uint32_t rng_mode,
+                     uint64_t seed, uint8_t* rgb_inout, PtStats* stats) {
+    try {
+        if (s->example.prebuilt) throw std::runtime_error("prebuilt known-answer scenes have no HierScene to render");
+        Image image("", width, height);
+        std::memcpy(image.buffer().data(), rgb_inout, image.buffer().size());
+        RenderOptions opts;
+        opts.samples = samples;
+        opts.rng_mode = rng_mode;
+        opts.seed = seed;
+        opts.stats = stats;
+        image.render<NullProgress>(s->example.scene, s->example.cam, s->example.background, opts);
+        std::memcpy(rgb_inout, image.buffer().data(), image.buffer().size());
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// Known-answer scenes restating the reference's own unit tests for the hot
+// path, so oracle and device can be run on exactly what those tests build:
+//   kat-edge-case / kat-edge-case-flipped   src/kdtree/node.rs:219-352
+//   kat-mesh-equivalence-{mesh,kdmesh}      src/kdtree/kdmesh.rs:99-166
+#include "examples.hpp"
+using namespace portrayer;
+
+namespace {
+
+std::unique_ptr<KDIndexTree> leaf_of(std::vector<uint32_t> items, const std::vector<FlatSceneNode>& nodes) {
+    auto n = std::make_unique<KDIndexTree>();
+    n->is_leaf = true;
+    // leaf bounds do not matter currently (node.rs:276-277)
+    n->leaf.bounds = BoundingBox(Vec3::zero(), Vec3::zero());
+    for (uint32_t i : items)
+        n->leaf.nodes.push_back(std::make_shared<const NodeBounds<uint32_t>>(NodeBounds<uint32_t>{nodes[i].bounds(), i}));
+    return n;
+}
+
+// node.rs:219-293 (flipped = false) and node.rs:295-351 (flipped = true).
+// Instance 0 = B (red), instance 1 = C (blue); the expected hit is B.
+ExampleScene edge_case(bool flipped) {
+    const double sgn = flipped ? -1.0 : 1.0;
+    auto mat_b = Arc(Material{.diffuse = Rgb::red()});
+    auto mat_c = Arc(Material{.diffuse = Rgb::blue()});
+
+    Mat4 trans_b = Mat4::scaling_3d(2.0).rotated_x(Radians::from_degrees(sgn * 90.0).get()).translated_3d({0.0, 1.2, sgn * -0.4});
+    Mat4 trans_c = Mat4::scaling_3d(2.0).rotated_x(Radians::from_degrees(sgn * 50.0).get()).translated_3d({0.0, 0.0, sgn * -0.3});
+
+    auto kd = std::make_shared<KDTreeScene>();
+    kd->nodes.emplace_back(Geometry(Plane{}, mat_b), trans_b);
+    kd->nodes.emplace_back(Geometry(Plane{}, mat_c), trans_c);
+    const uint32_t B = 0, C = 1;
+
+    auto root = std::make_unique<KDIndexTree>();
+    root->is_leaf = false;
+    root->axis = 2;  // sep_plane normal = unit_z, point = zero
+    root->plane = 0.0;
+    std::vector<BoundingBox> both = {kd->nodes[B].bounds(), kd->nodes[C].bounds()};
+    root->bounds = bounds_of(both.begin(), both.end(), [](const BoundingBox& b) { return b; });
+    if (!flipped) {
+        root->front_nodes = leaf_of({C}, kd->nodes);
+        root->back_nodes = leaf_of({C, B}, kd->nodes);  // Force tree to check C again by putting it first
+    } else {
+        root->front_nodes = leaf_of({C, B}, kd->nodes);
+        root->back_nodes = leaf_of({C}, kd->nodes);
+    }
+    kd->root = std::move(root);
+    kd->ambient = {1.0, 1.0, 1.0};  // colour of a hit == the material's diffuse
+
+    ExampleScene ex;
+    ex.name = flipped ? "kat-edge-case-flipped" : "kat-edge-case";
+    ex.prebuilt = kd;
+    ex.cam = CameraSettings{.eye = {0.0, 0.5, sgn * 0.9}, .center = {0.0, 0.5, 0.0}, .up = Vec3::up(),
+                            .fovy = Radians::from_degrees(1.0)};
+    ex.width = 1;
+    ex.height = 1;
+    ex.background = [](Uv) { return Rgb::black(); };
+    return ex;
+}
+
+// kdmesh.rs:99-166
+ExampleScene mesh_equivalence(bool kd) {
+    auto mat_castle_walls = Arc(Material{.diffuse = {1.0, 0.0, 0.0}, .specular = {0.3, 0.3, 0.3}, .shininess = 25.0});
+    auto model = MeshData::load_obj("assets/castle.obj");
+    Primitive prim = kd ? Primitive(KDMesh(*model, Shading::Flat, MAX_TREE_DEPTH)) : Primitive(Mesh(model, Shading::Flat));
+
+    ExampleScene ex;
+    ex.name = kd ? "kat-mesh-equivalence-kdmesh" : "kat-mesh-equivalence-mesh";
+    ex.scene = HierScene{
+        .root = SceneNode::from(Geometry(prim, mat_castle_walls)).scaled(1.4).translated({0.0, 0.0, -229.0}).into(),
+        .lights = {Light{.position = {50.0, 110.0, -120.0}, .color = {0.9, 0.9, 0.9}}},
+        .ambient = {0.3, 0.3, 0.3},
+    };
+    ex.cam = CameraSettings{.eye = {0.0, 120.0, 240.0}, .center = {0.0, 100.0, -24.0}, .up = Vec3::up(),
+                            .fovy = Radians::from_degrees(25.0)};
+    ex.width = 533;
+    ex.height = 300;
+    ex.background = [](Uv) { return Rgb::black(); };
+    return ex;
+}
+
+}  // namespace
+
+PORTRAYER_EXAMPLE(kat_edge_case, "kat-edge-case") { return edge_case(false); }
+PORTRAYER_EXAMPLE(kat_edge_case_flipped, "kat-edge-case-flipped") { return edge_case(true); }
+PORTRAYER_EXAMPLE(kat_mesh_eq_mesh, "kat-mesh-equivalence-mesh") { return mesh_equivalence(false); }
+PORTRAYER_EXAMPLE(kat_mesh_eq_kdmesh, "kat-mesh-equivalence-kdmesh") { return mesh_equivalence(true); }

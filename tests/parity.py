@@ -1,0 +1,55 @@
+"""Shared helpers of the parity tests: run the same scene through the CPU oracle
+and through the CUDA path (via the C ABI), and compare by the bar of
+BASELINE.json: 8-bit RGB within +-1 LSB on >= 99.9 % of pixels, primitive hit
+ids bit-exact except grazing-edge pixels with |dt| below DT_EPSILON."""
+from __future__ import annotations
+
+import numpy as np
+
+import portrayer_b200 as pt
+from oracle import binding as oracle
+from portrayer_b200 import _ffi
+from portrayer_b200.render import _background_arg, make_params
+
+RGB_TOLERANCE_LSB = 1
+RGB_MIN_FRACTION = 0.999
+DT_EPSILON = 1e-7  # relative: |t_gpu - t_cpu| <= DT_EPSILON * max(1, |t|) at a hit-id mismatch counts as a grazing edge
+
+
+def render_oracle(scene: pt.Scene, samples=1, rng="fixed", seed=1, size=None, threads=None, **kw):
+    w, h = size or (scene.width, scene.height)
+    bg, bg_mode = _background_arg(scene, w, h)
+    params = make_params(w, h, samples, rng, seed, bg_mode=bg_mode, **kw)
+    return oracle.render(scene.blob, scene.camera(w, h), params, bg, threads=threads)
+
+
+def render_gpu(scene: pt.Scene, samples=1, rng="fixed", seed=1, size=None, dscene=None, **kw):
+    w, h = size or (scene.width, scene.height)
+    img = pt.Image(w, h)
+    stats = img.render(scene, samples=samples, rng=rng, seed=seed, want_hit_ids=True, dscene=dscene, **kw)
+    return img, stats
+
+
+def compare(gpu_img: pt.Image, ref: "oracle.OracleResult", label: str = "") -> dict:
+    a = gpu_img.buffer.astype(np.int32)
+    b = ref.rgb.astype(np.int32)
+    diff = np.abs(a - b).max(axis=2)
+    within = float((diff <= RGB_TOLERANCE_LSB).mean())
+    exact = float((diff == 0).mean())
+    id_mismatch = np.any(gpu_img.hit_id != ref.hit_id, axis=2)
+    n_mis = int(id_mismatch.sum())
+    grazing = 0
+    if n_mis:
+        tg, tc = gpu_img.hit_t[id_mismatch], ref.hit_t[id_mismatch]
+        fin = np.isfinite(tg) & np.isfinite(tc)
+        ok = np.zeros(n_mis, bool)
+        ok[fin] = np.abs(tg[fin] - tc[fin]) <= DT_EPSILON * np.maximum(1.0, np.abs(tc[fin]))
+        grazing = int(ok.sum())
+    t_same = np.array_equal(gpu_img.hit_t, ref.hit_t)
+    return {"label": label, "rgb_within_1lsb": within, "rgb_exact": exact, "max_lsb_diff": int(diff.max()),
+            "hit_id_mismatches": n_mis, "hit_id_grazing": grazing, "hit_t_bit_identical": t_same}
+
+
+def assert_parity(report: dict):
+    assert report["rgb_within_1lsb"] >= RGB_MIN_FRACTION, report
+    assert report["hit_id_mismatches"] == report["hit_id_grazing"], report

@@ -1,0 +1,161 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle. -m gpu."""
+import numpy as np
+import pytest
+
+import parity
+import portrayer_b200 as pt
+from conftest import has_reference_assets
+from oracle import binding as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _report(name, **kw):
+    scene = pt.Scene.example(name)
+    img, stats = parity.render_gpu(scene, **kw)
+    ref = parity.render_oracle(scene, **kw)
+    assert ref.rc == 0
+    rep = parity.compare(img, ref, name)
+    rep["rays"] = stats.rays
+    print(rep)
+    # the device and the oracle issue exactly the same rays
+    assert stats.rays_primary == ref.stats.rays_primary
+    assert stats.rays_shadow == ref.stats.rays_shadow
+    assert stats.rays_reflect == ref.stats.rays_reflect
+    assert stats.rays_refract == ref.stats.rays_refract
+    assert stats.rays_depth_cut == ref.stats.rays_depth_cut
+    return rep
+
+
+# BASELINE.json configs[0]: nonhier at its native resolution, SAMPLES=1, pixel-centre rays
+def test_nonhier_native(gpu_ready):
+    rep = _report("nonhier", samples=1, rng="fixed")
+    parity.assert_parity(rep)
+    assert rep["max_lsb_diff"] <= 1
+
+
+# configs[1]: all analytic primitives, instancing, a reflective dome
+def test_primitives_native(gpu_ready):
+    parity.assert_parity(_report("primitives", samples=1, rng="fixed"))
+
+
+@pytest.mark.skipif(not has_reference_assets(), reason="reference textures not synced (tools/sync_assets.py)")
+@pytest.mark.parametrize("name", ["texture-mapping", "normal-mapping", "normal-mapping-left", "normal-mapping-right"])
+def test_textured_scenes(gpu_ready, name):
+    parity.assert_parity(_report(name, samples=1, rng="fixed"))
+
+
+# configs[2]: kd-tree traversal stress, at reduced size so the oracle finishes in seconds
+@pytest.mark.parametrize("kd_depth", [10, 18])
+def test_big_scene(gpu_ready, kd_depth):
+    scene = pt.Scene.big_scene(10, kd_depth=kd_depth)
+    kw = dict(samples=1, rng="fixed", size=(495, 255))
+    img, stats = parity.render_gpu(scene, **kw)
+    ref = parity.render_oracle(scene, **kw)
+    rep = parity.compare(img, ref, f"big-scene kd{kd_depth}")
+    print(rep)
+    parity.assert_parity(rep)
+    assert stats.rays == ref.stats.rays
+
+
+# configs[3]: secondary-ray-bound recursion with hashed jitter, glossy + area-light + dielectric RNG dimensions
+@pytest.mark.parametrize("name,samples", [("glossy-reflection", 4), ("soft-shadows", 2)])
+def test_secondary_ray_scenes(gpu_ready, name, samples):
+    parity.assert_parity(_report(name, samples=samples, rng="hash", size=(455, 256)))
+
+
+@pytest.mark.skipif(not has_reference_assets(), reason="reference textures not synced (tools/sync_assets.py)")
+def test_water_glass(gpu_ready):
+    parity.assert_parity(_report("water-glass", samples=4, rng="hash", size=(455, 256)))
+
+
+# src/kdtree/node.rs:219-352 on the device
+@pytest.mark.parametrize("name,origin,direction", [
+    ("kat-edge-case", (0.0, 0.5, 0.9), (0.0, 0.0, -1.0)),
+    ("kat-edge-case-flipped", (0.0, 0.5, -0.9), (0.0, 0.0, 1.0)),
+])
+def test_ray_cast_edge_case_device(gpu_ready, name, origin, direction):
+    scene = pt.Scene.example(name)
+    ds = pt.DeviceScene(scene.blob)
+    color, hit_id, hit_t, _ = ds.trace_rays(np.array([origin]), np.array([direction]))
+    assert hit_id[0, 0] == 0 and tuple(color[0]) == (1.0, 0.0, 0.0)
+
+
+# src/kdtree/kdmesh.rs:99-166 on the device: Mesh == KDMesh bit-exact, and both == the oracle
+def test_mesh_equivalence_device(gpu_ready):
+    mesh = pt.Scene.example("kat-mesh-equivalence-mesh")
+    kdmesh = pt.Scene.example("kat-mesh-equivalence-kdmesh")
+    n = 100000
+    i = np.arange(n, dtype=np.float64)
+    origins, dirs = oracle.camera_rays(mesh.camera(533, 300), np.stack([533.0 * i / n, 300.0 * i / n], axis=1))
+    ca, ia, ta, _ = pt.DeviceScene(mesh.blob).trace_rays(origins, dirs)
+    cb, ib, tb, _ = pt.DeviceScene(kdmesh.blob).trace_rays(origins, dirs)
+    assert np.array_equal(ca, cb) and np.array_equal(ia, ib) and np.array_equal(ta, tb)
+    rc, co, io, to, _ = oracle.trace_rays(mesh.blob, origins, dirs)
+    assert rc == 0
+    assert np.array_equal(ia, io) and np.array_equal(ta, to)
+    # colours go through pow(): CUDA's and glibc's differ by <= 2 ulp
+    assert np.allclose(ca, co, rtol=1e-13, atol=0)
+
+
+def test_determinism_and_batch_independence(gpu_ready):
+    """The image must not depend on batch size (nor, therefore, on tile/GPU partitioning)."""
+    scene = pt.Scene.example("glossy-reflection")
+    a, _ = parity.render_gpu(scene, samples=2, rng="hash", size=(320, 180))
+    b, _ = parity.render_gpu(scene, samples=2, rng="hash", size=(320, 180), max_batch_paths=4096)
+    c, sc = parity.render_gpu(scene, samples=2, rng="hash", size=(320, 180), max_batch_paths=20000, node_pool_capacity=30000)
+    assert np.array_equal(a.buffer, b.buffer) and np.array_equal(a.buffer, c.buffer)
+    assert np.array_equal(a.hit_id, b.hit_id)
+    assert sc.batches > 1
+
+
+def test_slice_only_writes_slice(gpu_ready):
+    """slice_mut (render.rs:211-213): pixels outside the slice keep their old value (render.rs:136-138)."""
+    scene = pt.Scene.example("nonhier")
+    full, _ = parity.render_gpu(scene, samples=1, rng="fixed", size=(96, 96))
+    img = pt.Image(96, 96)
+    img.buffer[:] = 7
+    img.render(scene, samples=1, rng="fixed", slice_=(10, 20, 50, 40))
+    assert np.array_equal(img.buffer[20:41, 10:51], full.buffer[20:41, 10:51])
+    mask = np.ones((96, 96), bool)
+    mask[20:41, 10:51] = False
+    assert np.all(img.buffer[mask] == 7)
+    with pytest.raises(IndexError):
+        img.render(scene, samples=1, slice_=(0, 0, 96, 10))
+
+
+def test_tile_ownership_matches_single_rank(gpu_ready):
+    """Interleaved tile ownership: the union of world=3 partial renders is the single-rank image."""
+    scene = pt.Scene.example("primitives")
+    w, h = 200, 120
+    full, _ = parity.render_gpu(scene, samples=1, rng="hash", size=(w, h))
+    img = pt.Image(w, h)
+    for rank in range(3):
+        img.render(scene, samples=1, rng="hash", rank=rank, world=3, tile=16)
+    assert np.array_equal(img.buffer, full.buffer)
+
+
+def test_reference_panic_is_reported(gpu_ready):
+    """A textured material on a cylinder panics in the reference (material.rs:141); the C ABI returns that text."""
+    import ctypes as C
+
+    from portrayer_b200 import _ffi
+
+    scene = pt.Scene.example("water-glass") if has_reference_assets() else None
+    if scene is None:
+        pytest.skip("needs a textured scene")
+    # patch instance 2 (the water cylinder) to use the textured table material
+    blob = scene.blob.copy()
+    h = scene.header
+    inst = np.frombuffer(blob, dtype=np.uint8, count=h.n_instances * 128, offset=h.off_instances).view(np.uint32).reshape(h.n_instances, 32)
+    prims = inst[:, 24]
+    cyl = int(np.where(prims == 6)[0][0])
+    mats = np.frombuffer(blob, dtype=np.uint8, count=h.n_materials * 160, offset=h.off_materials).view(np.int32).reshape(h.n_materials, 40)
+    textured = int(np.where(mats[:, 38] >= 0)[0][0])
+    inst[cyl, 26] = textured
+    ds = pt.DeviceScene(blob)
+    img = pt.Image(64, 36)
+    params = pt.make_params(64, 36, 1, "fixed", bg_mode=_ffi.PT_BG_CONSTANT)
+    with pytest.raises(pt.PortrayerError) as err:
+        ds.render(scene.camera(64, 36), params, np.zeros(3), img.buffer)
+    assert "mapping is not supported for this primitive!" in str(err.value)

@@ -1,0 +1,73 @@
+"""The oracle against every known-answer test the reference holds for the hot path.
+CPU only: these pin the checker before it is trusted to check the CUDA path."""
+import math
+
+import numpy as np
+import pytest
+
+import portrayer_b200 as pt
+from oracle import binding as oracle
+
+
+def approx(a, b, eps=1e-6):  # assert_approx_eq!'s default
+    return abs(a - b) < eps
+
+
+# src/math.rs:159-172 solve_quadratic_equations
+def test_solve_quadratic_equations():
+    s = oracle.solve_quadratic(2.0, 8.0, 3.0)  # discriminant > 0, ascending
+    assert len(s) == 2 and approx(s[0], -2.0 - math.sqrt(5.0 / 2.0)) and approx(s[1], math.sqrt(5.0 / 2.0) - 2.0)
+    s = oracle.solve_quadratic(4.0, -4.0, 1.0)  # discriminant == 0
+    assert len(s) == 1 and approx(s[0], 0.5)
+    assert oracle.solve_quadratic(3.0, 4.0, 2.0) == []  # discriminant < 0
+
+
+# src/math.rs:174-179 solution_order
+def test_solution_order():
+    s = oracle.solve_quadratic(-2.0, 8.0, 3.0)
+    assert len(s) == 2 and approx(s[0], 2.0 - math.sqrt(11.0 / 2.0)) and approx(s[1], 2.0 + math.sqrt(11.0 / 2.0))
+    assert s[0] < s[1]
+
+
+def test_quadratic_linear_fallback():
+    assert oracle.solve_quadratic(0.0, 2.0, -4.0) == [2.0]  # a == 0 falls back to the linear solver
+    assert oracle.solve_quadratic(0.0, 0.0, 1.0) == []
+
+
+# src/kdtree/node.rs:219-293 / :295-351 — B (instance 0, red) must win over C (instance 1, blue)
+@pytest.mark.parametrize("name,origin,direction", [
+    ("kat-edge-case", (0.0, 0.5, 0.9), (0.0, 0.0, -1.0)),
+    ("kat-edge-case-flipped", (0.0, 0.5, -0.9), (0.0, 0.0, 1.0)),
+])
+def test_ray_cast_edge_case(name, origin, direction):
+    scene = pt.Scene.example(name)
+    rc, color, hit_id, hit_t, _ = oracle.trace_rays(scene.blob, np.array([origin]), np.array([direction]), threads=1)
+    assert rc == 0
+    assert hit_id[0, 0] == 0, "the nearer plane B must be returned, not C which straddles the split"
+    assert tuple(color[0]) == (1.0, 0.0, 0.0)  # mat_b = Rgb::red()
+    assert math.isfinite(hit_t[0]) and hit_t[0] > 0
+
+
+def _mesh_equivalence_rays(scene, n):
+    # kdmesh.rs:155-160: x = width * i / n, y = height * i / n
+    i = np.arange(n, dtype=np.float64)
+    xy = np.stack([533.0 * i / n, 300.0 * i / n], axis=1)
+    return oracle.camera_rays(scene.camera(533, 300), xy)
+
+
+# src/kdtree/kdmesh.rs:99-166 mesh_equivalence: Mesh and KDMesh give the SAME colour, bit for bit, for 100 000 rays
+def test_mesh_equivalence():
+    mesh = pt.Scene.example("kat-mesh-equivalence-mesh")
+    kdmesh = pt.Scene.example("kat-mesh-equivalence-kdmesh")
+    assert mesh.header.n_triangles == 1804  # castle.obj
+    n = 100000
+    origins, dirs = _mesh_equivalence_rays(mesh, n)
+    rc_a, color_a, id_a, t_a, st_a = oracle.trace_rays(mesh.blob, origins, dirs)
+    rc_b, color_b, id_b, t_b, st_b = oracle.trace_rays(kdmesh.blob, origins, dirs)
+    assert rc_a == 0 and rc_b == 0
+    assert np.array_equal(color_a, color_b), "pixels were not the same"
+    assert np.array_equal(t_a, t_b)
+    assert np.array_equal(id_a, id_b)  # same triangle index: both are MeshData.triangles order
+    assert (id_a[:, 0] != 0xFFFFFFFF).sum() > n // 10  # the sweep really crosses the castle
+    # the kd walk tests far fewer triangles than the linear scan
+    assert st_b.triangle_tests * 5 < st_a.triangle_tests
