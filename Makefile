@@ -33,12 +33,12 @@ example: $(EXAMPLE_BIN)
 $(PKG)/lib:
 	mkdir -p $@
 
-build/scene_blob.o: $(PKG)/csrc/scene_blob.c include/portrayer_gpu.h
+build/%.o: $(PKG)/csrc/%.c include/portrayer_gpu.h
 	mkdir -p build
 	$(CC) $(CFLAGS) -c $< -o $@
 
-$(GPU_LIB): $(GPU_SRC) $(GPU_HDR) build/scene_blob.o | $(PKG)/lib
-	$(NVCC) $(NVFLAGS) -shared $(GPU_SRC) build/scene_blob.o -o $@ 2> build/ptxas_gpu.log || (cat build/ptxas_gpu.log; false)
+$(GPU_LIB): $(GPU_SRC) $(GPU_HDR) build/scene_blob.o build/tiles.o | $(PKG)/lib
+	$(NVCC) $(NVFLAGS) -shared $(GPU_SRC) build/scene_blob.o build/tiles.o -o $@ 2> build/ptxas_gpu.log || (cat build/ptxas_gpu.log; false)
 	@grep -E "error|warning" build/ptxas_gpu.log || true
 
 $(HOST_LIB): $(HOST_SRC) $(HOST_HDR) $(GPU_LIB) | $(PKG)/lib

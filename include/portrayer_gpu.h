@@ -265,6 +265,7 @@ typedef struct PtRenderParams {
 
 #define PT_RENDER_COUNTERS 1u  /* run the counting variant of the traversal kernels (fills PtStats work counters) */
 #define PT_RENDER_LINEAR_TLAS 2u /* ignore the scene kd-tree: FlatScene linear scan, flat_scene.rs:71-99 + ray.rs:87-99 */
+#define PT_RENDER_KERNEL_TIMES 4u /* bracket every extend / shadow / shade launch with CUDA events (fills PtStats.ms_*) */
 
 typedef struct PtStats {
     /* rays = every ray_cast issued against the scene root */
@@ -282,6 +283,11 @@ typedef struct PtStats {
     double device_ms;           /* CUDA-event time of the kernels of the call */
     double h2d_ms, d2h_ms;
     uint64_t h2d_bytes, d2h_bytes;
+    /* work counters split by traversal kernel (only with PT_RENDER_COUNTERS): [0] extend, [1] shadow */
+    uint64_t k_kd_splits[2], k_instance_tests[2], k_triangle_tests[2], k_bbox_gates[2];
+    /* per-kernel device time and launch counts (only with PT_RENDER_KERNEL_TIMES): extend, shadow, shade */
+    double ms_extend, ms_shadow, ms_shade;
+    uint32_t n_extend, n_shadow, n_shade, reserved2;
 } PtStats;
 
 typedef struct PtScene PtScene; /* opaque, library-owned */
@@ -328,6 +334,10 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
 
 /* The same path with device-resident inputs/outputs, for callers that keep the
  * frame in HBM (multi-GPU gather, benchmarks). */
+/* The global pixel indices (y * W + x) a (rank, world) pair renders for these params, in output order.
+ * Pure host function (no GPU needed): returns the count; writes at most `capacity` entries when index_out != NULL. */
+uint64_t pt_owned_pixels(const PtRenderParams* params, uint32_t* index_out, uint64_t capacity);
+
 int pt_frame_create(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, PtFrame** out);
 void pt_frame_free(PtFrame* frame);
 uint64_t pt_frame_owned_pixels(const PtFrame* frame);   /* pixels this rank renders */

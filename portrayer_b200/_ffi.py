@@ -37,7 +37,7 @@ PT_ERR_NO_TEXCOORD_NORMALMAP, PT_ERR_NO_TEXCOORD_TEXTURE = -3, -4
 PT_ERR_KD_PLANE_MISS, PT_ERR_TIR_INSIDE, PT_ERR_KD_TOO_DEEP, PT_ERR_OVERFLOW = -5, -6, -7, -8
 PT_RNG_FIXED, PT_RNG_HASH = 0, 1
 PT_BG_PER_PIXEL, PT_BG_PER_ROW, PT_BG_CONSTANT = 0, 1, 2
-PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS = 1, 2
+PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS, PT_RENDER_KERNEL_TIMES = 1, 2, 4
 PT_EPSILON = 0.00001
 PT_MAX_RECURSION_DEPTH = 10
 PT_DEFAULT_SAMPLES = 100
@@ -80,10 +80,20 @@ class PtStats(C.Structure):
         ("device_error_bits", C.c_uint32), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
         ("device_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("k_kd_splits", C.c_uint64 * 2), ("k_instance_tests", C.c_uint64 * 2), ("k_triangle_tests", C.c_uint64 * 2),
+        ("k_bbox_gates", C.c_uint64 * 2),
+        ("ms_extend", C.c_double), ("ms_shadow", C.c_double), ("ms_shade", C.c_double),
+        ("n_extend", C.c_uint32), ("n_shadow", C.c_uint32), ("n_shade", C.c_uint32), ("reserved2", C.c_uint32),
     ]
 
     def as_dict(self) -> dict:
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+        out = {}
+        for name, _ in self._fields_:
+            if name.startswith("reserved"):
+                continue
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
 
     @property
     def rays(self) -> int:
@@ -128,6 +138,7 @@ GPU_SYMBOLS = {
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PtStats)]),
     "pt_trace_rays": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                 C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PtStats)]),
+    "pt_owned_pixels": (C.c_uint64, [C.POINTER(PtRenderParams), C.c_void_p, C.c_uint64]),
     "pt_frame_create": (C.c_int, [C.c_void_p, C.POINTER(PtCamera), C.POINTER(PtRenderParams), C.POINTER(C.c_void_p)]),
     "pt_frame_free": (None, [C.c_void_p]),
     "pt_frame_owned_pixels": (C.c_uint64, [C.c_void_p]),

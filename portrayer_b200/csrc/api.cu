@@ -77,6 +77,7 @@ struct PtFrame {
     BatchCtl* d_ctl = nullptr;
     BatchCtl* h_ctl = nullptr;  // pinned
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::vector<cudaEvent_t> kernel_events;  // PT_RENDER_KERNEL_TIMES: begin/end pairs, reused per batch
     uint32_t max_depth = PT_MAX_RECURSION_DEPTH;
     int n_levels = 1;
 };
@@ -159,6 +160,7 @@ void free_frame(PtFrame* f) {
     if (f->h_ctl) cudaFreeHost(f->h_ctl);
     if (f->ev_start) cudaEventDestroy(f->ev_start);
     if (f->ev_stop) cudaEventDestroy(f->ev_stop);
+    for (cudaEvent_t e : f->kernel_events) cudaEventDestroy(e);
     delete f;
 }
 
@@ -202,17 +204,62 @@ FrameParams frame_params(const PtFrame* f) {
     return fp;
 }
 
+// Optional per-kernel timing: one begin/end event pair per extend / shadow / shade launch.
+struct KernelTimer {
+    std::vector<cudaEvent_t>* events = nullptr;  // null: timing off
+    size_t used = 0;
+    struct Span { int kind; size_t begin; };
+    std::vector<Span> spans;
+    void begin(int kind, cudaStream_t st) {
+        if (!events) return;
+        while (events->size() < used + 2) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            events->push_back(e);
+        }
+        spans.push_back({kind, used});
+        cudaEventRecord((*events)[used], st);
+    }
+    void end(cudaStream_t st) {
+        if (!events) return;
+        cudaEventRecord((*events)[used + 1], st);
+        used += 2;
+    }
+    // after the stream has been synchronised
+    void collect(PtStats* stats) {
+        if (!events || !stats) return;
+        for (const Span& s : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, (*events)[s.begin], (*events)[s.begin + 1]);
+            if (s.kind == 0) { stats->ms_extend += ms; ++stats->n_extend; }
+            else if (s.kind == 1) { stats->ms_shadow += ms; ++stats->n_shadow; }
+            else { stats->ms_shade += ms; ++stats->n_shade; }
+        }
+        spans.clear();
+        used = 0;
+    }
+};
+
 // Run one batch of `n_paths` root rays (already written into level 0) through every level.
 // Returns the control block in h_ctl (after a stream sync).
 int run_levels(const DScene& sc, const FrameParams& fp, const NodePool& pool, BatchCtl* d_ctl, BatchCtl* h_ctl,
-               uint32_t first_slot, uint32_t n_paths, int n_levels, bool count, cudaStream_t st, uint32_t* launches) {
+               uint32_t first_slot, uint32_t n_paths, int n_levels, bool count, cudaStream_t st, uint32_t* launches,
+               KernelTimer* timer) {
     for (int level = 0; level < n_levels; ++level) {
         // level d holds at most n_paths * 2^d rays, and never more than the pool
         unsigned long long bound = (unsigned long long)n_paths << std::min(level, 31);
         const uint32_t max_items = (uint32_t)std::min<unsigned long long>(bound, pool.capacity);
+        timer->begin(0, st);
         launch_extend(sc, pool, d_ctl, level, max_items, count, st);
-        launch_shadow(sc, fp, pool, d_ctl, level, first_slot, max_items, count, st);
+        timer->end(st);
+        if (sc.n_lights) {
+            timer->begin(1, st);
+            launch_shadow(sc, fp, pool, d_ctl, level, first_slot, max_items, count, st);
+            timer->end(st);
+        }
+        timer->begin(2, st);
         launch_shade(sc, fp, pool, d_ctl, level, first_slot, max_items, st);
+        timer->end(st);
         *launches += sc.n_lights ? 3 : 2;
     }
     CUDA_TRY(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
@@ -228,10 +275,16 @@ void accumulate_stats(PtStats* stats, const BatchCtl& c, uint32_t n_paths) {
     stats->rays_reflect += c.rays_reflect;
     stats->rays_refract += c.rays_refract;
     stats->rays_depth_cut += c.rays_depth_cut;
-    stats->kd_splits += c.kd_splits;
-    stats->instance_tests += c.instance_tests;
-    stats->triangle_tests += c.triangle_tests;
-    stats->bbox_gates += c.bbox_gates;
+    for (int k = 0; k < 2; ++k) {
+        stats->k_kd_splits[k] += c.work[k][0];
+        stats->k_instance_tests[k] += c.work[k][1];
+        stats->k_triangle_tests[k] += c.work[k][2];
+        stats->k_bbox_gates[k] += c.work[k][3];
+        stats->kd_splits += c.work[k][0];
+        stats->instance_tests += c.work[k][1];
+        stats->triangle_tests += c.work[k][2];
+        stats->bbox_gates += c.work[k][3];
+    }
     stats->shaded_hits += c.shaded_hits;
     stats->texel_lookups += c.texel_lookups;
     stats->nodes_total += std::min<uint32_t>(c.pool_count, 0xFFFFFFFFu);
@@ -351,25 +404,9 @@ int pt_frame_create(PtScene* scene, const PtCamera* camera, const PtRenderParams
     f->max_depth = effective_max_depth(p);
     f->n_levels = scene->has_reflective ? (int)f->max_depth + 1 : 1;
 
-    // owned pixels: interleaved tiles, 8x4 micro-tiles inside a tile so that a warp covers a compact block
-    const uint32_t tw = p.tile_w ? p.tile_w : 32, th = p.tile_h ? p.tile_h : 32;
-    const uint32_t tiles_x = (p.width + tw - 1) / tw, tiles_y = (p.height + th - 1) / th;
-    const uint32_t world = p.world > 1 ? p.world : 1;
-    for (uint32_t ty = 0; ty < tiles_y; ++ty)
-        for (uint32_t tx = 0; tx < tiles_x; ++tx) {
-            const uint64_t tile = (uint64_t)ty * tiles_x + tx;
-            if (tile % world != (world > 1 ? p.rank : 0)) continue;
-            const uint32_t x0 = tx * tw, y0 = ty * th;
-            for (uint32_t my = 0; my < th; my += 4)
-                for (uint32_t mx = 0; mx < tw; mx += 8)
-                    for (uint32_t dy = 0; dy < 4 && my + dy < th; ++dy)
-                        for (uint32_t dx = 0; dx < 8 && mx + dx < tw; ++dx) {
-                            const uint32_t x = x0 + mx + dx, y = y0 + my + dy;
-                            if (x >= p.width || y >= p.height) continue;
-                            if (x < p.x1 || x > p.x2 || y < p.y1 || y > p.y2) continue;  // render.rs:136-138
-                            f->pixel_index.push_back(y * p.width + x);
-                        }
-        }
+    // owned pixels: interleaved tiles, 8x4 micro-tiles inside a tile (tiles.c)
+    f->pixel_index.resize(pt_owned_pixels(&p, nullptr, 0));
+    pt_owned_pixels(&p, f->pixel_index.data(), f->pixel_index.size());
     const uint64_t owned = f->pixel_index.size();
 
     f->bg_doubles = p.bg_mode == PT_BG_PER_PIXEL ? (uint64_t)p.width * p.height * 3
@@ -445,6 +482,8 @@ int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* u
         stats->h2d_ms = h2d_ms; stats->d2h_ms = d2h_ms; stats->h2d_bytes = h2d_b; stats->d2h_bytes = d2h_b;
     }
     uint32_t launches = 0, batches = 0, retries = 0, error_bits = 0;
+    KernelTimer timer;
+    if (f->params.flags & PT_RENDER_KERNEL_TIMES) timer.events = &f->kernel_events;
 
     CUDA_TRY(cudaEventRecord(f->ev_start, st));
     uint32_t first_slot = 0;
@@ -455,8 +494,9 @@ int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* u
         launch_begin_batch(f->d_ctl, n_paths, st);
         launch_camera(fp, f->pool, first_slot, n_paths, st);
         launches += 2;
-        int rc = run_levels(sc, fp, f->pool, f->d_ctl, f->h_ctl, first_slot, n_paths, f->n_levels, count, st, &launches);
+        int rc = run_levels(sc, fp, f->pool, f->d_ctl, f->h_ctl, first_slot, n_paths, f->n_levels, count, st, &launches, &timer);
         if (rc != PT_OK) return rc;
+        timer.collect(stats);
         if (f->h_ctl->error_bits & PT_DEVERR_OVERFLOW) {
             // the ray trees of this batch do not fit: halve the batch and redo it (results do not depend on batching)
             if (n_slots == 1) return fail(PT_ERR_OVERFLOW, "%s", panic_text(PT_ERR_OVERFLOW));
@@ -606,7 +646,8 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
         const uint32_t n_paths = (uint32_t)std::min<uint64_t>(step, n - first);
         launch_begin_batch(d_ctl, n_paths, g_stream);
         launch_load_rays(d_o, d_d, pool, (uint32_t)first, n_paths, g_stream);
-        rc = run_levels(scene->view, fp, pool, d_ctl, h_ctl, (uint32_t)first, n_paths, n_levels, count, g_stream, &launches);
+        KernelTimer timer;
+        rc = run_levels(scene->view, fp, pool, d_ctl, h_ctl, (uint32_t)first, n_paths, n_levels, count, g_stream, &launches, &timer);
         if (rc != PT_OK) break;
         if (h_ctl->error_bits & PT_DEVERR_OVERFLOW) {
             if (n_paths == 1) { rc = fail(PT_ERR_OVERFLOW, "%s", panic_text(PT_ERR_OVERFLOW)); break; }

@@ -67,7 +67,7 @@ struct BatchCtl {
     uint32_t error_bits;       // PT_DEVERR_*
     uint32_t blocks_done[16];  // per level "last block" tickets of the shade kernel
     unsigned long long rays_shadow, rays_reflect, rays_refract, rays_depth_cut, shaded_hits, texel_lookups;
-    unsigned long long kd_splits, instance_tests, triangle_tests, bbox_gates;
+    unsigned long long work[2][4];  // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates]
 };
 
 // per-frame constants

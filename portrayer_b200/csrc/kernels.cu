@@ -35,7 +35,7 @@ PT_D void background_of(const FrameParams& fp, uint32_t pixel, double* bg) {
 }
 
 // warp-aggregated add of per-thread work counters into the batch control block
-PT_D void flush_counters(BatchCtl* ctl, const WorkCounters& wc) {
+PT_D void flush_counters(BatchCtl* ctl, int kind, const WorkCounters& wc) {
     unsigned long long v[4] = {wc.kd_splits, wc.instance_tests, wc.triangle_tests, wc.bbox_gates};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -43,10 +43,9 @@ PT_D void flush_counters(BatchCtl* ctl, const WorkCounters& wc) {
         for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xFFFFFFFFu, v[k], off);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (v[0]) atomicAdd(&ctl->kd_splits, v[0]);
-        if (v[1]) atomicAdd(&ctl->instance_tests, v[1]);
-        if (v[2]) atomicAdd(&ctl->triangle_tests, v[2]);
-        if (v[3]) atomicAdd(&ctl->bbox_gates, v[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (v[k]) atomicAdd(&ctl->work[kind][k], v[k]);
     }
 }
 
@@ -108,7 +107,7 @@ __global__ void __launch_bounds__(kBlock) extend_kernel(DScene sc, NodePool pool
         pool.sub[i] = found ? hit.sub : 0u;
     }
     if (err) atomicOr(&ctl->error_bits, err);
-    if (COUNT) flush_counters(ctl, wc);
+    if (COUNT) flush_counters(ctl, 0, wc);
 }
 
 // ------------------------------------------------------------------ shadow (any hit), light-major
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(DScene sc, FrameParams f
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cast += __shfl_down_sync(0xFFFFFFFFu, cast, off);
     if ((threadIdx.x & 31) == 0 && cast) atomicAdd(&ctl->rays_shadow, cast);
-    if (COUNT) flush_counters(ctl, wc);
+    if (COUNT) flush_counters(ctl, 1, wc);
 }
 
 // ------------------------------------------------------------------ shade
@@ -520,10 +519,11 @@ __global__ void __launch_bounds__(kBlock) export_rays_kernel(NodePool pool, uint
 }
 
 __global__ void begin_batch_kernel(BatchCtl* ctl, uint32_t n_paths) {
-    if (threadIdx.x < 16) {
-        ctl->level_start[threadIdx.x] = threadIdx.x == 0 ? 0u : n_paths;
-        ctl->blocks_done[threadIdx.x] = 0u;
-    }
+    // the whole control block starts from zero: error bits and counters are per batch
+    uint32_t* words = reinterpret_cast<uint32_t*>(ctl);
+    for (uint32_t i = threadIdx.x; i < sizeof(BatchCtl) / 4; i += blockDim.x) words[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x < 16) ctl->level_start[threadIdx.x] = threadIdx.x == 0 ? 0u : n_paths;
     if (threadIdx.x == 0) ctl->pool_count = n_paths;
 }
 
