@@ -339,7 +339,9 @@ def run_ours(args, rank, world, local_rank):
         return rays, h2d, d2h
 
     e2e = None
-    if world == 1:
+    if args.device_only:
+        pass
+    elif world == 1:
         for _ in range(2):
             e2e_step()
         barrier()
@@ -423,7 +425,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample
     cpu = None
-    if world == 1:
+    if world == 1 and not args.device_only:
         from oracle import binding as oracle
 
         threads = host_threads()
@@ -464,6 +466,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="configs1")
     ap.add_argument("--samples", type=int, default=0, help="samples per pixel at N=1 (default: the workload's)")
+    ap.add_argument("--device-only", action="store_true", help="skip the e2e and cpu_baseline legs (for runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Summarise ncu output into the small text files kept under profiles/.
+
+    python tools/ncu_summary.py launches gpurun_out/launches.csv          > profiles/rNN_launches.txt
+    python tools/ncu_summary.py report   gpurun_out/prof.ncu-rep          > profiles/rNN_kernels.txt
+    python tools/ncu_summary.py stalls   gpurun_out/prof.ncu-rep [kernel] > profiles/rNN_stalls.txt
+
+`launches` reads the CSV of `ncu --metrics gpu__time_duration.sum --csv`; `report` / `stalls` call
+`ncu -i <rep> --page raw|source --csv` (ncu is in the image; no GPU needed to read a report).
+"""
+from __future__ import annotations
+
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_bytes_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_local_op_st.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+]
+
+
+def ncu_page(rep: str, page: str) -> list[list[str]]:
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True, check=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
+def launches(path: str) -> None:
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        v = v / 1000 if r[ui] == "ns" else v * 1000 if r[ui] == "ms" else v
+        name = r[ki].split("(")[0].replace("void ", "").replace("ptd::<unnamed>::", "")
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"# {path}: {sum(v[0] for v in agg.values())} launches, {tot:.1f} us serialised device time (cold cache, under ncu)")
+    print(f"{'kernel':58s} {'n':>5s} {'total_us':>10s} {'share':>7s} {'avg_us':>8s}")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k[:58]:58s} {v[0]:5d} {v[1]:10.1f} {v[1] / tot:7.3f} {v[1] / v[0]:8.1f}")
+
+
+def report(rep: str) -> None:
+    rows = ncu_page(rep, "raw")
+    hdr, units = rows[0], rows[1]
+    name_i = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        print("== " + r[name_i].replace("ptd::<unnamed>::", "")[:110] + "  grid " + r[hdr.index("Grid Size")] + " block " + r[hdr.index("Block Size")])
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"   {k:82s} {r[i]:>16s} {units[i]}")
+
+
+def stalls(rep: str, kernel: str | None) -> None:
+    rows = ncu_page(rep, "source")
+    # the source page is a sequence of per-kernel tables; keep the top source lines by sampled stalls
+    hdr = None
+    cur = None
+    tables = []
+    for r in rows:
+        if r and r[0] in ("#", "Source") or (r and "Source" in r and "# Samples" in " ".join(r)):
+            hdr = r
+            cur = []
+            tables.append((hdr, cur))
+        elif hdr is not None and len(r) == len(hdr):
+            cur.append(r)
+    for hdr, body in tables:
+        cols = {c: i for i, c in enumerate(hdr)}
+        samp = next((c for c in hdr if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)"), None)
+        src = "Source" if "Source" in cols else hdr[1]
+        if samp is None:
+            continue
+
+        def val(r):
+            try:
+                return float(r[cols[samp]].replace(",", ""))
+            except ValueError:
+                return 0.0
+
+        tot = sum(val(r) for r in body) or 1.0
+        print(f"== table with {len(body)} lines, {tot:.0f} samples ({samp})")
+        for r in sorted(body, key=val, reverse=True)[:25]:
+            print(f"   {val(r) / tot:6.3f}  {r[cols[src]].strip()[:140]}")
+
+
+def main() -> None:
+    mode = sys.argv[1]
+    if mode == "launches":
+        launches(sys.argv[2])
+    elif mode == "report":
+        report(sys.argv[2])
+    elif mode == "stalls":
+        stalls(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
+    else:
+        raise SystemExit(__doc__)
+
+
+if __name__ == "__main__":
+    main()
