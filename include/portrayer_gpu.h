@@ -164,11 +164,18 @@ typedef struct PtLight {
     double pad;
 } PtLight;
 
-/* RGB8 row-major image in the texel pool (RgbImageBuffer, src/texture.rs:78-80). */
+/* RGB8 row-major image in the texel pool (RgbImageBuffer, src/texture.rs:78-80).  32 bytes.
+ * key: 0, or a caller-chosen identity of the image CONTENT (the Rust glue passes the address of the
+ * Arc<Texture>'s RgbImageBuffer; the host mirror a hash of the file path + size).  Textures with a
+ * non-zero key stay resident in HBM between scenes: a later pt_scene_upload that carries the same
+ * (key, width, height) does not copy those texels to the device again.  The caller guarantees that
+ * equal keys mean equal texels (textures are immutable once loaded in the reference, texture.rs:96-102). */
 typedef struct PtTexture {
     uint32_t width;
     uint32_t height;
     uint64_t offset; /* byte offset into the texel pool */
+    uint64_t key;
+    uint64_t reserved;
 } PtTexture;
 
 /* Pointer form of a prepared scene: what the Rust glue fills from KDTreeScene. */
@@ -195,7 +202,7 @@ typedef struct PtSceneDesc {
  * 128-byte aligned, offsets from the start of the blob.  This is what crosses
  * NVLink verbatim when the scene is broadcast to the other ranks. */
 #define PT_BLOB_MAGIC 0x43535450u /* "PTSC" */
-#define PT_BLOB_VERSION 2u
+#define PT_BLOB_VERSION 3u
 
 typedef struct PtBlobHeader {
     uint32_t magic;
@@ -265,7 +272,9 @@ typedef struct PtRenderParams {
 
 #define PT_RENDER_COUNTERS 1u  /* run the counting variant of the traversal kernels (fills PtStats work counters) */
 #define PT_RENDER_LINEAR_TLAS 2u /* ignore the scene kd-tree: FlatScene linear scan, flat_scene.rs:71-99 + ray.rs:87-99 */
-#define PT_RENDER_KERNEL_TIMES 4u /* bracket every extend / shadow / shade launch with CUDA events (fills PtStats.ms_*) */
+#define PT_RENDER_KERNEL_TIMES 4u /* bracket every extend / shadow / shade launch with CUDA events (fills PtStats.ms_*); uses the stream path */
+#define PT_RENDER_ROW_MAJOR 8u    /* pt_frame_*: device outputs are full-image row-major (W*H entries) instead of compact owned-pixel order; world <= 1 only */
+#define PT_RENDER_NO_GRAPH 16u    /* launch kernel by kernel on the stream (one host check per recursion level) instead of replaying the frame's CUDA graph */
 
 typedef struct PtStats {
     /* rays = every ray_cast issued against the scene root */
@@ -302,6 +311,11 @@ void pt_shutdown(void);
 const char* pt_last_error(void);
 const char* pt_error_string(int code);   /* the reference's panic text for PT_ERR_* */
 int pt_device_count(void);
+/* The library keeps device buffers (node pools, frames, resident textures) cached between calls;
+ * this returns them to the driver. */
+void pt_release_cached_memory(void);
+/* bytes of texels currently resident in the texture cache */
+uint64_t pt_resident_texture_bytes(void);
 
 /* ---- scene (replaces nothing in the reference: it is the glue's output) ---- */
 /* bytes needed to pack desc; pack it. Pure host code, works without a GPU. */
@@ -309,10 +323,18 @@ uint64_t pt_scene_blob_size(const PtSceneDesc* desc);
 int pt_scene_pack(const PtSceneDesc* desc, void* blob_out, uint64_t capacity);
 /* validate a blob and view it as a desc (pointers into the blob). Host only. */
 int pt_scene_unpack(const void* blob, uint64_t bytes, PtSceneDesc* desc_out);
+/* the same for a blob cut off at its texel section (bytes >= off_texels; desc_out->texels = NULL): what a caller
+ * sends when every texture carries a key and is already resident on the device. Host only. */
+int pt_scene_unpack_records(const void* blob, uint64_t bytes, PtSceneDesc* desc_out);
 
-int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out);        /* host blob -> device */
-int pt_scene_upload_device(const void* d_blob, uint64_t bytes, PtScene** out); /* blob already in HBM (after the NCCL broadcast) */
+/* host blob -> device.  The record sections are copied verbatim; textures with a key that is already resident are
+ * not copied again.  `bytes` may stop at header.off_texels (records-only upload) when every texture is resident,
+ * otherwise PT_ERR_INVALID names the missing texture. */
+int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out);
+int pt_scene_upload_device(const void* d_blob, uint64_t bytes, PtScene** out); /* blob already in HBM (after the NCCL broadcast); same rules */
 void pt_scene_free(PtScene* scene);
+/* bytes pt_scene_upload copied host -> device for this scene (records + the textures that were not resident) */
+uint64_t pt_scene_uploaded_bytes(const PtScene* scene);
 
 /* ---- render: replaces ImageSliceMut::render's pixel loop, render.rs:127-150 ---- */
 /* One blocking call with HOST buffers (the call the Rust shim makes).

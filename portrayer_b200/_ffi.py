@@ -38,6 +38,7 @@ PT_ERR_KD_PLANE_MISS, PT_ERR_TIR_INSIDE, PT_ERR_KD_TOO_DEEP, PT_ERR_OVERFLOW = -
 PT_RNG_FIXED, PT_RNG_HASH = 0, 1
 PT_BG_PER_PIXEL, PT_BG_PER_ROW, PT_BG_CONSTANT = 0, 1, 2
 PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS, PT_RENDER_KERNEL_TIMES = 1, 2, 4
+PT_RENDER_ROW_MAJOR, PT_RENDER_NO_GRAPH = 8, 16
 PT_EPSILON = 0.00001
 PT_MAX_RECURSION_DEPTH = 10
 PT_DEFAULT_SAMPLES = 100
@@ -128,12 +129,16 @@ GPU_SYMBOLS = {
     "pt_last_error": (C.c_char_p, []),
     "pt_error_string": (C.c_char_p, [C.c_int]),
     "pt_device_count": (C.c_int, []),
+    "pt_release_cached_memory": (None, []),
+    "pt_resident_texture_bytes": (C.c_uint64, []),
     "pt_scene_blob_size": (C.c_uint64, [C.c_void_p]),
     "pt_scene_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "pt_scene_unpack": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "pt_scene_unpack_records": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "pt_scene_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "pt_scene_upload_device": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "pt_scene_free": (None, [C.c_void_p]),
+    "pt_scene_uploaded_bytes": (C.c_uint64, [C.c_void_p]),
     "pt_render": (C.c_int, [C.c_void_p, C.POINTER(PtCamera), C.POINTER(PtRenderParams), C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PtStats)]),
     "pt_trace_rays": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,

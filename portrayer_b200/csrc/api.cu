@@ -1,13 +1,27 @@
 // C ABI of libportrayer_gpu.so (include/portrayer_gpu.h): scene upload, frame
 // management and the batch loop that drives the wavefront kernels.
+//
+// Runtime design (DESIGN.md "host runtime"):
+//   * one library context per process: a stream, a caching device arena (node pools and frame
+//     buffers are reused between calls, no cudaMalloc/cudaFree in steady state), a pinned host
+//     arena for control blocks and staging, and a texture residency cache keyed by PtTexture.key;
+//   * a frame's kernels read everything from a __constant__ FrameState slot, so the frame owns
+//     ONE CUDA graph — camera -> WHILE(level has rays){extend, shadow, shade} -> tree_eval ->
+//     resolve — that is replayed for any scene / camera after one small async copy;
+//   * pt_render enqueues background H2D, the graph(s), the control-block and image D2H on one
+//     stream and synchronises once.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.h"
@@ -20,6 +34,8 @@ namespace {
 thread_local std::string g_error;
 cudaStream_t g_stream = nullptr;
 bool g_initialised = false;
+std::recursive_mutex g_mu;  // the ABI is blocking and serialised: one render at a time per process
+using Lock = std::lock_guard<std::recursive_mutex>;
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -46,43 +62,159 @@ int ensure_init() {
     return pt_init(-1);
 }
 
+// ------------------------------------------------------------------ caching arenas
+// Freed blocks are kept and handed out again to requests of a similar size.  The hot path of a
+// renderer allocates the same few shapes over and over (node pool, frame buffers, scene records).
+template <bool PINNED>
+class Arena {
+public:
+    void* alloc(size_t bytes, cudaError_t* err) {
+        bytes = (std::max<size_t>(bytes, 1) + 511) & ~size_t(511);
+        auto it = free_.lower_bound(bytes);
+        if (it != free_.end() && it->first <= bytes + bytes / 4 + (size_t(1) << 16)) {
+            void* p = it->second;
+            live_[p] = it->first;
+            cached_ -= it->first;
+            free_.erase(it);
+            *err = cudaSuccess;
+            return p;
+        }
+        void* p = nullptr;
+        *err = raw_alloc(&p, bytes);
+        if (*err != cudaSuccess) {  // give cached blocks back to the driver and retry once
+            cudaGetLastError();
+            trim();
+            *err = raw_alloc(&p, bytes);
+        }
+        if (*err != cudaSuccess) return nullptr;
+        live_[p] = bytes;
+        return p;
+    }
+    void release(void* p) {
+        if (!p) return;
+        auto it = live_.find(p);
+        if (it == live_.end()) return;
+        free_.emplace(it->second, p);
+        cached_ += it->second;
+        live_.erase(it);
+        while (cached_ > limit_ && !free_.empty()) {  // drop the largest idle blocks first
+            auto last = std::prev(free_.end());
+            raw_free(last->second);
+            cached_ -= last->first;
+            free_.erase(last);
+        }
+    }
+    void trim() {
+        for (auto& kv : free_) raw_free(kv.second);
+        free_.clear();
+        cached_ = 0;
+    }
+    void set_limit(size_t bytes) { limit_ = bytes; }
+
+private:
+    static cudaError_t raw_alloc(void** p, size_t bytes) { return PINNED ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes); }
+    static void raw_free(void* p) {
+        if (PINNED) cudaFreeHost(p);
+        else cudaFree(p);
+    }
+    std::multimap<size_t, void*> free_;
+    std::unordered_map<void*, size_t> live_;
+    size_t cached_ = 0;
+    size_t limit_ = size_t(24) << 30;
+};
+
+Arena<false> g_dev;
+Arena<true> g_pin;
+
+// ------------------------------------------------------------------ texture residency cache
+struct ResidentTexture {
+    uint8_t* d_texels = nullptr;
+    uint64_t bytes = 0;
+    uint32_t width = 0, height = 0;
+    uint32_t refs = 0;
+    uint64_t last_use = 0;
+};
+std::unordered_map<uint64_t, ResidentTexture> g_textures;
+uint64_t g_texture_bytes = 0, g_texture_tick = 0;
+uint64_t g_texture_limit = uint64_t(32) << 30;  // of 180 GB
+
+void evict_textures(uint64_t need) {
+    while (g_texture_bytes + need > g_texture_limit) {
+        uint64_t best_key = 0, best_tick = ~0ull;
+        for (auto& kv : g_textures)
+            if (kv.second.refs == 0 && kv.second.last_use < best_tick) { best_tick = kv.second.last_use; best_key = kv.first; }
+        if (best_tick == ~0ull) return;
+        auto it = g_textures.find(best_key);
+        g_dev.release(it->second.d_texels);
+        g_texture_bytes -= it->second.bytes;
+        g_textures.erase(it);
+    }
+}
+
+uint32_t g_slots_used = 0;  // bitmap of __constant__ FrameState slots in use
+int take_slot() {
+    for (int i = 0; i < kStateSlots - 1; ++i)
+        if (!(g_slots_used & (1u << i))) { g_slots_used |= 1u << i; return i; }
+    return kStateSlots - 1;  // shared overflow slot: state is re-uploaded before every render
+}
+void give_slot(int slot) {
+    if (slot >= 0 && slot < kStateSlots - 1) g_slots_used &= ~(1u << slot);
+}
+
 }  // namespace
 
 struct PtScene {
-    unsigned char* d_blob = nullptr;
+    unsigned char* d_records = nullptr;  // blob sections [0, off_texels) (+ inline texels when not cached)
     uint64_t bytes = 0;
     PtBlobHeader h{};
     DScene view{};
     bool has_reflective = false;
-    PtFrame* cached_frame = nullptr;
-    PtRenderParams cached_params{};
-    PtCamera cached_cam{};
+    TextureDev* d_textures = nullptr;
+    std::vector<uint64_t> resident_keys;    // textures held in the residency cache (refs to drop)
+    std::vector<uint8_t*> private_texels;   // unkeyed textures owned by this scene
+    uint64_t h2d_bytes = 0;                 // bytes the upload copied to the device
 };
 
 struct PtFrame {
     PtScene* scene = nullptr;
     PtCamera cam{};
     PtRenderParams params{};
+    bool row_major = false;
     std::vector<uint32_t> pixel_index;  // owned slot -> global pixel
     uint32_t* d_pixel_index = nullptr;
     double* d_background = nullptr;
     uint64_t bg_doubles = 0;
+    uint64_t out_pixels = 0;  // entries of the output buffers (owned pixels, or W*H when row-major)
     uint8_t* d_rgb = nullptr;
     uint32_t* d_hit_id = nullptr;
     double* d_hit_t = nullptr;
     // node pool
     unsigned char* d_pool = nullptr;
     NodePool pool{};
+    uint32_t n_lights_cap = 0;
+    bool reflective_cap = false;
     uint32_t batch_slots = 0;  // owned pixels per batch
     BatchCtl* d_ctl = nullptr;
-    BatchCtl* h_ctl = nullptr;  // pinned
+    BatchCtl* h_ctl = nullptr;  // pinned ring, one per batch
+    uint32_t h_ctl_count = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     std::vector<cudaEvent_t> kernel_events;  // PT_RENDER_KERNEL_TIMES: begin/end pairs, reused per batch
     uint32_t max_depth = PT_MAX_RECURSION_DEPTH;
     int n_levels = 1;
+    // __constant__ slot + graph
+    int slot = -1;
+    cudaGraph_t graph[2] = {nullptr, nullptr};  // [0] plain, [1] counting kernels
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    cudaGraphNode_t camera_node[2] = {nullptr, nullptr};
+    bool graph_failed = false;
+    uint64_t last_use = 0;
 };
 
 namespace {
+
+std::vector<PtFrame*> g_frame_cache;  // frames pt_render keeps between calls (LRU, small)
+uint64_t g_frame_tick = 0;
+constexpr size_t kFrameCacheMax = 6;
 
 const char* panic_text(int code) {
     switch (code) {
@@ -110,7 +242,7 @@ int device_error_to_code(uint32_t bits) {
 void fill_view(PtScene* s) {
     const PtBlobHeader& h = s->h;
     DScene& v = s->view;
-    unsigned char* b = s->d_blob;
+    unsigned char* b = s->d_records;
     v.tlas_nodes = reinterpret_cast<const PtKdNode*>(b + h.off_tlas_nodes);
     v.tlas_items = reinterpret_cast<const uint32_t*>(b + h.off_tlas_items);
     v.instances = reinterpret_cast<const PtInstance*>(b + h.off_instances);
@@ -123,8 +255,7 @@ void fill_view(PtScene* s) {
     v.tri_uvs = reinterpret_cast<const PtTriUvs*>(b + h.off_tri_uvs);
     v.materials = reinterpret_cast<const PtMaterial*>(b + h.off_materials);
     v.lights = reinterpret_cast<const PtLight*>(b + h.off_lights);
-    v.textures = reinterpret_cast<const PtTexture*>(b + h.off_textures);
-    v.texels = b + h.off_texels;
+    v.textures = s->d_textures;
     v.ambient[0] = h.ambient[0]; v.ambient[1] = h.ambient[1]; v.ambient[2] = h.ambient[2];
     v.tlas_extent = h.tlas_extent;
     v.n_lights = h.n_lights;
@@ -133,34 +264,115 @@ void fill_view(PtScene* s) {
     v.n_tlas_items = h.n_tlas_items;
 }
 
-// validate on the host copy, then keep what the host needs to know about the scene
-int adopt_header(PtScene* s, const void* host_blob, uint64_t bytes) {
+void free_scene(PtScene* s) {
+    if (!s) return;
+    for (uint64_t key : s->resident_keys) {
+        auto it = g_textures.find(key);
+        if (it != g_textures.end() && it->second.refs > 0) --it->second.refs;
+    }
+    for (uint8_t* p : s->private_texels) g_dev.release(p);
+    g_dev.release(s->d_textures);
+    g_dev.release(s->d_records);
+    delete s;
+}
+
+// Validate the records on the host; `texels_present` says whether the blob carries its texel section.
+int adopt_header(PtScene* s, const void* host_blob, uint64_t bytes, bool* texels_present) {
+    if (bytes < sizeof(PtBlobHeader)) return fail(PT_ERR_INVALID, "malformed scene blob");
+    PtBlobHeader h;
+    memcpy(&h, host_blob, sizeof h);
+    if (h.magic != PT_BLOB_MAGIC || h.version != PT_BLOB_VERSION) return fail(PT_ERR_INVALID, "malformed scene blob (magic / version)");
+    *texels_present = bytes >= h.total_bytes;
     PtSceneDesc d;
-    int rc = pt_scene_unpack(host_blob, bytes, &d);
+    int rc = *texels_present ? pt_scene_unpack(host_blob, bytes, &d) : pt_scene_unpack_records(host_blob, bytes, &d);
     if (rc != PT_OK) return fail(rc, "malformed scene blob");
-    memcpy(&s->h, host_blob, sizeof s->h);
-    if (s->h.tlas_depth > PT_MAX_KD_STACK || s->h.blas_max_depth > PT_MAX_KD_STACK)
-        return fail(PT_ERR_KD_TOO_DEEP, "kd-tree depth %u / %u exceeds PT_MAX_KD_STACK = %d", s->h.tlas_depth,
-                    s->h.blas_max_depth, PT_MAX_KD_STACK);
     s->has_reflective = false;
     for (uint32_t i = 0; i < d.n_materials; ++i)
         if (d.materials[i].reflectivity > 0.0) s->has_reflective = true;
+    s->h = h;
+    if (h.tlas_depth > PT_MAX_KD_STACK || h.blas_max_depth > PT_MAX_KD_STACK)
+        return fail(PT_ERR_KD_TOO_DEEP, "kd-tree depth %u / %u exceeds PT_MAX_KD_STACK = %d", h.tlas_depth, h.blas_max_depth,
+                    PT_MAX_KD_STACK);
     return PT_OK;
+}
+
+// Bind every texture of the scene to device texels: resident copy (by key), or a fresh upload from
+// `texel_src` (host or device pointer to the blob's texel section; nullptr = records-only upload).
+int bind_textures(PtScene* s, const PtTexture* tex, const unsigned char* texel_src, cudaMemcpyKind kind) {
+    const uint32_t n = s->h.n_textures;
+    if (n == 0) return PT_OK;
+    std::vector<TextureDev> table(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const PtTexture& t = tex[i];
+        const uint64_t bytes = (uint64_t)t.width * t.height * 3;
+        if (t.width == 0 || t.height == 0) return fail(PT_ERR_INVALID, "texture %u is empty", i);
+        uint8_t* d = nullptr;
+        if (t.key != 0) {
+            auto it = g_textures.find(t.key);
+            if (it != g_textures.end() && it->second.width == t.width && it->second.height == t.height) {
+                d = it->second.d_texels;
+                ++it->second.refs;
+                it->second.last_use = ++g_texture_tick;
+                s->resident_keys.push_back(t.key);
+            }
+        }
+        if (!d) {
+            if (!texel_src) return fail(PT_ERR_INVALID, "texture %u (key %llx) is not resident and the blob carries no texels", i,
+                                        (unsigned long long)t.key);
+            if (t.offset > s->h.n_texel_bytes || bytes > s->h.n_texel_bytes - t.offset)
+                return fail(PT_ERR_INVALID, "texture %u lies outside the texel pool", i);
+            if (t.key != 0) evict_textures(bytes);
+            cudaError_t e;
+            d = static_cast<uint8_t*>(g_dev.alloc(bytes, &e));
+            if (!d) return fail(PT_ERR_CUDA, "texture allocation failed: %s", cudaGetErrorString(e));
+            e = cudaMemcpyAsync(d, texel_src + t.offset, bytes, kind, g_stream);
+            if (e != cudaSuccess) { g_dev.release(d); return fail(PT_ERR_CUDA, "texture upload failed: %s", cudaGetErrorString(e)); }
+            if (kind == cudaMemcpyHostToDevice) s->h2d_bytes += bytes;
+            if (t.key != 0 && g_textures.find(t.key) == g_textures.end()) {
+                ResidentTexture r;
+                r.d_texels = d; r.bytes = bytes; r.width = t.width; r.height = t.height; r.refs = 1; r.last_use = ++g_texture_tick;
+                g_textures.emplace(t.key, r);
+                g_texture_bytes += bytes;
+                s->resident_keys.push_back(t.key);
+            } else {
+                s->private_texels.push_back(d);
+            }
+        }
+        table[i] = TextureDev{t.width, t.height, d};
+    }
+    cudaError_t e;
+    s->d_textures = static_cast<TextureDev*>(g_dev.alloc(n * sizeof(TextureDev), &e));
+    if (!s->d_textures) return fail(PT_ERR_CUDA, "texture table allocation failed: %s", cudaGetErrorString(e));
+    // pageable source: the copy is staged before the call returns, so `table` may go out of scope
+    CUDA_TRY(cudaMemcpyAsync(s->d_textures, table.data(), n * sizeof(TextureDev), cudaMemcpyHostToDevice, g_stream));
+    s->h2d_bytes += n * sizeof(TextureDev);
+    return PT_OK;
+}
+
+void destroy_graphs(PtFrame* f) {
+    for (int k = 0; k < 2; ++k) {
+        if (f->exec[k]) cudaGraphExecDestroy(f->exec[k]);
+        if (f->graph[k]) cudaGraphDestroy(f->graph[k]);
+        f->exec[k] = nullptr;
+        f->graph[k] = nullptr;
+    }
 }
 
 void free_frame(PtFrame* f) {
     if (!f) return;
-    cudaFree(f->d_pixel_index);
-    cudaFree(f->d_background);
-    cudaFree(f->d_rgb);
-    cudaFree(f->d_hit_id);
-    cudaFree(f->d_hit_t);
-    cudaFree(f->d_pool);
-    cudaFree(f->d_ctl);
-    if (f->h_ctl) cudaFreeHost(f->h_ctl);
+    destroy_graphs(f);
+    g_dev.release(f->d_pixel_index);
+    g_dev.release(f->d_background);
+    g_dev.release(f->d_rgb);
+    g_dev.release(f->d_hit_id);
+    g_dev.release(f->d_hit_t);
+    g_dev.release(f->d_pool);
+    g_dev.release(f->d_ctl);
+    g_pin.release(f->h_ctl);
     if (f->ev_start) cudaEventDestroy(f->ev_start);
     if (f->ev_stop) cudaEventDestroy(f->ev_stop);
     for (cudaEvent_t e : f->kernel_events) cudaEventDestroy(e);
+    give_slot(f->slot);
     delete f;
 }
 
@@ -174,7 +386,9 @@ int alloc_pool(unsigned char** d_pool, NodePool* pool, uint32_t capacity, uint32
     for (int i = 0; i < 6; ++i) { o_u32[i] = off; off = up(off + cap * sizeof(uint32_t)); }
     o_mode = off; off = up(off + cap);
     o_occl = off; off = up(off + cap * std::max<uint32_t>(n_lights, 1));
-    CUDA_TRY(cudaMalloc(d_pool, off));
+    cudaError_t e;
+    *d_pool = static_cast<unsigned char*>(g_dev.alloc(off, &e));
+    if (!*d_pool) return fail(PT_ERR_CUDA, "node pool allocation (%zu bytes) failed: %s", off, cudaGetErrorString(e));
     unsigned char* b = *d_pool;
     double** f64[12] = {&pool->ox, &pool->oy, &pool->oz, &pool->dx, &pool->dy, &pool->dz,
                         &pool->t,  &pool->cr, &pool->cg, &pool->cb, &pool->refl, &pool->fres};
@@ -202,6 +416,20 @@ FrameParams frame_params(const PtFrame* f) {
     fp.seed = f->params.seed;
     fp.max_depth = f->max_depth;
     return fp;
+}
+
+FrameState frame_state(const PtFrame* f) {
+    FrameState st{};
+    st.sc = f->scene->view;
+    st.fp = frame_params(f);
+    st.pool = f->pool;
+    st.ctl = f->d_ctl;
+    st.rgb = f->d_rgb;
+    st.hit_id = f->d_hit_id;
+    st.hit_t = f->d_hit_t;
+    st.row_major = f->row_major ? 1u : 0u;
+    st.n_levels = (uint32_t)f->n_levels;
+    return st;
 }
 
 // Optional per-kernel timing: one begin/end event pair per extend / shadow / shade launch.
@@ -240,30 +468,31 @@ struct KernelTimer {
     }
 };
 
-// Run one batch of `n_paths` root rays (already written into level 0) through every level.
-// Returns the control block in h_ctl (after a stream sync).
-int run_levels(const DScene& sc, const FrameParams& fp, const NodePool& pool, BatchCtl* d_ctl, BatchCtl* h_ctl,
-               uint32_t first_slot, uint32_t n_paths, int n_levels, bool count, cudaStream_t st, uint32_t* launches,
-               KernelTimer* timer) {
+// Stream path: run the levels of one batch kernel by kernel; the host looks at the control block after every
+// level and stops at the first level without rays.  Leaves the final control block in *h_ctl.
+int run_levels_stream(int slot, uint32_t n_lights, uint64_t capacity, BatchCtl* d_ctl, BatchCtl* h_ctl, uint32_t n_paths,
+                      int n_levels, bool count, cudaStream_t st, uint32_t* launches, KernelTimer* timer) {
     for (int level = 0; level < n_levels; ++level) {
         // level d holds at most n_paths * 2^d rays, and never more than the pool
-        unsigned long long bound = (unsigned long long)n_paths << std::min(level, 31);
-        const uint32_t max_items = (uint32_t)std::min<unsigned long long>(bound, pool.capacity);
+        const uint64_t bound = (uint64_t)n_paths << std::min(level, 31);
+        const uint64_t max_items = std::min<uint64_t>(bound, capacity);
         timer->begin(0, st);
-        launch_extend(sc, pool, d_ctl, level, max_items, count, st);
+        launch_extend(slot, max_items, count, st);
         timer->end(st);
-        if (sc.n_lights) {
+        if (n_lights) {
             timer->begin(1, st);
-            launch_shadow(sc, fp, pool, d_ctl, level, first_slot, max_items, count, st);
+            launch_shadow(slot, max_items, n_lights, count, st);
             timer->end(st);
         }
         timer->begin(2, st);
-        launch_shade(sc, fp, pool, d_ctl, level, first_slot, max_items, st);
+        launch_shade(slot, max_items, 0, st);
         timer->end(st);
-        *launches += sc.n_lights ? 3 : 2;
+        *launches += n_lights ? 3 : 2;
+        CUDA_TRY(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_ctl->error_bits & PT_DEVERR_OVERFLOW) break;
+        if (h_ctl->level_start[level + 2] <= h_ctl->level_start[level + 1]) break;  // next level is empty
     }
-    CUDA_TRY(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     return PT_OK;
 }
@@ -287,10 +516,195 @@ void accumulate_stats(PtStats* stats, const BatchCtl& c, uint32_t n_paths) {
     }
     stats->shaded_hits += c.shaded_hits;
     stats->texel_lookups += c.texel_lookups;
-    stats->nodes_total += std::min<uint32_t>(c.pool_count, 0xFFFFFFFFu);
+    stats->nodes_total += c.pool_count;
     stats->device_error_bits |= c.error_bits & ~PT_DEVERR_OVERFLOW;
     for (uint32_t d = 0; d + 1 < 16; ++d)
         if (c.level_start[d + 1] > c.level_start[d] && d > stats->max_level) stats->max_level = d;
+}
+
+bool graphs_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PT_DISABLE_GRAPHS");
+        v = (e && *e && *e != '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+int ensure_graph(PtFrame* f, bool count) {
+    const int k = count ? 1 : 0;
+    if (f->exec[k]) return PT_OK;
+    cudaError_t e = build_frame_graph(f->slot, f->batch_slots, f->params.samples, std::max<uint32_t>(f->n_lights_cap, 1),
+                                      f->pool.capacity, count, &f->graph[k], &f->exec[k], &f->camera_node[k]);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        f->graph_failed = true;
+        return fail(PT_ERR_CUDA, "frame graph construction failed: %s", cudaGetErrorString(e));
+    }
+    return PT_OK;
+}
+
+int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, PtFrame** out) {
+    const PtRenderParams& p = *params;
+    if (p.width == 0 || p.height == 0 || p.samples == 0) return fail(PT_ERR_INVALID, "empty image or zero samples");
+    if (p.x1 >= p.width || p.x2 >= p.width || p.y1 >= p.height || p.y2 >= p.height)
+        return fail(PT_ERR_INVALID, "The positions {x: %u, y: %u} and/or {x: %u, y: %u} are not within an image with width = %u and height = %u",
+                    p.x1, p.y1, p.x2, p.y2, p.width, p.height);
+    if ((uint64_t)p.width * p.height > 0xFFFFFFF0ull) return fail(PT_ERR_INVALID, "image too large");
+    if (p.world > 1 && p.rank >= p.world) return fail(PT_ERR_INVALID, "rank %u out of range for world %u", p.rank, p.world);
+    if (p.bg_mode > PT_BG_CONSTANT || p.rng_mode > PT_RNG_HASH) return fail(PT_ERR_INVALID, "bad bg_mode / rng_mode");
+    if (effective_max_depth(p) > 13) return fail(PT_ERR_INVALID, "max_depth > 13 is not supported");
+    if ((p.flags & PT_RENDER_ROW_MAJOR) && p.world > 1)
+        return fail(PT_ERR_INVALID, "PT_RENDER_ROW_MAJOR needs world <= 1 (ranks own interleaved tiles)");
+
+    PtFrame* f = new PtFrame();
+    f->scene = scene;
+    f->cam = *camera;
+    f->params = p;
+    f->row_major = (p.flags & PT_RENDER_ROW_MAJOR) != 0;
+    f->max_depth = effective_max_depth(p);
+    f->reflective_cap = scene->has_reflective;
+    f->n_lights_cap = scene->h.n_lights;
+    f->n_levels = scene->has_reflective ? (int)f->max_depth + 1 : 1;
+    f->slot = take_slot();
+
+    // owned pixels: interleaved tiles, 8x4 micro-tiles inside a tile (tiles.c)
+    f->pixel_index.resize(pt_owned_pixels(&p, nullptr, 0));
+    pt_owned_pixels(&p, f->pixel_index.data(), f->pixel_index.size());
+    const uint64_t owned = f->pixel_index.size();
+    f->out_pixels = f->row_major ? (uint64_t)p.width * p.height : owned;
+
+    f->bg_doubles = p.bg_mode == PT_BG_PER_PIXEL ? (uint64_t)p.width * p.height * 3
+                    : p.bg_mode == PT_BG_PER_ROW ? (uint64_t)p.height * 3
+                                                 : 3;
+    // batch geometry: whole pixels per batch so a pixel's samples are summed in one place, in order
+    uint64_t max_paths = p.max_batch_paths ? p.max_batch_paths : (1ull << 22);
+    uint64_t slots = std::max<uint64_t>(1, max_paths / p.samples);
+    slots = std::min<uint64_t>(slots, std::max<uint64_t>(owned, 1));
+    if (slots * p.samples > 0x7FFFFFFFull) slots = 0x7FFFFFFFull / p.samples;
+    if (slots == 0) { free_frame(f); return fail(PT_ERR_INVALID, "samples too large"); }
+    f->batch_slots = (uint32_t)slots;
+    const uint64_t batch_paths = slots * p.samples;
+    uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * 4 : batch_paths);
+    capacity = std::max<uint64_t>(capacity, batch_paths);
+    capacity = std::min<uint64_t>(capacity, 0xFFFFFF00ull);
+    const uint64_t n_batches = owned ? (owned + slots - 1) / slots : 1;
+    f->h_ctl_count = (uint32_t)std::min<uint64_t>(n_batches, 1u << 16);
+
+    cudaError_t e = cudaSuccess;
+    auto dev = [&](size_t bytes) -> void* {
+        if (e != cudaSuccess) return nullptr;
+        return g_dev.alloc(std::max<size_t>(bytes, 16), &e);
+    };
+    f->d_pixel_index = static_cast<uint32_t*>(dev(owned * sizeof(uint32_t)));
+    f->d_background = static_cast<double*>(dev(f->bg_doubles * sizeof(double)));
+    f->d_rgb = static_cast<uint8_t*>(dev(f->out_pixels * 3));
+    f->d_ctl = static_cast<BatchCtl*>(dev(sizeof(BatchCtl)));
+    if (e == cudaSuccess) f->h_ctl = static_cast<BatchCtl*>(g_pin.alloc(sizeof(BatchCtl) * f->h_ctl_count, &e));
+    if (e == cudaSuccess) e = cudaEventCreate(&f->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&f->ev_stop);
+    if (e == cudaSuccess && owned)
+        e = cudaMemcpyAsync(f->d_pixel_index, f->pixel_index.data(), owned * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        free_frame(f);
+        return fail(PT_ERR_CUDA, "frame allocation failed: %s", cudaGetErrorString(e));
+    }
+    int rc = alloc_pool(&f->d_pool, &f->pool, (uint32_t)capacity, scene->h.n_lights);
+    if (rc != PT_OK) { free_frame(f); return rc; }
+    *out = f;
+    return PT_OK;
+}
+
+// the hit-id / hit-t outputs are optional: allocate them the first time a caller asks
+int ensure_id_buffers(PtFrame* f) {
+    cudaError_t e = cudaSuccess;
+    if (!f->d_hit_id) f->d_hit_id = static_cast<uint32_t*>(g_dev.alloc(std::max<uint64_t>(f->out_pixels, 1) * 2 * sizeof(uint32_t), &e));
+    if (e == cudaSuccess && !f->d_hit_t) f->d_hit_t = static_cast<double*>(g_dev.alloc(std::max<uint64_t>(f->out_pixels, 1) * sizeof(double), &e));
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "hit-id buffer allocation failed: %s", cudaGetErrorString(e));
+    return PT_OK;
+}
+
+// careful mode: one batch at a time, host check after every level, halve the batch on node-pool overflow
+int render_stream_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void* user, PtStats* stats, uint32_t* launches_out,
+                       uint32_t* batches_out, uint32_t* retries_out, uint32_t* error_bits_out) {
+    const bool count = (f->params.flags & PT_RENDER_COUNTERS) != 0;
+    const uint32_t owned = (uint32_t)f->pixel_index.size();
+    const uint32_t S = f->params.samples;
+    KernelTimer timer;
+    if (f->params.flags & PT_RENDER_KERNEL_TIMES) timer.events = &f->kernel_events;
+    uint32_t first_slot = 0;
+    uint32_t batch_slots = f->batch_slots;
+    while (first_slot < owned) {
+        const uint32_t n_slots = std::min(batch_slots, owned - first_slot);
+        const uint32_t n_paths = n_slots * S;
+        launch_camera(f->slot, first_slot, n_slots, S, st);
+        *launches_out += 1;
+        int rc = run_levels_stream(f->slot, f->scene->h.n_lights, f->pool.capacity, f->d_ctl, f->h_ctl, n_paths, f->n_levels, count,
+                                   st, launches_out, &timer);
+        if (rc != PT_OK) return rc;
+        timer.collect(stats);
+        if (f->h_ctl->error_bits & PT_DEVERR_OVERFLOW) {
+            // the ray trees of this batch do not fit: halve the batch and redo it (results do not depend on batching)
+            if (n_slots == 1) return fail(PT_ERR_OVERFLOW, "%s", panic_text(PT_ERR_OVERFLOW));
+            batch_slots = std::max<uint32_t>(1, n_slots / 2);
+            ++*retries_out;
+            continue;
+        }
+        launch_tree_eval(f->slot, n_paths, st);
+        launch_resolve(f->slot, n_slots, st);
+        *launches_out += 2;
+        *error_bits_out |= f->h_ctl->error_bits;
+        accumulate_stats(stats, *f->h_ctl, n_paths);
+        ++*batches_out;
+        first_slot += n_slots;
+        if (progress) progress(user, n_slots);  // reporter.report_finished_pixels, render.rs:149
+    }
+    return PT_OK;
+}
+
+// graph path: every batch is one replay of the frame graph; control blocks come back through a pinned ring and
+// are looked at once, after the single synchronisation.  Returns 1 when a batch overflowed the node pool (the
+// caller then redoes the frame on the careful path).
+int render_graph_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void* user, PtStats* stats, uint32_t* launches_out,
+                      uint32_t* batches_out, uint32_t* error_bits_out, bool* overflow) {
+    const bool count = (f->params.flags & PT_RENDER_COUNTERS) != 0;
+    const int k = count ? 1 : 0;
+    int rc = ensure_graph(f, count);
+    if (rc != PT_OK) return rc;
+    const uint32_t owned = (uint32_t)f->pixel_index.size();
+    const uint32_t S = f->params.samples;
+    const uint32_t n_batches = (owned + f->batch_slots - 1) / f->batch_slots;
+    *overflow = false;
+    std::vector<std::pair<uint32_t, uint32_t>> done;  // (n_slots, n_paths) per enqueued batch
+    uint32_t first_slot = 0;
+    for (uint32_t b = 0; b < n_batches;) {
+        // enqueue up to h_ctl_count batches, then synchronise and read their control blocks
+        const uint32_t group = std::min<uint32_t>(f->h_ctl_count, n_batches - b);
+        done.clear();
+        for (uint32_t g = 0; g < group; ++g) {
+            const uint32_t n_slots = std::min(f->batch_slots, owned - first_slot);
+            CUDA_TRY(set_graph_batch(f->exec[k], f->camera_node[k], f->slot, first_slot, n_slots, f->batch_slots, S));
+            CUDA_TRY(cudaGraphLaunch(f->exec[k], st));
+            CUDA_TRY(cudaMemcpyAsync(&f->h_ctl[g], f->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
+            done.emplace_back(n_slots, n_slots * S);
+            first_slot += n_slots;
+        }
+        if (b + group >= n_batches) CUDA_TRY(cudaEventRecord(f->ev_stop, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+        for (uint32_t g = 0; g < group; ++g) {
+            const BatchCtl& c = f->h_ctl[g];
+            if (c.error_bits & PT_DEVERR_OVERFLOW) { *overflow = true; return PT_OK; }
+            *error_bits_out |= c.error_bits;
+            accumulate_stats(stats, c, done[g].second);
+            *launches_out += 3 + c.levels_run * 3;
+            ++*batches_out;
+            if (progress) progress(user, done[g].first);
+        }
+        b += group;
+    }
+    return PT_OK;
 }
 
 }  // namespace
@@ -299,6 +713,7 @@ void accumulate_stats(PtStats* stats, const BatchCtl& c, uint32_t n_paths) {
 extern "C" {
 
 int pt_init(int device) {
+    Lock lock(g_mu);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -311,7 +726,31 @@ int pt_init(int device) {
     return PT_OK;
 }
 
+void pt_release_cached_memory(void) {
+    Lock lock(g_mu);
+    for (PtFrame* f : g_frame_cache) free_frame(f);
+    g_frame_cache.clear();
+    for (auto it = g_textures.begin(); it != g_textures.end();) {
+        if (it->second.refs == 0) {
+            g_dev.release(it->second.d_texels);
+            g_texture_bytes -= it->second.bytes;
+            it = g_textures.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    g_dev.trim();
+    g_pin.trim();
+}
+
+uint64_t pt_resident_texture_bytes(void) {
+    Lock lock(g_mu);
+    return g_texture_bytes;
+}
+
 void pt_shutdown(void) {
+    Lock lock(g_mu);
+    pt_release_cached_memory();
     if (g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
     g_initialised = false;
@@ -329,20 +768,32 @@ int pt_device_count(void) {
 // =================================================================== scene
 int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out) {
     if (!blob || !out) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
     int rc = ensure_init();
     if (rc != PT_OK) return rc;
     PtScene* s = new PtScene();
-    rc = adopt_header(s, blob, bytes);
+    bool texels_present = false;
+    rc = adopt_header(s, blob, bytes, &texels_present);
     if (rc != PT_OK) { delete s; return rc; }
-    s->bytes = s->h.total_bytes;
-    cudaError_t e = cudaMalloc(&s->d_blob, s->bytes);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_blob, blob, s->bytes, cudaMemcpyHostToDevice, g_stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    // records: everything before the texel section, verbatim
+    s->bytes = std::min<uint64_t>(s->h.off_texels, s->h.total_bytes);
+    cudaError_t e;
+    s->d_records = static_cast<unsigned char*>(g_dev.alloc(s->bytes, &e));
+    if (s->d_records) e = cudaMemcpyAsync(s->d_records, blob, s->bytes, cudaMemcpyHostToDevice, g_stream);
     if (e != cudaSuccess) {
-        cudaFree(s->d_blob);
-        delete s;
+        cudaGetLastError();
+        free_scene(s);
         return fail(PT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
     }
+    s->h2d_bytes = s->bytes;
+    const unsigned char* base = static_cast<const unsigned char*>(blob);
+    rc = bind_textures(s, reinterpret_cast<const PtTexture*>(base + s->h.off_textures),
+                       texels_present ? base + s->h.off_texels : nullptr, cudaMemcpyHostToDevice);
+    if (rc == PT_OK) {
+        e = cudaStreamSynchronize(g_stream);  // the caller may free / reuse `blob` when this returns
+        if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != PT_OK) { free_scene(s); return rc; }
     fill_view(s);
     *out = s;
     return PT_OK;
@@ -350,117 +801,84 @@ int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out) {
 
 int pt_scene_upload_device(const void* d_blob, uint64_t bytes, PtScene** out) {
     if (!d_blob || !out || bytes < sizeof(PtBlobHeader)) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
     int rc = ensure_init();
     if (rc != PT_OK) return rc;
     // The records are validated on a host copy (a few MB at most for the reference's scenes; the texel pool is skipped).
     PtBlobHeader h;
     CUDA_TRY(cudaMemcpy(&h, d_blob, sizeof h, cudaMemcpyDeviceToHost));
-    if (h.magic != PT_BLOB_MAGIC || h.version != PT_BLOB_VERSION || h.total_bytes > bytes)
+    if (h.magic != PT_BLOB_MAGIC || h.version != PT_BLOB_VERSION || h.off_texels > h.total_bytes || bytes < h.off_texels)
         return fail(PT_ERR_INVALID, "malformed scene blob");
-    std::vector<unsigned char> host(h.total_bytes);
-    const uint64_t records = std::min<uint64_t>(h.off_texels, h.total_bytes);
-    CUDA_TRY(cudaMemcpy(host.data(), d_blob, records, cudaMemcpyDeviceToHost));
+    const bool texels_present = bytes >= h.total_bytes;
+    std::vector<unsigned char> host(texels_present ? h.total_bytes : h.off_texels);
+    CUDA_TRY(cudaMemcpy(host.data(), d_blob, h.off_texels, cudaMemcpyDeviceToHost));
     PtScene* s = new PtScene();
-    rc = adopt_header(s, host.data(), host.size());
+    bool present2 = false;
+    rc = adopt_header(s, host.data(), host.size(), &present2);
     if (rc != PT_OK) { delete s; return rc; }
-    s->bytes = h.total_bytes;
-    cudaError_t e = cudaMalloc(&s->d_blob, s->bytes);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_blob, d_blob, s->bytes, cudaMemcpyDeviceToDevice, g_stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    s->bytes = h.off_texels;
+    cudaError_t e;
+    s->d_records = static_cast<unsigned char*>(g_dev.alloc(s->bytes, &e));
+    if (s->d_records) e = cudaMemcpyAsync(s->d_records, d_blob, s->bytes, cudaMemcpyDeviceToDevice, g_stream);
     if (e != cudaSuccess) {
-        cudaFree(s->d_blob);
-        delete s;
+        cudaGetLastError();
+        free_scene(s);
         return fail(PT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
     }
+    rc = bind_textures(s, reinterpret_cast<const PtTexture*>(host.data() + h.off_textures),
+                       texels_present ? static_cast<const unsigned char*>(d_blob) + h.off_texels : nullptr,
+                       cudaMemcpyDeviceToDevice);
+    if (rc == PT_OK) {
+        e = cudaStreamSynchronize(g_stream);
+        if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != PT_OK) { free_scene(s); return rc; }
     fill_view(s);
     *out = s;
     return PT_OK;
 }
 
+uint64_t pt_scene_uploaded_bytes(const PtScene* scene) { return scene ? scene->h2d_bytes : 0; }
+
 void pt_scene_free(PtScene* scene) {
     if (!scene) return;
-    free_frame(scene->cached_frame);
-    cudaFree(scene->d_blob);
-    delete scene;
+    Lock lock(g_mu);
+    for (PtFrame* f : g_frame_cache)
+        if (f->scene == scene) f->scene = nullptr;
+    free_scene(scene);
 }
 
 // =================================================================== frames
 int pt_frame_create(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, PtFrame** out) {
     if (!scene || !camera || !params || !out) return fail(PT_ERR_INVALID, "null argument");
-    const PtRenderParams& p = *params;
-    if (p.width == 0 || p.height == 0 || p.samples == 0) return fail(PT_ERR_INVALID, "empty image or zero samples");
-    if (p.x1 >= p.width || p.x2 >= p.width || p.y1 >= p.height || p.y2 >= p.height)
-        return fail(PT_ERR_INVALID, "The positions {x: %u, y: %u} and/or {x: %u, y: %u} are not within an image with width = %u and height = %u",
-                    p.x1, p.y1, p.x2, p.y2, p.width, p.height);
-    if ((uint64_t)p.width * p.height > 0xFFFFFFF0ull) return fail(PT_ERR_INVALID, "image too large");
-    if (p.world > 1 && p.rank >= p.world) return fail(PT_ERR_INVALID, "rank %u out of range for world %u", p.rank, p.world);
-    if (p.bg_mode > PT_BG_CONSTANT || p.rng_mode > PT_RNG_HASH) return fail(PT_ERR_INVALID, "bad bg_mode / rng_mode");
-    if (effective_max_depth(p) > 13) return fail(PT_ERR_INVALID, "max_depth > 13 is not supported");
-
-    PtFrame* f = new PtFrame();
-    f->scene = scene;
-    f->cam = *camera;
-    f->params = p;
-    f->max_depth = effective_max_depth(p);
-    f->n_levels = scene->has_reflective ? (int)f->max_depth + 1 : 1;
-
-    // owned pixels: interleaved tiles, 8x4 micro-tiles inside a tile (tiles.c)
-    f->pixel_index.resize(pt_owned_pixels(&p, nullptr, 0));
-    pt_owned_pixels(&p, f->pixel_index.data(), f->pixel_index.size());
-    const uint64_t owned = f->pixel_index.size();
-
-    f->bg_doubles = p.bg_mode == PT_BG_PER_PIXEL ? (uint64_t)p.width * p.height * 3
-                    : p.bg_mode == PT_BG_PER_ROW ? (uint64_t)p.height * 3
-                                                 : 3;
-    // batch geometry: whole pixels per batch so a pixel's samples are summed in one place, in order
-    uint64_t max_paths = p.max_batch_paths ? p.max_batch_paths : (1ull << 22);
-    uint64_t slots = std::max<uint64_t>(1, max_paths / p.samples);
-    slots = std::min<uint64_t>(slots, std::max<uint64_t>(owned, 1));
-    if (slots * p.samples > 0x7FFFFFFFull) slots = 0x7FFFFFFFull / p.samples;
-    if (slots == 0) { delete f; return fail(PT_ERR_INVALID, "samples too large"); }
-    f->batch_slots = (uint32_t)slots;
-    const uint64_t batch_paths = slots * p.samples;
-    uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * 4 : batch_paths);
-    capacity = std::max<uint64_t>(capacity, batch_paths);
-    capacity = std::min<uint64_t>(capacity, 0xFFFFFF00ull);
-
-    cudaError_t e = cudaSuccess;
-    auto try_alloc = [&](void** ptr, size_t bytes) {
-        if (e == cudaSuccess) e = cudaMalloc(ptr, std::max<size_t>(bytes, 16));
-    };
-    try_alloc((void**)&f->d_pixel_index, owned * sizeof(uint32_t));
-    try_alloc((void**)&f->d_background, f->bg_doubles * sizeof(double));
-    try_alloc((void**)&f->d_rgb, owned * 3);
-    try_alloc((void**)&f->d_hit_id, owned * 2 * sizeof(uint32_t));
-    try_alloc((void**)&f->d_hit_t, owned * sizeof(double));
-    try_alloc((void**)&f->d_ctl, sizeof(BatchCtl));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&f->h_ctl, sizeof(BatchCtl));
-    if (e == cudaSuccess) e = cudaEventCreate(&f->ev_start);
-    if (e == cudaSuccess) e = cudaEventCreate(&f->ev_stop);
-    if (e == cudaSuccess && owned)
-        e = cudaMemcpy(f->d_pixel_index, f->pixel_index.data(), owned * sizeof(uint32_t), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        free_frame(f);
-        return fail(PT_ERR_CUDA, "frame allocation failed: %s", cudaGetErrorString(e));
-    }
-    int rc = alloc_pool(&f->d_pool, &f->pool, (uint32_t)capacity, scene->h.n_lights);
+    Lock lock(g_mu);
+    PtFrame* f = nullptr;
+    int rc = create_frame(scene, camera, params, &f);
+    if (rc != PT_OK) return rc;
+    rc = ensure_id_buffers(f);  // explicit frames always expose hit ids
     if (rc != PT_OK) { free_frame(f); return rc; }
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
     *out = f;
     return PT_OK;
 }
 
-void pt_frame_free(PtFrame* frame) { free_frame(frame); }
+void pt_frame_free(PtFrame* frame) {
+    Lock lock(g_mu);
+    free_frame(frame);
+}
 uint64_t pt_frame_owned_pixels(const PtFrame* frame) { return frame ? frame->pixel_index.size() : 0; }
 uint64_t pt_frame_background_doubles(const PtFrame* frame) { return frame ? frame->bg_doubles : 0; }
 
 int pt_frame_set_background(PtFrame* frame, const double* background) {
     if (!frame || !background) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
     CUDA_TRY(cudaMemcpyAsync(frame->d_background, background, frame->bg_doubles * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     return PT_OK;
 }
 int pt_frame_set_background_device(PtFrame* frame, const double* d_background) {
     if (!frame || !d_background) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
     CUDA_TRY(cudaMemcpyAsync(frame->d_background, d_background, frame->bg_doubles * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     return PT_OK;
@@ -468,13 +886,10 @@ int pt_frame_set_background_device(PtFrame* frame, const double* d_background) {
 
 int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* user, PtStats* stats) {
     if (!frame) return fail(PT_ERR_INVALID, "null frame");
+    Lock lock(g_mu);
     PtFrame* f = frame;
+    if (!f->scene) return fail(PT_ERR_INVALID, "the frame's scene has been freed");
     cudaStream_t st = stream ? (cudaStream_t)stream : g_stream;
-    const DScene& sc = f->scene->view;
-    const FrameParams fp = frame_params(f);
-    const bool count = (f->params.flags & PT_RENDER_COUNTERS) != 0;
-    const uint32_t owned = (uint32_t)f->pixel_index.size();
-    const uint32_t S = f->params.samples;
     if (stats) {
         const double h2d_ms = stats->h2d_ms, d2h_ms = stats->d2h_ms;
         const uint64_t h2d_b = stats->h2d_bytes, d2h_b = stats->d2h_bytes;
@@ -482,38 +897,40 @@ int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* u
         stats->h2d_ms = h2d_ms; stats->d2h_ms = d2h_ms; stats->h2d_bytes = h2d_b; stats->d2h_bytes = d2h_b;
     }
     uint32_t launches = 0, batches = 0, retries = 0, error_bits = 0;
-    KernelTimer timer;
-    if (f->params.flags & PT_RENDER_KERNEL_TIMES) timer.events = &f->kernel_events;
+    const uint32_t owned = (uint32_t)f->pixel_index.size();
 
+    const FrameState state = frame_state(f);
     CUDA_TRY(cudaEventRecord(f->ev_start, st));
-    uint32_t first_slot = 0;
-    uint32_t batch_slots = f->batch_slots;
-    while (first_slot < owned) {
-        const uint32_t n_slots = std::min(batch_slots, owned - first_slot);
-        const uint32_t n_paths = n_slots * S;
-        launch_begin_batch(f->d_ctl, n_paths, st);
-        launch_camera(fp, f->pool, first_slot, n_paths, st);
-        launches += 2;
-        int rc = run_levels(sc, fp, f->pool, f->d_ctl, f->h_ctl, first_slot, n_paths, f->n_levels, count, st, &launches, &timer);
-        if (rc != PT_OK) return rc;
-        timer.collect(stats);
-        if (f->h_ctl->error_bits & PT_DEVERR_OVERFLOW) {
-            // the ray trees of this batch do not fit: halve the batch and redo it (results do not depend on batching)
-            if (n_slots == 1) return fail(PT_ERR_OVERFLOW, "%s", panic_text(PT_ERR_OVERFLOW));
-            batch_slots = std::max<uint32_t>(1, n_slots / 2);
-            ++retries;
-            continue;
+    CUDA_TRY(upload_state(f->slot, state, st));
+    int rc = PT_OK;
+    const bool want_stream = (f->params.flags & (PT_RENDER_KERNEL_TIMES | PT_RENDER_NO_GRAPH)) != 0 || !graphs_enabled() ||
+                             f->graph_failed;
+    bool done = owned == 0;
+    if (!done && !want_stream) {
+        bool overflow = false;
+        PtStats scratch{};
+        uint32_t l = 0, b = 0, eb = 0;
+        rc = render_graph_path(f, st, progress, user, stats ? &scratch : nullptr, &l, &b, &eb, &overflow);
+        if (rc == PT_OK && !overflow) {
+            if (stats) {
+                const PtStats keep = *stats;
+                *stats = scratch;
+                stats->h2d_ms = keep.h2d_ms; stats->d2h_ms = keep.d2h_ms; stats->h2d_bytes = keep.h2d_bytes; stats->d2h_bytes = keep.d2h_bytes;
+            }
+            launches = l; batches = b; error_bits = eb;
+            done = true;
+        } else if (rc == PT_OK) {
+            ++retries;  // node pool overflow: redo the frame with per-batch checks
+        } else if (f->graph_failed) {
+            rc = PT_OK;  // no graph support on this driver: fall through to the stream path
         }
-        launch_tree_eval(fp, f->pool, first_slot, n_paths, st);
-        launch_resolve(fp, f->pool, first_slot, n_slots, f->d_rgb, f->d_hit_id, f->d_hit_t, st);
-        launches += 2;
-        error_bits |= f->h_ctl->error_bits;
-        accumulate_stats(stats, *f->h_ctl, n_paths);
-        ++batches;
-        first_slot += n_slots;
-        if (progress) progress(user, n_slots);  // reporter.report_finished_pixels, render.rs:149
     }
-    CUDA_TRY(cudaEventRecord(f->ev_stop, st));
+    if (rc == PT_OK && !done) {
+        rc = render_stream_path(f, st, progress, user, stats, &launches, &batches, &retries, &error_bits);
+        if (rc == PT_OK) CUDA_TRY(cudaEventRecord(f->ev_stop, st));
+    }
+    if (rc != PT_OK) return rc;
+    if (owned == 0) CUDA_TRY(cudaEventRecord(f->ev_stop, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
@@ -542,22 +959,46 @@ int pt_frame_pixel_index(const PtFrame* frame, uint32_t* index_out) {
 
 int pt_frame_read(PtFrame* frame, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtStats* stats) {
     if (!frame) return fail(PT_ERR_INVALID, "null frame");
+    Lock lock(g_mu);
     const size_t owned = frame->pixel_index.size();
     const double t0 = now_ms();
     uint64_t bytes = 0;
-    std::vector<uint8_t> rgb;
-    std::vector<uint32_t> ids;
-    std::vector<double> ts;
-    if (rgb_inout) { rgb.resize(owned * 3); CUDA_TRY(cudaMemcpyAsync(rgb.data(), frame->d_rgb, owned * 3, cudaMemcpyDeviceToHost, g_stream)); bytes += owned * 3; }
-    if (hit_id_out) { ids.resize(owned * 2); CUDA_TRY(cudaMemcpyAsync(ids.data(), frame->d_hit_id, owned * 8, cudaMemcpyDeviceToHost, g_stream)); bytes += owned * 8; }
-    if (hit_t_out) { ts.resize(owned); CUDA_TRY(cudaMemcpyAsync(ts.data(), frame->d_hit_t, owned * 8, cudaMemcpyDeviceToHost, g_stream)); bytes += owned * 8; }
-    CUDA_TRY(cudaStreamSynchronize(g_stream));
-    // write only the pixels this call owns (render.rs:136-138)
-    for (size_t k = 0; k < owned; ++k) {
-        const size_t px = frame->pixel_index[k];
-        if (rgb_inout) { rgb_inout[px * 3] = rgb[k * 3]; rgb_inout[px * 3 + 1] = rgb[k * 3 + 1]; rgb_inout[px * 3 + 2] = rgb[k * 3 + 2]; }
-        if (hit_id_out) { hit_id_out[px * 2] = ids[k * 2]; hit_id_out[px * 2 + 1] = ids[k * 2 + 1]; }
-        if (hit_t_out) hit_t_out[px] = ts[k];
+    if ((hit_id_out && !frame->d_hit_id) || (hit_t_out && !frame->d_hit_t))
+        return fail(PT_ERR_INVALID, "hit ids were not rendered for this frame");
+    if (owned == 0) return PT_OK;
+    if (frame->row_major) {
+        // the slice rectangle goes straight into the caller's image: only slice pixels are written (render.rs:136-138)
+        const PtRenderParams& p = frame->params;
+        const size_t W = p.width, w = p.x2 - p.x1 + 1, hgt = p.y2 - p.y1 + 1;
+        const size_t first = (size_t)p.y1 * W + p.x1;
+        if (rgb_inout) { CUDA_TRY(cudaMemcpy2DAsync(rgb_inout + first * 3, W * 3, frame->d_rgb + first * 3, W * 3, w * 3, hgt, cudaMemcpyDeviceToHost, g_stream)); bytes += w * hgt * 3; }
+        if (hit_id_out) { CUDA_TRY(cudaMemcpy2DAsync(hit_id_out + first * 2, W * 8, frame->d_hit_id + first * 2, W * 8, w * 8, hgt, cudaMemcpyDeviceToHost, g_stream)); bytes += w * hgt * 8; }
+        if (hit_t_out) { CUDA_TRY(cudaMemcpy2DAsync(hit_t_out + first, W * 8, frame->d_hit_t + first, W * 8, w * 8, hgt, cudaMemcpyDeviceToHost, g_stream)); bytes += w * hgt * 8; }
+        CUDA_TRY(cudaStreamSynchronize(g_stream));
+    } else {
+        // compact outputs -> pinned staging -> scatter into the caller's images
+        cudaError_t e = cudaSuccess;
+        uint8_t* rgb = nullptr;
+        uint32_t* ids = nullptr;
+        double* ts = nullptr;
+        if (rgb_inout) { rgb = static_cast<uint8_t*>(g_pin.alloc(owned * 3, &e)); if (rgb) e = cudaMemcpyAsync(rgb, frame->d_rgb, owned * 3, cudaMemcpyDeviceToHost, g_stream); bytes += owned * 3; }
+        if (e == cudaSuccess && hit_id_out) { ids = static_cast<uint32_t*>(g_pin.alloc(owned * 8, &e)); if (ids) e = cudaMemcpyAsync(ids, frame->d_hit_id, owned * 8, cudaMemcpyDeviceToHost, g_stream); bytes += owned * 8; }
+        if (e == cudaSuccess && hit_t_out) { ts = static_cast<double*>(g_pin.alloc(owned * 8, &e)); if (ts) e = cudaMemcpyAsync(ts, frame->d_hit_t, owned * 8, cudaMemcpyDeviceToHost, g_stream); bytes += owned * 8; }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+        if (e == cudaSuccess) {
+            // write only the pixels this call owns (render.rs:136-138)
+            const uint32_t* index = frame->pixel_index.data();
+            for (size_t k = 0; k < owned; ++k) {
+                const size_t px = index[k];
+                if (rgb) { rgb_inout[px * 3] = rgb[k * 3]; rgb_inout[px * 3 + 1] = rgb[k * 3 + 1]; rgb_inout[px * 3 + 2] = rgb[k * 3 + 2]; }
+                if (ids) { hit_id_out[px * 2] = ids[k * 2]; hit_id_out[px * 2 + 1] = ids[k * 2 + 1]; }
+                if (ts) hit_t_out[px] = ts[k];
+            }
+        }
+        g_pin.release(rgb);
+        g_pin.release(ids);
+        g_pin.release(ts);
+        if (e != cudaSuccess) return fail(PT_ERR_CUDA, "frame read failed: %s", cudaGetErrorString(e));
     }
     if (stats) { stats->d2h_ms += now_ms() - t0; stats->d2h_bytes += bytes; }
     return PT_OK;
@@ -568,33 +1009,49 @@ static bool same_geometry(const PtRenderParams& a, const PtRenderParams& b) {
     return a.width == b.width && a.height == b.height && a.x1 == b.x1 && a.y1 == b.y1 && a.x2 == b.x2 && a.y2 == b.y2 &&
            a.samples == b.samples && a.bg_mode == b.bg_mode && a.max_depth == b.max_depth && a.tile_w == b.tile_w &&
            a.tile_h == b.tile_h && a.rank == b.rank && a.world == b.world && a.max_batch_paths == b.max_batch_paths &&
-           a.node_pool_capacity == b.node_pool_capacity;
+           a.node_pool_capacity == b.node_pool_capacity && ((a.flags ^ b.flags) & PT_RENDER_ROW_MAJOR) == 0;
 }
 
 int pt_render(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, const double* background,
               uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtProgressFn progress, void* user,
               PtStats* stats) {
     if (!scene || !camera || !params || !background || !rgb_inout) return fail(PT_ERR_INVALID, "null argument");
-    // device buffers are kept between calls on the same scene with the same geometry
-    PtFrame* f = scene->cached_frame;
-    if (f && same_geometry(scene->cached_params, *params)) {
+    Lock lock(g_mu);
+    PtRenderParams p = *params;
+    if (p.world <= 1) p.flags |= PT_RENDER_ROW_MAJOR;  // single rank: resolve writes the image in place, D2H is one 2-D copy
+    else p.flags &= ~PT_RENDER_ROW_MAJOR;
+    // Frames (device buffers + CUDA graph) are kept between calls and re-bound to whatever scene comes next: a
+    // program that renders many scenes at one resolution (examples/normal-mapping.rs) allocates once.
+    PtFrame* f = nullptr;
+    for (PtFrame* c : g_frame_cache)
+        if (same_geometry(c->params, p) && c->n_lights_cap == scene->h.n_lights && c->reflective_cap == scene->has_reflective) { f = c; break; }
+    if (f) {
+        f->scene = scene;
         f->cam = *camera;
-        f->params = *params;
+        f->params = p;
     } else {
-        free_frame(f);
-        scene->cached_frame = nullptr;
-        int rc = pt_frame_create(scene, camera, params, &f);
+        int rc = create_frame(scene, camera, &p, &f);
         if (rc != PT_OK) return rc;
-        scene->cached_frame = f;
-        scene->cached_params = *params;
+        if (g_frame_cache.size() >= kFrameCacheMax) {
+            size_t oldest = 0;
+            for (size_t i = 1; i < g_frame_cache.size(); ++i)
+                if (g_frame_cache[i]->last_use < g_frame_cache[oldest]->last_use) oldest = i;
+            free_frame(g_frame_cache[oldest]);
+            g_frame_cache.erase(g_frame_cache.begin() + oldest);
+        }
+        g_frame_cache.push_back(f);
+    }
+    f->last_use = ++g_frame_tick;
+    if (hit_id_out || hit_t_out) {
+        int rc = ensure_id_buffers(f);
+        if (rc != PT_OK) return rc;
     }
     PtStats local{};
     const double t0 = now_ms();
-    int rc = pt_frame_set_background(f, background);
-    if (rc != PT_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(f->d_background, background, f->bg_doubles * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     local.h2d_ms = now_ms() - t0;
     local.h2d_bytes = f->bg_doubles * sizeof(double);
-    rc = pt_frame_render(f, nullptr, progress, user, &local);
+    int rc = pt_frame_render(f, nullptr, progress, user, &local);
     int rc2 = pt_frame_read(f, rgb_inout, hit_id_out, hit_t_out, &local);
     if (stats) *stats = local;
     return rc != PT_OK ? rc : rc2;
@@ -608,6 +1065,7 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
     if (!scene || !origins || !dirs || !background3) return fail(PT_ERR_INVALID, "null argument");
     if (n == 0) return PT_OK;
     if (n > 0x7FFFFFFFull) return fail(PT_ERR_INVALID, "too many rays");
+    Lock lock(g_mu);
     const uint32_t depth = max_depth ? max_depth : PT_MAX_RECURSION_DEPTH;
     if (depth > 13) return fail(PT_ERR_INVALID, "max_depth > 13 is not supported");
     const int n_levels = scene->has_reflective ? (int)depth + 1 : 1;
@@ -622,40 +1080,55 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
     NodePool pool{};
     int rc = PT_OK;
     cudaError_t e = cudaSuccess;
-    auto try_alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
-    try_alloc((void**)&d_o, n * 24); try_alloc((void**)&d_d, n * 24); try_alloc((void**)&d_bg, 24);
-    try_alloc((void**)&d_color, n * 24); try_alloc((void**)&d_t, n * 8); try_alloc((void**)&d_id, n * 8);
-    try_alloc((void**)&d_ctl, sizeof(BatchCtl));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&h_ctl, sizeof(BatchCtl));
-    if (e == cudaSuccess) e = cudaMemcpy(d_o, origins, n * 24, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_d, dirs, n * 24, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_bg, background3, 24, cudaMemcpyHostToDevice);
+    auto dev = [&](size_t bytes) -> void* { return e == cudaSuccess ? g_dev.alloc(bytes, &e) : nullptr; };
+    d_o = static_cast<double*>(dev(n * 24)); d_d = static_cast<double*>(dev(n * 24)); d_bg = static_cast<double*>(dev(24));
+    d_color = static_cast<double*>(dev(n * 24)); d_t = static_cast<double*>(dev(n * 8)); d_id = static_cast<uint32_t*>(dev(n * 8));
+    d_ctl = static_cast<BatchCtl*>(dev(sizeof(BatchCtl)));
+    if (e == cudaSuccess) h_ctl = static_cast<BatchCtl*>(g_pin.alloc(sizeof(BatchCtl), &e));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, origins, n * 24, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, n * 24, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_bg, background3, 24, cudaMemcpyHostToDevice, g_stream);
     if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "trace_rays allocation failed: %s", cudaGetErrorString(e));
     if (rc == PT_OK) rc = alloc_pool(&d_pool, &pool, capacity, scene->h.n_lights);
 
-    FrameParams fp{};
-    fp.pixel_index = nullptr;
-    fp.background = d_bg;
-    fp.bg_mode = PT_BG_CONSTANT;
-    fp.width = 1; fp.height = 1; fp.samples = 1;
-    fp.rng_mode = rng_mode; fp.seed = seed; fp.max_depth = depth;
+    const int slot = take_slot();
+    FrameState state{};
+    state.sc = scene->view;
+    state.fp.pixel_index = nullptr;
+    state.fp.background = d_bg;
+    state.fp.bg_mode = PT_BG_CONSTANT;
+    state.fp.width = 1; state.fp.height = 1; state.fp.samples = 1;
+    state.fp.rng_mode = rng_mode; state.fp.seed = seed; state.fp.max_depth = depth;
+    state.pool = pool;
+    state.ctl = d_ctl;
+    state.hit_id = d_id;
+    state.hit_t = d_t;
+    state.n_levels = (uint32_t)n_levels;
+    state.ray_origins = d_o;
+    state.ray_dirs = d_d;
+    state.ray_color = d_color;
+    if (rc == PT_OK) {
+        e = upload_state(slot, state, g_stream);
+        if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "trace_rays state upload failed: %s", cudaGetErrorString(e));
+    }
     if (stats) memset(stats, 0, sizeof *stats);
     uint32_t launches = 0, error_bits = 0;
     uint32_t step = batch;
     for (uint64_t first = 0; rc == PT_OK && first < n;) {
         const uint32_t n_paths = (uint32_t)std::min<uint64_t>(step, n - first);
-        launch_begin_batch(d_ctl, n_paths, g_stream);
-        launch_load_rays(d_o, d_d, pool, (uint32_t)first, n_paths, g_stream);
+        launch_load_rays(slot, (uint32_t)first, n_paths, g_stream);
+        ++launches;
         KernelTimer timer;
-        rc = run_levels(scene->view, fp, pool, d_ctl, h_ctl, (uint32_t)first, n_paths, n_levels, count, g_stream, &launches, &timer);
+        rc = run_levels_stream(slot, scene->h.n_lights, capacity, d_ctl, h_ctl, n_paths, n_levels, count, g_stream, &launches, &timer);
         if (rc != PT_OK) break;
         if (h_ctl->error_bits & PT_DEVERR_OVERFLOW) {
             if (n_paths == 1) { rc = fail(PT_ERR_OVERFLOW, "%s", panic_text(PT_ERR_OVERFLOW)); break; }
             step = std::max<uint32_t>(1, n_paths / 2);
             continue;
         }
-        launch_tree_eval(fp, pool, (uint32_t)first, n_paths, g_stream);
-        launch_export_rays(pool, (uint32_t)first, n_paths, d_color, d_id, d_t, g_stream);
+        launch_tree_eval(slot, n_paths, g_stream);
+        launch_export_rays(slot, n_paths, g_stream);
+        launches += 2;
         error_bits |= h_ctl->error_bits;
         accumulate_stats(stats, *h_ctl, n_paths);
         first += n_paths;
@@ -666,10 +1139,13 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
         if (e == cudaSuccess && hit_id_out) e = cudaMemcpy(hit_id_out, d_id, n * 8, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && hit_t_out) e = cudaMemcpy(hit_t_out, d_t, n * 8, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "trace_rays copy back failed: %s", cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(g_stream);
     }
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_bg); cudaFree(d_color); cudaFree(d_t); cudaFree(d_id);
-    cudaFree(d_pool); cudaFree(d_ctl);
-    if (h_ctl) cudaFreeHost(h_ctl);
+    give_slot(slot);
+    g_dev.release(d_o); g_dev.release(d_d); g_dev.release(d_bg); g_dev.release(d_color); g_dev.release(d_t); g_dev.release(d_id);
+    g_dev.release(d_pool); g_dev.release(d_ctl);
+    g_pin.release(h_ctl);
     if (stats) { stats->kernel_launches = launches; stats->device_error_bits = error_bits & ~PT_DEVERR_OVERFLOW; }
     if (rc != PT_OK) return rc;
     const int code = device_error_to_code(error_bits);

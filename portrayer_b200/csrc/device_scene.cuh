@@ -7,8 +7,15 @@
 
 namespace ptd {
 
-// Pointers into the blob as it lies in HBM (the blob is uploaded verbatim, so
-// an NCCL-broadcast copy is usable as is).
+// One texture as the kernels see it: the texels live either inside the uploaded blob or in the
+// library's texture residency cache (PtTexture.key), so the record carries a device pointer.
+struct TextureDev {
+    uint32_t width, height;
+    const uint8_t* texels;
+};
+
+// Pointers into the scene records as they lie in HBM (the record sections of the blob are
+// uploaded verbatim, so an NCCL-broadcast copy is usable as is).
 struct DScene {
     const PtKdNode* tlas_nodes;
     const uint32_t* tlas_items;
@@ -22,8 +29,7 @@ struct DScene {
     const PtTriUvs* tri_uvs;
     const PtMaterial* materials;
     const PtLight* lights;
-    const PtTexture* textures;
-    const uint8_t* texels;
+    const TextureDev* textures;
     double ambient[3];
     double tlas_extent;
     uint32_t n_lights;
@@ -66,6 +72,12 @@ struct BatchCtl {
     uint32_t pool_count;       // bump allocator of the node pool
     uint32_t error_bits;       // PT_DEVERR_*
     uint32_t blocks_done[16];  // per level "last block" tickets of the shade kernel
+    uint32_t level;            // the recursion level the next extend / shadow / shade launch works on
+    uint32_t first_slot;       // first owned-pixel slot of the batch
+    uint32_t n_slots;          // owned pixels in the batch
+    uint32_t n_paths;          // n_slots * samples
+    uint32_t levels_run;       // levels that held at least one ray
+    uint32_t pad_[3];
     unsigned long long rays_shadow, rays_reflect, rays_refract, rays_depth_cut, shaded_hits, texel_lookups;
     unsigned long long work[2][4];  // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates]
 };
@@ -82,5 +94,25 @@ struct FrameParams {
     uint64_t seed;
     uint32_t max_depth;
 };
+
+// Everything the kernels of one frame read, in __constant__ memory (kernels.cu: c_state[slot]):
+// rebinding a frame to another scene / camera is one small async copy, and the frame's CUDA graph
+// (whose kernel nodes only carry the slot number) is replayed unchanged.
+struct FrameState {
+    DScene sc;
+    FrameParams fp;
+    NodePool pool;
+    BatchCtl* ctl;
+    uint8_t* rgb;       // resolve outputs: compact owned-pixel order, or full-image row-major
+    uint32_t* hit_id;   // nullable
+    double* hit_t;      // nullable
+    uint32_t row_major;
+    uint32_t n_levels;  // 1 when no material reflects, else max_depth + 1
+    // pt_trace_rays: explicit rays in, linear colours out
+    const double* ray_origins;
+    const double* ray_dirs;
+    double* ray_color;
+};
+constexpr int kStateSlots = 16;
 
 }  // namespace ptd

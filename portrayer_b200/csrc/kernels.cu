@@ -21,6 +21,10 @@
 
 namespace ptd {
 
+// Per-frame constants (scene pointers, camera, node pool, outputs).  Kernels take only the slot number, so a
+// frame's CUDA graph can be replayed for any scene / camera after one cudaMemcpyToSymbolAsync.
+__constant__ FrameState c_state[kStateSlots];
+
 namespace {
 
 constexpr int kBlock = 128;
@@ -51,7 +55,28 @@ PT_D void flush_counters(BatchCtl* ctl, int kind, const WorkCounters& wc) {
 
 // ------------------------------------------------------------------ camera
 // path p of the batch = (owned pixel slot, sample); Camera::ray_at, camera.rs:48-84
-__global__ void __launch_bounds__(kBlock) camera_kernel(FrameParams fp, NodePool pool, uint32_t first_slot, uint32_t n_paths) {
+// Block 0 also resets the batch control block: nothing in this kernel reads it, and every later kernel of the
+// batch starts after this one has finished.
+PT_D void begin_batch(BatchCtl* ctl, uint32_t first_slot, uint32_t n_slots, uint32_t n_paths) {
+    if (blockIdx.x != 0) return;
+    uint32_t* words = reinterpret_cast<uint32_t*>(ctl);
+    for (uint32_t i = threadIdx.x; i < sizeof(BatchCtl) / 4; i += blockDim.x) words[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x < 16) ctl->level_start[threadIdx.x] = threadIdx.x == 0 ? 0u : n_paths;
+    if (threadIdx.x == 0) {
+        ctl->pool_count = n_paths;
+        ctl->first_slot = first_slot;
+        ctl->n_slots = n_slots;
+        ctl->n_paths = n_paths;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) camera_kernel(int slot_id, uint32_t first_slot, uint32_t n_slots) {
+    const FrameState& fs = c_state[slot_id];
+    const FrameParams& fp = fs.fp;
+    const NodePool& pool = fs.pool;
+    const uint32_t n_paths = n_slots * fp.samples;
+    begin_batch(fs.ctl, first_slot, n_slots, n_paths);
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_paths) return;
     const uint32_t slot = first_slot + p / fp.samples;
@@ -79,8 +104,12 @@ __global__ void __launch_bounds__(kBlock) camera_kernel(FrameParams fp, NodePool
 }
 
 // explicit rays instead of camera rays (pt_trace_rays): ray i is "pixel" i, sample 0
-__global__ void __launch_bounds__(kBlock) load_rays_kernel(const double* __restrict__ origins, const double* __restrict__ dirs,
-                                                         NodePool pool, uint32_t first, uint32_t n_paths) {
+__global__ void __launch_bounds__(kBlock) load_rays_kernel(int slot_id, uint32_t first, uint32_t n_paths) {
+    const FrameState& fs = c_state[slot_id];
+    const NodePool& pool = fs.pool;
+    const double* __restrict__ origins = fs.ray_origins;
+    const double* __restrict__ dirs = fs.ray_dirs;
+    begin_batch(fs.ctl, first, n_paths, n_paths);
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_paths) return;
     const size_t i = (size_t)(first + p) * 3;
@@ -92,7 +121,12 @@ __global__ void __launch_bounds__(kBlock) load_rays_kernel(const double* __restr
 
 // ------------------------------------------------------------------ extend (closest hit)
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) extend_kernel(DScene sc, NodePool pool, BatchCtl* ctl, int level) {
+__global__ void __launch_bounds__(kBlock) extend_kernel(int slot_id) {
+    const FrameState& fs = c_state[slot_id];
+    const DScene& sc = fs.sc;
+    const NodePool& pool = fs.pool;
+    BatchCtl* ctl = fs.ctl;
+    const uint32_t level = ctl->level;
     const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
     KdStack tlas_stack, blas_stack;
     WorkCounters wc;
@@ -112,8 +146,14 @@ __global__ void __launch_bounds__(kBlock) extend_kernel(DScene sc, NodePool pool
 
 // ------------------------------------------------------------------ shadow (any hit), light-major
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) shadow_kernel(DScene sc, FrameParams fp, NodePool pool, BatchCtl* ctl, int level,
-                                                       uint32_t first_slot) {
+__global__ void __launch_bounds__(kBlock) shadow_kernel(int slot_id) {
+    const FrameState& fs = c_state[slot_id];
+    const DScene& sc = fs.sc;
+    const FrameParams& fp = fs.fp;
+    const NodePool& pool = fs.pool;
+    BatchCtl* ctl = fs.ctl;
+    const uint32_t level = ctl->level;
+    const uint32_t first_slot = ctl->first_slot;
     const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
     const uint32_t n = end - begin;
     const unsigned long long total = (unsigned long long)n * sc.n_lights;
@@ -163,8 +203,16 @@ PT_D uint32_t warp_alloc(BatchCtl* ctl, bool want) {
     return want ? base + (uint32_t)__popc(mask & ((1u << lane) - 1u)) : kNone;
 }
 
-__global__ void __launch_bounds__(kBlock) shade_kernel(DScene sc, FrameParams fp, NodePool pool, BatchCtl* ctl, int level,
-                                                      uint32_t first_slot) {
+// `loop`: the conditional handle of the frame graph's WHILE node (0 on the stream path); the last block to
+// finish decides whether another recursion level has rays to trace.
+__global__ void __launch_bounds__(kBlock) shade_kernel(int slot_id, cudaGraphConditionalHandle loop) {
+    const FrameState& fs = c_state[slot_id];
+    const DScene& sc = fs.sc;
+    const FrameParams& fp = fs.fp;
+    const NodePool& pool = fs.pool;
+    BatchCtl* ctl = fs.ctl;
+    const uint32_t level = ctl->level;
+    const uint32_t first_slot = ctl->first_slot;
     const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
     const uint32_t n = end - begin;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -322,7 +370,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DScene sc, FrameParams fp
             }
 
             // depth cut-off: a child at depth > max_depth is bg whatever it hits (material.rs:102-104)
-            if ((uint32_t)level + 1 > fp.max_depth) {
+            if (level + 1 > fp.max_depth) {
                 if (want0) { c0 = kChildBg; ++n_cut; want0 = false; }
                 if (want1) { c1 = kChildBg; ++n_cut; want1 = false; }
             }
@@ -387,7 +435,12 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DScene sc, FrameParams fp
         const uint32_t ticket = atomicAdd(&ctl->blocks_done[level], 1u);
         if (ticket == gridDim.x - 1) {
             const uint32_t count = atomicAdd(&ctl->pool_count, 0u);
-            ctl->level_start[level + 2] = count < pool.capacity ? count : pool.capacity;
+            const uint32_t next_end = count < pool.capacity ? count : pool.capacity;
+            ctl->level_start[level + 2] = next_end;
+            ctl->level = level + 1;
+            ctl->levels_run = level + 1;
+            const bool more = next_end > end && level + 1 < fs.n_levels;
+            if (loop) cudaGraphSetConditional(loop, more ? 1u : 0u);
         }
     }
 }
@@ -395,7 +448,11 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DScene sc, FrameParams fp
 // ------------------------------------------------------------------ tree evaluation
 // Colour of one path = post-order walk of its ray tree with the reference's own
 // expressions (material.rs:280,307-309,315); writes the result over the root's local colour.
-__global__ void __launch_bounds__(kBlock) tree_eval_kernel(FrameParams fp, NodePool pool, uint32_t first_slot, uint32_t n_paths) {
+__global__ void __launch_bounds__(kBlock) tree_eval_kernel(int slot_id) {
+    const FrameState& fs = c_state[slot_id];
+    const FrameParams& fp = fs.fp;
+    const NodePool& pool = fs.pool;
+    const uint32_t first_slot = fs.ctl->first_slot, n_paths = fs.ctl->n_paths;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_paths) return;
     if (pool.mode[p] == kModeLeaf) return;  // colour already final
@@ -481,9 +538,14 @@ PT_D double clamp01(double v) {
 }
 
 // one thread per owned pixel of the batch: render.rs:43-50,143-147
-__global__ void __launch_bounds__(kBlock) resolve_kernel(FrameParams fp, NodePool pool, uint32_t first_slot, uint32_t n_slots,
-                                                        uint8_t* __restrict__ rgb, uint32_t* __restrict__ hit_id,
-                                                        double* __restrict__ hit_t) {
+__global__ void __launch_bounds__(kBlock) resolve_kernel(int slot_id) {
+    const FrameState& fs = c_state[slot_id];
+    const FrameParams& fp = fs.fp;
+    const NodePool& pool = fs.pool;
+    const uint32_t first_slot = fs.ctl->first_slot, n_slots = fs.ctl->n_slots;
+    uint8_t* __restrict__ rgb = fs.rgb;
+    uint32_t* __restrict__ hit_id = fs.hit_id;
+    double* __restrict__ hit_t = fs.hit_t;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_slots) return;
     const uint32_t p0 = k * fp.samples;
@@ -493,22 +555,29 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(FrameParams fp, NodePoo
         total[1] = total[1] + pool.cg[p0 + s];
         total[2] = total[2] + pool.cb[p0 + s];
     }
-    const size_t slot = (size_t)first_slot + k;
+    // compact owned-pixel order (multi-GPU gather), or the pixel's own place in a full row-major image
+    const size_t slot = fs.row_major ? (size_t)__ldg(fp.pixel_index + first_slot + k) : (size_t)first_slot + k;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         double c = total[ch] / (double)fp.samples;
         c = pow(c, 1.0 / PT_GAMMA);
         rgb[slot * 3 + ch] = to_u8(clamp01(c));
     }
-    hit_id[slot * 2] = pool.inst[p0];
-    hit_id[slot * 2 + 1] = pool.sub[p0];
-    hit_t[slot] = pool.t[p0];
+    if (hit_id) {
+        hit_id[slot * 2] = pool.inst[p0];
+        hit_id[slot * 2 + 1] = pool.sub[p0];
+    }
+    if (hit_t) hit_t[slot] = pool.t[p0];
 }
 
 // pt_trace_rays: linear colour of each explicit ray, no gamma
-__global__ void __launch_bounds__(kBlock) export_rays_kernel(NodePool pool, uint32_t first, uint32_t n_paths,
-                                                            double* __restrict__ color, uint32_t* __restrict__ hit_id,
-                                                            double* __restrict__ hit_t) {
+__global__ void __launch_bounds__(kBlock) export_rays_kernel(int slot_id) {
+    const FrameState& fs = c_state[slot_id];
+    const NodePool& pool = fs.pool;
+    const uint32_t first = fs.ctl->first_slot, n_paths = fs.ctl->n_paths;
+    double* __restrict__ color = fs.ray_color;
+    uint32_t* __restrict__ hit_id = fs.hit_id;
+    double* __restrict__ hit_t = fs.hit_t;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_paths) return;
     const size_t i = (size_t)first + p;
@@ -516,15 +585,6 @@ __global__ void __launch_bounds__(kBlock) export_rays_kernel(NodePool pool, uint
     hit_id[i * 2] = pool.inst[p];
     hit_id[i * 2 + 1] = pool.sub[p];
     hit_t[i] = pool.t[p];
-}
-
-__global__ void begin_batch_kernel(BatchCtl* ctl, uint32_t n_paths) {
-    // the whole control block starts from zero: error bits and counters are per batch
-    uint32_t* words = reinterpret_cast<uint32_t*>(ctl);
-    for (uint32_t i = threadIdx.x; i < sizeof(BatchCtl) / 4; i += blockDim.x) words[i] = 0u;
-    __syncthreads();
-    if (threadIdx.x < 16) ctl->level_start[threadIdx.x] = threadIdx.x == 0 ? 0u : n_paths;
-    if (threadIdx.x == 0) ctl->pool_count = n_paths;
 }
 
 int g_grid_extend[2] = {0, 0}, g_grid_shadow[2] = {0, 0}, g_grid_shade = 0;
@@ -550,51 +610,131 @@ void kernels_init() {
     g_grid_shade = persistent_grid(shade_kernel);
 }
 
-static inline uint32_t blocks_for(uint32_t n) { return (n + kBlock - 1) / kBlock; }
-
-void launch_begin_batch(BatchCtl* ctl, uint32_t n_paths, cudaStream_t st) { begin_batch_kernel<<<1, 32, 0, st>>>(ctl, n_paths); }
-
-void launch_camera(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_paths, cudaStream_t st) {
-    camera_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(fp, pool, first_slot, n_paths);
+static inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
+static inline int capped(int grid, uint64_t max_items) {
+    const uint64_t need = blocks_for(max_items ? max_items : 1);
+    return (uint64_t)grid > need ? (int)need : grid;
 }
-void launch_load_rays(const double* origins, const double* dirs, const NodePool& pool, uint32_t first, uint32_t n_paths,
-                      cudaStream_t st) {
-    load_rays_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(origins, dirs, pool, first, n_paths);
+
+cudaError_t upload_state(int slot, const FrameState& state, cudaStream_t st) {
+    return cudaMemcpyToSymbolAsync(c_state, &state, sizeof(FrameState), (size_t)slot * sizeof(FrameState),
+                                   cudaMemcpyHostToDevice, st);
+}
+
+void launch_camera(int slot, uint32_t first_slot, uint32_t n_slots, uint32_t samples, cudaStream_t st) {
+    camera_kernel<<<blocks_for((uint64_t)n_slots * samples), kBlock, 0, st>>>(slot, first_slot, n_slots);
+}
+void launch_load_rays(int slot, uint32_t first, uint32_t n_paths, cudaStream_t st) {
+    load_rays_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(slot, first, n_paths);
 }
 // A level can never hold more rays than `max_items`; the persistent grid is capped to it.
-void launch_extend(const DScene& sc, const NodePool& pool, BatchCtl* ctl, int level, uint32_t max_items, bool count,
-                   cudaStream_t st) {
-    int grid = g_grid_extend[count ? 1 : 0];
-    if ((uint32_t)grid > blocks_for(max_items)) grid = (int)blocks_for(max_items);
-    if (count) extend_kernel<true><<<grid, kBlock, 0, st>>>(sc, pool, ctl, level);
-    else extend_kernel<false><<<grid, kBlock, 0, st>>>(sc, pool, ctl, level);
+void launch_extend(int slot, uint64_t max_items, bool count, cudaStream_t st) {
+    const int grid = capped(g_grid_extend[count ? 1 : 0], max_items);
+    if (count) extend_kernel<true><<<grid, kBlock, 0, st>>>(slot);
+    else extend_kernel<false><<<grid, kBlock, 0, st>>>(slot);
 }
-void launch_shadow(const DScene& sc, const FrameParams& fp, const NodePool& pool, BatchCtl* ctl, int level,
-                   uint32_t first_slot, uint32_t max_items, bool count, cudaStream_t st) {
-    if (sc.n_lights == 0) return;
-    int grid = g_grid_shadow[count ? 1 : 0];
-    const unsigned long long items = (unsigned long long)max_items * sc.n_lights;
-    const unsigned long long need = (items + kBlock - 1) / kBlock;
-    if ((unsigned long long)grid > need) grid = (int)need;
-    if (count) shadow_kernel<true><<<grid, kBlock, 0, st>>>(sc, fp, pool, ctl, level, first_slot);
-    else shadow_kernel<false><<<grid, kBlock, 0, st>>>(sc, fp, pool, ctl, level, first_slot);
+void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, bool count, cudaStream_t st) {
+    const int grid = capped(g_grid_shadow[count ? 1 : 0], max_items * (n_lights ? n_lights : 1));
+    if (count) shadow_kernel<true><<<grid, kBlock, 0, st>>>(slot);
+    else shadow_kernel<false><<<grid, kBlock, 0, st>>>(slot);
 }
-void launch_shade(const DScene& sc, const FrameParams& fp, const NodePool& pool, BatchCtl* ctl, int level,
-                  uint32_t first_slot, uint32_t max_items, cudaStream_t st) {
-    int grid = g_grid_shade;
-    if ((uint32_t)grid > blocks_for(max_items)) grid = (int)blocks_for(max_items);
-    shade_kernel<<<grid, kBlock, 0, st>>>(sc, fp, pool, ctl, level, first_slot);
+void launch_shade(int slot, uint64_t max_items, cudaGraphConditionalHandle loop, cudaStream_t st) {
+    shade_kernel<<<capped(g_grid_shade, max_items), kBlock, 0, st>>>(slot, loop);
 }
-void launch_tree_eval(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_paths, cudaStream_t st) {
-    tree_eval_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(fp, pool, first_slot, n_paths);
+void launch_tree_eval(int slot, uint32_t n_paths, cudaStream_t st) {
+    tree_eval_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(slot);
 }
-void launch_resolve(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_slots, uint8_t* rgb,
-                    uint32_t* hit_id, double* hit_t, cudaStream_t st) {
-    resolve_kernel<<<blocks_for(n_slots), kBlock, 0, st>>>(fp, pool, first_slot, n_slots, rgb, hit_id, hit_t);
+void launch_resolve(int slot, uint32_t n_slots, cudaStream_t st) {
+    resolve_kernel<<<blocks_for(n_slots), kBlock, 0, st>>>(slot);
 }
-void launch_export_rays(const NodePool& pool, uint32_t first, uint32_t n_paths, double* color, uint32_t* hit_id,
-                        double* hit_t, cudaStream_t st) {
-    export_rays_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(pool, first, n_paths, color, hit_id, hit_t);
+void launch_export_rays(int slot, uint32_t n_paths, cudaStream_t st) {
+    export_rays_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(slot);
+}
+
+// The frame graph: camera -> WHILE(level has rays){extend, shadow, shade} -> tree_eval -> resolve.  Grids are
+// sized for a full batch of `n_slots` pixels; the camera node's (first_slot, n_slots) parameters are patched
+// per batch (cudaGraphExecKernelNodeSetParams), everything else is read from c_state[slot] / the control block.
+cudaError_t build_frame_graph(int slot, uint32_t n_slots, uint32_t samples, uint32_t n_lights_max, uint64_t capacity,
+                              bool count, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out, cudaGraphNode_t* camera_node) {
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaGraphCreate(&graph, 0);
+    if (e != cudaSuccess) return e;
+    const uint64_t n_paths = (uint64_t)n_slots * samples;
+
+    static uint32_t zero_first = 0;
+    uint32_t first_slot = zero_first, slots = n_slots;
+    void* cam_args[3] = {&slot, &first_slot, &slots};
+    cudaKernelNodeParams kp{};
+    kp.func = (void*)camera_kernel;
+    kp.gridDim = dim3(blocks_for(n_paths));
+    kp.blockDim = dim3(kBlock);
+    kp.kernelParams = cam_args;
+    cudaGraphNode_t n_camera = nullptr, n_loop = nullptr, n_tree = nullptr, n_resolve = nullptr;
+    e = cudaGraphAddKernelNode(&n_camera, graph, nullptr, 0, &kp);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+
+    cudaGraphConditionalHandle handle;
+    e = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    e = cudaGraphAddNode(&n_loop, graph, &n_camera, 1, &cp);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    {
+        // one recursion level; a level never holds more rays than the node pool
+        void* args1[1] = {&slot};
+        cudaGraphNode_t n_ext = nullptr, n_shd = nullptr, n_sha = nullptr;
+        cudaKernelNodeParams k{};
+        k.blockDim = dim3(kBlock);
+        k.kernelParams = args1;
+        k.func = count ? (void*)extend_kernel<true> : (void*)extend_kernel<false>;
+        k.gridDim = dim3(capped(g_grid_extend[count ? 1 : 0], capacity));
+        e = cudaGraphAddKernelNode(&n_ext, body, nullptr, 0, &k);
+        if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+        k.func = count ? (void*)shadow_kernel<true> : (void*)shadow_kernel<false>;
+        k.gridDim = dim3(capped(g_grid_shadow[count ? 1 : 0], capacity * (n_lights_max ? n_lights_max : 1)));
+        e = cudaGraphAddKernelNode(&n_shd, body, &n_ext, 1, &k);
+        if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+        void* args2[2] = {&slot, &handle};
+        k.func = (void*)shade_kernel;
+        k.kernelParams = args2;
+        k.gridDim = dim3(capped(g_grid_shade, capacity));
+        e = cudaGraphAddKernelNode(&n_sha, body, &n_shd, 1, &k);
+        if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+    }
+    void* args1[1] = {&slot};
+    kp.func = (void*)tree_eval_kernel;
+    kp.kernelParams = args1;
+    kp.gridDim = dim3(blocks_for(n_paths));
+    e = cudaGraphAddKernelNode(&n_tree, graph, &n_loop, 1, &kp);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+    kp.func = (void*)resolve_kernel;
+    kp.gridDim = dim3(blocks_for(n_slots));
+    e = cudaGraphAddKernelNode(&n_resolve, graph, &n_tree, 1, &kp);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+    *graph_out = graph;
+    *exec_out = exec;
+    *camera_node = n_camera;
+    return cudaSuccess;
+}
+
+// patch the camera node for one batch (a smaller last batch keeps the grids: surplus threads exit at once)
+cudaError_t set_graph_batch(cudaGraphExec_t exec, cudaGraphNode_t camera_node, int slot, uint32_t first_slot, uint32_t n_slots,
+                            uint32_t grid_slots, uint32_t samples) {
+    void* cam_args[3] = {&slot, &first_slot, &n_slots};
+    cudaKernelNodeParams kp{};
+    kp.func = (void*)camera_kernel;
+    kp.gridDim = dim3(blocks_for((uint64_t)grid_slots * samples));
+    kp.blockDim = dim3(kBlock);
+    kp.kernelParams = cam_args;
+    return cudaGraphExecKernelNodeSetParams(exec, camera_node, &kp);
 }
 
 }  // namespace ptd

@@ -6,19 +6,22 @@
 
 namespace ptd {
 void kernels_init();
-void launch_begin_batch(BatchCtl* ctl, uint32_t n_paths, cudaStream_t st);
-void launch_camera(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_paths, cudaStream_t st);
-void launch_load_rays(const double* origins, const double* dirs, const NodePool& pool, uint32_t first, uint32_t n_paths,
-                      cudaStream_t st);
-void launch_extend(const DScene& sc, const NodePool& pool, BatchCtl* ctl, int level, uint32_t max_items, bool count,
-                   cudaStream_t st);
-void launch_shadow(const DScene& sc, const FrameParams& fp, const NodePool& pool, BatchCtl* ctl, int level,
-                   uint32_t first_slot, uint32_t max_items, bool count, cudaStream_t st);
-void launch_shade(const DScene& sc, const FrameParams& fp, const NodePool& pool, BatchCtl* ctl, int level,
-                  uint32_t first_slot, uint32_t max_items, cudaStream_t st);
-void launch_tree_eval(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_paths, cudaStream_t st);
-void launch_resolve(const FrameParams& fp, const NodePool& pool, uint32_t first_slot, uint32_t n_slots, uint8_t* rgb,
-                    uint32_t* hit_id, double* hit_t, cudaStream_t st);
-void launch_export_rays(const NodePool& pool, uint32_t first, uint32_t n_paths, double* color, uint32_t* hit_id,
-                        double* hit_t, cudaStream_t st);
+// copy a frame's constants into __constant__ slot `slot` (stream-ordered)
+cudaError_t upload_state(int slot, const FrameState& state, cudaStream_t st);
+
+// stream path: one launch per call; batch / level bookkeeping lives in the device control block
+void launch_camera(int slot, uint32_t first_slot, uint32_t n_slots, uint32_t samples, cudaStream_t st);
+void launch_load_rays(int slot, uint32_t first, uint32_t n_paths, cudaStream_t st);
+void launch_extend(int slot, uint64_t max_items, bool count, cudaStream_t st);
+void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, bool count, cudaStream_t st);
+void launch_shade(int slot, uint64_t max_items, cudaGraphConditionalHandle loop, cudaStream_t st);
+void launch_tree_eval(int slot, uint32_t n_paths, cudaStream_t st);
+void launch_resolve(int slot, uint32_t n_slots, cudaStream_t st);
+void launch_export_rays(int slot, uint32_t n_paths, cudaStream_t st);
+
+// graph path: camera -> WHILE(level has rays){extend, shadow, shade} -> tree_eval -> resolve
+cudaError_t build_frame_graph(int slot, uint32_t n_slots, uint32_t samples, uint32_t n_lights_max, uint64_t capacity,
+                              bool count, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out, cudaGraphNode_t* camera_node);
+cudaError_t set_graph_batch(cudaGraphExec_t exec, cudaGraphNode_t camera_node, int slot, uint32_t first_slot, uint32_t n_slots,
+                            uint32_t grid_slots, uint32_t samples);
 }  // namespace ptd

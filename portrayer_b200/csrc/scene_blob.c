@@ -119,13 +119,18 @@ static int kd_tree_ok(const PtKdNode* nodes, uint32_t n_nodes, uint32_t n_items_
     return 1;
 }
 
-int pt_scene_unpack(const void* blob, uint64_t bytes, PtSceneDesc* d) {
+static int unpack_impl(const void* blob, uint64_t bytes, PtSceneDesc* d, int records_only) {
     if (!blob || !d || bytes < sizeof(PtBlobHeader)) return PT_ERR_INVALID;
     PtBlobHeader h;
     memcpy(&h, blob, sizeof h);
     if (h.magic != PT_BLOB_MAGIC || h.version != PT_BLOB_VERSION) return PT_ERR_INVALID;
-    if (h.total_bytes > bytes) return PT_ERR_INVALID;
-    const uint64_t T = h.total_bytes;
+    if (records_only) {
+        /* the texel section may be missing: everything before it must be there */
+        if (h.off_texels > h.total_bytes || h.off_texels > bytes) return PT_ERR_INVALID;
+    } else if (h.total_bytes > bytes) {
+        return PT_ERR_INVALID;
+    }
+    const uint64_t T = records_only ? h.off_texels : h.total_bytes;
     const unsigned char* base = (const unsigned char*)blob;
     if (!section_ok(h.off_tlas_nodes, (uint64_t)h.n_tlas_nodes * sizeof(PtKdNode), T) ||
         !section_ok(h.off_tlas_items, (uint64_t)h.n_tlas_items * sizeof(uint32_t), T) ||
@@ -140,7 +145,7 @@ int pt_scene_unpack(const void* blob, uint64_t bytes, PtSceneDesc* d) {
         !section_ok(h.off_materials, (uint64_t)h.n_materials * sizeof(PtMaterial), T) ||
         !section_ok(h.off_lights, (uint64_t)h.n_lights * sizeof(PtLight), T) ||
         !section_ok(h.off_textures, (uint64_t)h.n_textures * sizeof(PtTexture), T) ||
-        !section_ok(h.off_texels, h.n_texel_bytes, T))
+        (!records_only && !section_ok(h.off_texels, h.n_texel_bytes, T)))
         return PT_ERR_INVALID;
 
     memset(d, 0, sizeof *d);
@@ -160,7 +165,7 @@ int pt_scene_unpack(const void* blob, uint64_t bytes, PtSceneDesc* d) {
     d->n_materials = h.n_materials;     d->materials = (const PtMaterial*)(base + h.off_materials);
     d->n_lights = h.n_lights;           d->lights = (const PtLight*)(base + h.off_lights);
     d->n_textures = h.n_textures;       d->textures = (const PtTexture*)(base + h.off_textures);
-    d->n_texel_bytes = h.n_texel_bytes; d->texels = base + h.off_texels;
+    d->n_texel_bytes = h.n_texel_bytes; d->texels = records_only ? NULL : base + h.off_texels;
 
     /* semantic validation: every index the kernels will follow must be in range */
     if (d->n_tlas_nodes == 0 || d->n_lights > PT_MAX_LIGHTS) return PT_ERR_INVALID;
@@ -212,3 +217,6 @@ int pt_scene_unpack(const void* blob, uint64_t bytes, PtSceneDesc* d) {
     }
     return PT_OK;
 }
+
+int pt_scene_unpack(const void* blob, uint64_t bytes, PtSceneDesc* d) { return unpack_impl(blob, bytes, d, 0); }
+int pt_scene_unpack_records(const void* blob, uint64_t bytes, PtSceneDesc* d) { return unpack_impl(blob, bytes, d, 1); }

@@ -195,15 +195,16 @@ PT_D long long rem_euclid(long long value, long long rhs) {  // texture.rs:107-1
 }
 // RgbImageBuffer::at, texture.rs:104-141
 PT_D void texture_at(const DScene& sc, int tex, double u, double v, double* rgb) {
-    const PtTexture* t = sc.textures + tex;
-    const uint2 wh = __ldg(reinterpret_cast<const uint2*>(t));
-    const unsigned long long offset = __ldg(reinterpret_cast<const unsigned long long*>(&t->offset));
+    const TextureDev* t = sc.textures + tex;
+    const uint4 rec = __ldg(reinterpret_cast<const uint4*>(t));  // width, height, texel pointer
+    const uint2 wh = make_uint2(rec.x, rec.y);
+    const uint8_t* texels = reinterpret_cast<const uint8_t*>(((unsigned long long)rec.w << 32) | rec.z);
     const long long width = wh.x, height = wh.y;
     const long long x = f64_as_i64(u * (double)(width - 1));
     const long long y = f64_as_i64(v * (double)(height - 1));
     const unsigned xi = (unsigned)rem_euclid(x, width);
     const unsigned yi = (unsigned)rem_euclid(y, height);
-    const uint8_t* p = sc.texels + offset + ((unsigned long long)yi * wh.x + xi) * 3ull;
+    const uint8_t* p = texels + ((unsigned long long)yi * wh.x + xi) * 3ull;
     rgb[0] = (double)__ldg(p) / 255.0;
     rgb[1] = (double)__ldg(p + 1) / 255.0;
     rgb[2] = (double)__ldg(p + 2) / 255.0;

@@ -92,7 +92,7 @@ struct Builder {
         if (it != texture_ids.end()) return static_cast<int32_t>(it->second);
         // keep every texture 128-byte aligned in the pool
         while (texels.size() % 128) texels.push_back(0);
-        PtTexture t{buf->width, buf->height, texels.size()};
+        PtTexture t{buf->width, buf->height, texels.size(), buf->content_key(), 0};
         texels.insert(texels.end(), buf->data.begin(), buf->data.end());
         uint32_t id = static_cast<uint32_t>(textures.size());
         textures.push_back(t);

@@ -12,6 +12,7 @@
 //   Triangle/MeshData   src/primitive/triangle.rs:9-36, src/primitive/mesh.rs:12-143
 //   CameraSettings      src/camera.rs:5-14
 #pragma once
+#include <cstring>
 #include <cassert>
 #include <functional>
 #include <memory>
@@ -33,6 +34,29 @@ struct RgbImageBuffer {
     std::vector<uint8_t> data;  // RGB8 row-major
     std::string name;
     static std::shared_ptr<RgbImageBuffer> open(const std::string& path);
+    // Identity of the texel content for the device-side texture residency cache (PtTexture.key):
+    // 64-bit FNV-1a over (width, height, texels), computed once per loaded image.  The Rust glue
+    // would use the Arc's address instead; a content hash also survives re-loading the same file.
+    uint64_t content_key() const {
+        if (key_ == 0) {
+            uint64_t h = 0xCBF29CE484222325ull;
+            auto mix = [&h](uint64_t v) { h = (h ^ v) * 0x100000001B3ull; };
+            mix(width);
+            mix(height);
+            size_t i = 0;
+            for (; i + 8 <= data.size(); i += 8) {
+                uint64_t w;
+                memcpy(&w, data.data() + i, 8);
+                mix(w);
+            }
+            for (; i < data.size(); ++i) mix(data[i]);
+            key_ = h ? h : 1;
+        }
+        return key_;
+    }
+
+private:
+    mutable uint64_t key_ = 0;
 };
 struct ImageTexture {  // src/texture.rs:149-169
     std::shared_ptr<RgbImageBuffer> buffer;

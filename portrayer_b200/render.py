@@ -65,6 +65,11 @@ class DeviceScene:
     def handle(self) -> C.c_void_p:
         return self._h
 
+    @property
+    def uploaded_bytes(self) -> int:
+        """host -> device bytes of the upload (records + textures that were not already resident)"""
+        return gpu.pt_scene_uploaded_bytes(self._h)
+
     def render(self, camera: PtCamera, params: PtRenderParams, background: np.ndarray, rgb: np.ndarray,
                hit_id: np.ndarray | None = None, hit_t: np.ndarray | None = None, progress=None) -> PtStats:
         """pt_render with HOST buffers: H2D of the background, kernels, D2H of the outputs."""
