@@ -13,7 +13,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("PORTRAYER_LIB_DIR") or os.path.join(_HERE, "lib")  # override: A/B builds of the native libraries
 
 
 def _load(name: str) -> C.CDLL:

@@ -170,6 +170,7 @@ struct PtScene {
     DScene view{};
     bool has_reflective = false;
     TextureDev* d_textures = nullptr;
+    float4* d_aabb = nullptr;               // padded FP32 world box per instance (conservative cull, traverse.cuh)
     std::vector<uint64_t> resident_keys;    // textures held in the residency cache (refs to drop)
     std::vector<uint8_t*> private_texels;   // unkeyed textures owned by this scene
     uint64_t h2d_bytes = 0;                 // bytes the upload copied to the device
@@ -256,6 +257,7 @@ void fill_view(PtScene* s) {
     v.materials = reinterpret_cast<const PtMaterial*>(b + h.off_materials);
     v.lights = reinterpret_cast<const PtLight*>(b + h.off_lights);
     v.textures = s->d_textures;
+    v.inst_aabb = s->d_aabb;
     v.ambient[0] = h.ambient[0]; v.ambient[1] = h.ambient[1]; v.ambient[2] = h.ambient[2];
     v.tlas_extent = h.tlas_extent;
     v.n_lights = h.n_lights;
@@ -272,6 +274,7 @@ void free_scene(PtScene* s) {
     }
     for (uint8_t* p : s->private_texels) g_dev.release(p);
     g_dev.release(s->d_textures);
+    g_dev.release(s->d_aabb);
     g_dev.release(s->d_records);
     delete s;
 }
@@ -346,6 +349,22 @@ int bind_textures(PtScene* s, const PtTexture* tex, const unsigned char* texel_s
     // pageable source: the copy is staged before the call returns, so `table` may go out of scope
     CUDA_TRY(cudaMemcpyAsync(s->d_textures, table.data(), n * sizeof(TextureDev), cudaMemcpyHostToDevice, g_stream));
     s->h2d_bytes += n * sizeof(TextureDev);
+    return PT_OK;
+}
+
+// instance boxes for the FP32 cull, computed on the device from the uploaded records
+int build_instance_bounds(PtScene* s) {
+    const uint32_t n = s->h.n_instances;
+    cudaError_t e;
+    s->d_aabb = static_cast<float4*>(g_dev.alloc(std::max<size_t>(n, 1) * 2 * sizeof(float4), &e));
+    if (!s->d_aabb) return fail(PT_ERR_CUDA, "instance bounds allocation failed: %s", cudaGetErrorString(e));
+    double* scratch = static_cast<double*>(g_dev.alloc(std::max<size_t>(s->h.n_meshes, 1) * 6 * sizeof(double), &e));
+    if (!scratch) return fail(PT_ERR_CUDA, "mesh bounds allocation failed: %s", cudaGetErrorString(e));
+    fill_view(s);
+    launch_instance_bounds(s->view, s->h.n_meshes, scratch, s->d_aabb, g_stream);
+    g_dev.release(scratch);  // stream-ordered reuse: later users of the block run after this kernel on g_stream
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "instance bounds kernel failed: %s", cudaGetErrorString(e));
     return PT_OK;
 }
 
@@ -789,6 +808,7 @@ int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out) {
     const unsigned char* base = static_cast<const unsigned char*>(blob);
     rc = bind_textures(s, reinterpret_cast<const PtTexture*>(base + s->h.off_textures),
                        texels_present ? base + s->h.off_texels : nullptr, cudaMemcpyHostToDevice);
+    if (rc == PT_OK) rc = build_instance_bounds(s);
     if (rc == PT_OK) {
         e = cudaStreamSynchronize(g_stream);  // the caller may free / reuse `blob` when this returns
         if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
@@ -828,6 +848,7 @@ int pt_scene_upload_device(const void* d_blob, uint64_t bytes, PtScene** out) {
     rc = bind_textures(s, reinterpret_cast<const PtTexture*>(host.data() + h.off_textures),
                        texels_present ? static_cast<const unsigned char*>(d_blob) + h.off_texels : nullptr,
                        cudaMemcpyDeviceToDevice);
+    if (rc == PT_OK) rc = build_instance_bounds(s);
     if (rc == PT_OK) {
         e = cudaStreamSynchronize(g_stream);
         if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));

@@ -30,6 +30,7 @@ struct DScene {
     const PtMaterial* materials;
     const PtLight* lights;
     const TextureDev* textures;
+    const float4* inst_aabb;  // [2 * n_instances] padded world-space box of every instance (lo, hi), FP32, rounded outward
     double ambient[3];
     double tlas_extent;
     uint32_t n_lights;

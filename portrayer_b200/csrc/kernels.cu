@@ -28,6 +28,17 @@ __constant__ FrameState c_state[kStateSlots];
 namespace {
 
 constexpr int kBlock = 128;
+// minimum resident blocks per SM asked of ptxas (register budget = 65536 / (kBlock * min blocks)); tuned on B200,
+// see DESIGN.md "occupancy"
+#ifndef PT_EXTEND_MIN_BLOCKS
+#define PT_EXTEND_MIN_BLOCKS 4
+#endif
+#ifndef PT_SHADOW_MIN_BLOCKS
+#define PT_SHADOW_MIN_BLOCKS 5
+#endif
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 5
+#endif
 
 PT_D void background_of(const FrameParams& fp, uint32_t pixel, double* bg) {
     const double* src = fp.bg_mode == PT_BG_PER_PIXEL ? fp.background + (size_t)pixel * 3
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(kBlock) load_rays_kernel(int slot_id, uint32_t
 
 // ------------------------------------------------------------------ extend (closest hit)
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) extend_kernel(int slot_id) {
+__global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(int slot_id) {
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
     const NodePool& pool = fs.pool;
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(kBlock) extend_kernel(int slot_id) {
 
 // ------------------------------------------------------------------ shadow (any hit), light-major
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) shadow_kernel(int slot_id) {
+__global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(int slot_id) {
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
     const FrameParams& fp = fs.fp;
@@ -205,7 +216,7 @@ PT_D uint32_t warp_alloc(BatchCtl* ctl, bool want) {
 
 // `loop`: the conditional handle of the frame graph's WHILE node (0 on the stream path); the last block to
 // finish decides whether another recursion level has rays to trace.
-__global__ void __launch_bounds__(kBlock) shade_kernel(int slot_id, cudaGraphConditionalHandle loop) {
+__global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int slot_id, cudaGraphConditionalHandle loop) {
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
     const FrameParams& fp = fs.fp;
@@ -587,6 +598,95 @@ __global__ void __launch_bounds__(kBlock) export_rays_kernel(int slot_id) {
     hit_t[i] = pool.t[p];
 }
 
+// ------------------------------------------------------------------ instance bounds (upload time)
+// Object-space bounds of every mesh: one block per mesh, min/max over its triangle vertices.
+__global__ void __launch_bounds__(kBlock) mesh_bounds_kernel(const PtMesh* __restrict__ meshes, const PtTriPos* __restrict__ tri_pos,
+                                                            uint32_t n_meshes, double* __restrict__ out /* [n_meshes][6] */) {
+    const uint32_t m = blockIdx.x;
+    if (m >= n_meshes) return;
+    const uint32_t first = meshes[m].tri_first, count = meshes[m].tri_count;
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) {
+        const double* v = reinterpret_cast<const double*>(tri_pos + first + k);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const double x = v[c];
+            lo[c % 3] = fmin(lo[c % 3], x);
+            hi[c % 3] = fmax(hi[c % 3], x);
+        }
+    }
+    __shared__ double s_lo[kBlock / 32][3], s_hi[kBlock / 32][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_down_sync(0xFFFFFFFFu, lo[c], off));
+            hi[c] = fmax(hi[c], __shfl_down_sync(0xFFFFFFFFu, hi[c], off));
+        }
+        if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5][c] = lo[c]; s_hi[threadIdx.x >> 5][c] = hi[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        double l = s_lo[0][c], h = s_hi[0][c];
+        for (int w = 1; w < kBlock / 32; ++w) { l = fmin(l, s_lo[w][c]); h = fmax(h, s_hi[w][c]); }
+        out[m * 6 + c] = l;
+        out[m * 6 + 3 + c] = h;
+    }
+}
+
+// Padded world-space box of every flat instance, FP32, rounded outward (the FP32 cull of traverse.cuh).
+// Object boxes: unit sphere [-1,1]^3 (sphere.rs), everything else analytic [-0.5,0.5]^3 (cube / cylinder / cone;
+// the plane is the y = 0 slice of it), meshes their vertex bounds; all grown by 1e-4 of their size, which
+// covers the 1e-5 slack of Cube::contains / Plane (cube.rs:22-27, plane.rs:43).
+__global__ void __launch_bounds__(kBlock) instance_bounds_kernel(const PtInstance* __restrict__ instances,
+                                                                const PtInstanceTrans* __restrict__ trans, uint32_t n,
+                                                                const double* __restrict__ mesh_bounds, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t prim = instances[i].prim;
+    double lo[3], hi[3];
+    if (prim == PT_PRIM_SPHERE) {
+        lo[0] = lo[1] = lo[2] = -1.0; hi[0] = hi[1] = hi[2] = 1.0;
+    } else if (prim == PT_PRIM_TRIANGLE || prim == PT_PRIM_MESH || prim == PT_PRIM_KDMESH) {
+        const double* b = mesh_bounds + (size_t)instances[i].mesh * 6;
+        for (int c = 0; c < 3; ++c) { lo[c] = b[c]; hi[c] = b[3 + c]; }
+    } else {
+        lo[0] = lo[1] = lo[2] = -0.5; hi[0] = hi[1] = hi[2] = 0.5;
+        if (prim == PT_PRIM_PLANE) { lo[1] = 0.0; hi[1] = 0.0; }
+    }
+    double diag = 0.0;
+    for (int c = 0; c < 3; ++c) diag = fmax(diag, hi[c] - lo[c]);
+    for (int c = 0; c < 3; ++c) {
+        const double g = 1e-4 * diag + 1e-4 * fmax(fabs(lo[c]), fabs(hi[c]));
+        lo[c] -= g;
+        hi[c] += g;
+    }
+    const double* m = trans[i].trans;  // object -> world, rows 0..2
+    double wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool finite = true;
+    for (int corner = 0; corner < 8; ++corner) {
+        const double x = (corner & 1) ? hi[0] : lo[0], y = (corner & 2) ? hi[1] : lo[1], z = (corner & 4) ? hi[2] : lo[2];
+        for (int r = 0; r < 3; ++r) {
+            const double w = m[r * 4 + 0] * x + m[r * 4 + 1] * y + m[r * 4 + 2] * z + m[r * 4 + 3];
+            if (!isfinite(w)) finite = false;
+            wlo[r] = fmin(wlo[r], w);
+            whi[r] = fmax(whi[r], w);
+        }
+    }
+    float flo[3], fhi[3];
+    double wdiag = 0.0;
+    for (int r = 0; r < 3; ++r) wdiag = fmax(wdiag, whi[r] - wlo[r]);
+    for (int r = 0; r < 3; ++r) {
+        const double g = 1e-5 * fmax(fabs(wlo[r]), fabs(whi[r])) + 1e-5 * wdiag + 1e-30;
+        flo[r] = __double2float_rd(wlo[r] - g);
+        fhi[r] = __double2float_ru(whi[r] + g);
+        if (!finite || !(wlo[r] <= whi[r])) { flo[r] = -INFINITY; fhi[r] = INFINITY; }  // never cull what cannot be bounded
+    }
+    out[2 * (size_t)i] = make_float4(flo[0], flo[1], flo[2], 0.f);
+    out[2 * (size_t)i + 1] = make_float4(fhi[0], fhi[1], fhi[2], 0.f);
+}
+
 int g_grid_extend[2] = {0, 0}, g_grid_shadow[2] = {0, 0}, g_grid_shade = 0;
 
 template <class K>
@@ -614,6 +714,13 @@ static inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 
 static inline int capped(int grid, uint64_t max_items) {
     const uint64_t need = blocks_for(max_items ? max_items : 1);
     return (uint64_t)grid > need ? (int)need : grid;
+}
+
+void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bounds_scratch, float4* out, cudaStream_t st) {
+    if (n_meshes) mesh_bounds_kernel<<<n_meshes, kBlock, 0, st>>>(sc.meshes, sc.tri_pos, n_meshes, mesh_bounds_scratch);
+    if (sc.n_instances)
+        instance_bounds_kernel<<<blocks_for(sc.n_instances), kBlock, 0, st>>>(sc.instances, sc.instance_trans, sc.n_instances,
+                                                                            mesh_bounds_scratch, out);
 }
 
 cudaError_t upload_state(int slot, const FrameState& state, cudaStream_t st) {

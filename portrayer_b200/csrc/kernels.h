@@ -9,6 +9,9 @@ void kernels_init();
 // copy a frame's constants into __constant__ slot `slot` (stream-ordered)
 cudaError_t upload_state(int slot, const FrameState& state, cudaStream_t st);
 
+// upload time: padded FP32 world boxes of all instances (mesh_bounds_scratch: n_meshes * 6 doubles)
+void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bounds_scratch, float4* out, cudaStream_t st);
+
 // stream path: one launch per call; batch / level bookkeeping lives in the device control block
 void launch_camera(int slot, uint32_t first_slot, uint32_t n_slots, uint32_t samples, cudaStream_t st);
 void launch_load_rays(int slot, uint32_t first, uint32_t n_paths, cudaStream_t st);

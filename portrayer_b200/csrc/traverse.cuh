@@ -355,11 +355,49 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     return hit;
 }
 
+// ------------------------------------------------------------------ conservative FP32 cull
+// Before an instance is tested exactly (f64, object space) its padded world-space bounding box
+// (DScene::inst_aabb, built at upload by instance_bounds_kernel) is slab-tested in FP32.  The test
+// may only answer "certainly no hit inside [s, e)": every rounding source is covered by padding
+// that is orders of magnitude larger than the FP32 error (the box is padded at build time, the ray
+// origin by 4e-6 * |o|, the slab parameters by 2e-5 relative), so a candidate the f64 test would
+// accept is never dropped and the result stays bit-identical to the un-culled walk.  The cull runs
+// on the FP32 pipe; the f64 pipe — the binding resource of this kernel — only sees the survivors.
+struct RayF {
+    float ox_lo, oy_lo, oz_lo;  // origin + pad  (subtracted from box minima)
+    float ox_hi, oy_hi, oz_hi;  // origin - pad  (subtracted from box maxima)
+    float ix, iy, iz;           // 1 / direction (inf when a component is 0)
+};
+PT_D RayF make_rayf(V3 o, V3 d) {
+    RayF r;
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float pad = 4e-6f * fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz)));
+    r.ox_lo = ox + pad; r.oy_lo = oy + pad; r.oz_lo = oz + pad;
+    r.ox_hi = ox - pad; r.oy_hi = oy - pad; r.oz_hi = oz - pad;
+    r.ix = 1.0f / (float)d.x; r.iy = 1.0f / (float)d.y; r.iz = 1.0f / (float)d.z;
+    return r;
+}
+// false = the ray certainly misses the instance inside [s, e)
+PT_D bool aabb_may_hit(const float4* __restrict__ bb, const RayF& r, double s, double e) {
+    const float4 lo = __ldg(bb), hi = __ldg(bb + 1);
+    const float ax = (lo.x - r.ox_lo) * r.ix, bx = (hi.x - r.ox_hi) * r.ix;
+    const float ay = (lo.y - r.oy_lo) * r.iy, by = (hi.y - r.oy_hi) * r.iy;
+    const float az = (lo.z - r.oz_lo) * r.iz, bz = (hi.z - r.oz_hi) * r.iz;
+    // fminf / fmaxf drop a NaN operand (0 * inf on a slab boundary): the slab then does not constrain
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    tn -= 2e-5f * fabsf(tn);
+    tf += 2e-5f * fabsf(tf);
+    const float sf = (float)s * 0.9999f, ef = (float)e * 1.0001f;  // s, e > 0
+    return !(tn > tf) && !(tf < sf) && !(tn > ef);
+}
+
 // leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99)
 template <bool ANY>
 struct TlasLeaf {
     const DScene& sc;
     V3 o, d;
+    RayF rf;
     KdStack& blas_stack;
     Hit& hit;
     uint32_t& err;
@@ -369,6 +407,7 @@ struct TlasLeaf {
         for (uint32_t k = 0; k < count; ++k) {
             const uint32_t inst = __ldg(sc.tlas_items + first + k);
             ++wc.instance_tests;
+            if (!aabb_may_hit(sc.inst_aabb + 2 * (size_t)inst, rf, s, e)) continue;
             // FlatSceneNode::ray_cast: the ray in object space, direction NOT renormalised (flat_scene.rs:75, ray.rs:130-135)
             const PtInstance* rec = sc.instances + inst;
             double m[12];
@@ -394,7 +433,7 @@ struct TlasLeaf {
 template <bool ANY>
 PT_D bool scene_cast(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& tlas_stack, KdStack& blas_stack, uint32_t& err,
                      WorkCounters& wc) {
-    TlasLeaf<ANY> leaf{sc, o, d, blas_stack, hit, err, wc};
+    TlasLeaf<ANY> leaf{sc, o, d, make_rayf(o, d), blas_stack, hit, err, wc};
     return kd_walk(sc.tlas_nodes, sc.tlas_extent, o, d, kEps, (double)INFINITY, tlas_stack, leaf, err, wc.kd_splits);
 }
 

@@ -1,0 +1,112 @@
+"""The C-ABI library without a GPU: it loads, exports every symbol include/portrayer_gpu.h declares, and its
+pure-host entry points (blob pack / unpack / validation, tile ownership, error strings) behave.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(REPO, "include", "portrayer_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(native_libraries):
+    from portrayer_b200 import _ffi
+
+    names = _declared_functions()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(_ffi.gpu, name), f"{name} is declared in include/portrayer_gpu.h but not exported"
+        assert name in _ffi.GPU_SYMBOLS, f"{name} has no ctypes signature in portrayer_b200/_ffi.py"
+
+
+def test_struct_sizes_match_the_header(native_libraries):
+    """ctypes mirrors vs the sizes the header documents (a mismatch would silently corrupt the blob)."""
+    from portrayer_b200 import _ffi
+
+    assert C.sizeof(_ffi.PtCamera) == 23 * 8
+    assert C.sizeof(_ffi.PtRenderParams) == 88
+    assert C.sizeof(_ffi.PtBlobHeader) % 8 == 0
+
+
+def test_error_strings_are_the_reference_panics(native_libraries):
+    from portrayer_b200 import _ffi
+
+    s = lambda code: _ffi.gpu.pt_error_string(code).decode()
+    assert s(_ffi.PT_ERR_NO_TEXCOORD_NORMALMAP) == "Normal/Texture mapping is not supported for this primitive!"  # material.rs:133
+    assert s(_ffi.PT_ERR_NO_TEXCOORD_TEXTURE) == "Texture mapping is not supported for this primitive!"  # material.rs:141
+    assert s(_ffi.PT_ERR_KD_PLANE_MISS) == "bug: ray should definitely hit infinite plane"  # kdtree/node.rs:147,178
+    assert s(_ffi.PT_ERR_TIR_INSIDE) == "bug: should not have total internal reflection when casting inside surface"  # material.rs:258
+
+
+def test_blob_unpack_validates(native_libraries):
+    import portrayer_b200 as pt
+    from portrayer_b200 import _ffi
+
+    scene = pt.Scene.example("nonhier")
+    blob = scene.blob.copy()
+    desc = (C.c_uint8 * 512)()  # PtSceneDesc is < 512 bytes
+    assert _ffi.gpu.pt_scene_unpack(blob.ctypes.data, blob.nbytes, desc) == 0
+    # records-only view: stops at the texel section
+    h = scene.header
+    assert _ffi.gpu.pt_scene_unpack_records(blob.ctypes.data, h.off_texels, desc) == 0
+    assert _ffi.gpu.pt_scene_unpack(blob.ctypes.data, h.off_texels - 1, desc) != 0
+    # truncated
+    assert _ffi.gpu.pt_scene_unpack(blob.ctypes.data, blob.nbytes - 1, desc) != 0
+    # bad magic
+    bad = blob.copy()
+    bad[0] ^= 0xFF
+    assert _ffi.gpu.pt_scene_unpack(bad.ctypes.data, bad.nbytes, desc) != 0
+    # an instance index out of range in a leaf
+    bad = blob.copy()
+    items = np.frombuffer(bad, dtype=np.uint32, count=h.n_tlas_items, offset=h.off_tlas_items)
+    items[0] = h.n_instances
+    assert _ffi.gpu.pt_scene_unpack(bad.ctypes.data, bad.nbytes, desc) != 0
+    # a kd child pointing backwards (cycle)
+    bad = blob.copy()
+    nodes = np.frombuffer(bad, dtype=np.uint32, count=h.n_tlas_nodes * 4, offset=h.off_tlas_nodes).reshape(-1, 4)
+    split = np.where((nodes[:, 2] & 3) != 3)[0]
+    if len(split):
+        nodes[split[0], 3] = 0
+        assert _ffi.gpu.pt_scene_unpack(bad.ctypes.data, bad.nbytes, desc) != 0
+    # a material pointing at a texture that does not exist
+    bad = blob.copy()
+    mats = np.frombuffer(bad, dtype=np.int32, count=h.n_materials * 40, offset=h.off_materials).reshape(-1, 40)
+    mats[0, 38] = 5
+    assert _ffi.gpu.pt_scene_unpack(bad.ctypes.data, bad.nbytes, desc) != 0
+
+
+def test_no_cpu_fallback_without_a_device(native_libraries):
+    """On a machine without a GPU the library must refuse to render, loudly (this container has none)."""
+    import torch
+
+    from portrayer_b200 import _ffi
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert _ffi.gpu.pt_device_count() == 0
+    assert _ffi.gpu.pt_init(0) == _ffi.PT_ERR_CUDA
+    assert b"no CPU fallback" in _ffi.gpu.pt_last_error()
+    import portrayer_b200 as pt
+
+    with pytest.raises(pt.PortrayerError):
+        pt.DeviceScene(pt.Scene.example("nonhier").blob)
+
+
+def test_product_code_never_touches_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may import / link / execute oracle/."""
+    pattern = re.compile(r"import\s+oracle|from\s+oracle|liboracle|oracle\.h|oracle/oracle|oracle_render|oracle_trace")
+    offenders = []
+    for root in ("portrayer_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(REPO, root)):
+            for f in files:
+                if f.endswith((".py", ".c", ".cpp", ".cu", ".cuh", ".h", ".hpp")):
+                    if pattern.search(open(os.path.join(dirpath, f), errors="ignore").read()):
+                        offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders

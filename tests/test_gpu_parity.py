@@ -159,3 +159,81 @@ def test_reference_panic_is_reported(gpu_ready):
     with pytest.raises(pt.PortrayerError) as err:
         ds.render(scene.camera(64, 36), params, np.zeros(3), img.buffer)
     assert "mapping is not supported for this primitive!" in str(err.value)
+
+
+def test_graph_and_stream_paths_agree(gpu_ready):
+    """The frame CUDA graph (conditional WHILE over recursion levels) and the kernel-by-kernel stream path run the
+    same kernels: identical images, hit ids, ray counts — also with several batches per frame."""
+    from portrayer_b200 import _ffi
+
+    scene = pt.Scene.example("glossy-reflection")
+    kw = dict(samples=3, rng="hash", size=(300, 170))
+    a, sa = parity.render_gpu(scene, **kw)
+    b, sb = parity.render_gpu(scene, flags=_ffi.PT_RENDER_NO_GRAPH, **kw)
+    c, sc = parity.render_gpu(scene, max_batch_paths=30000, **kw)  # 6 graph replays
+    d, sd = parity.render_gpu(scene, flags=_ffi.PT_RENDER_KERNEL_TIMES, **kw)
+    for other, st in ((b, sb), (c, sc), (d, sd)):
+        assert np.array_equal(a.buffer, other.buffer) and np.array_equal(a.hit_id, other.hit_id)
+        assert (st.rays_primary, st.rays_shadow, st.rays_reflect, st.rays_refract) == \
+               (sa.rays_primary, sa.rays_shadow, sa.rays_reflect, sa.rays_refract)
+    assert sc.batches >= 5 and sa.batches == 1
+    assert sd.n_extend > 0 and sd.ms_extend > 0.0
+    # only the levels that hold rays are launched: far fewer than 3 kernels x 11 levels
+    assert sa.kernel_launches <= 3 + 3 * (sa.max_level + 1)
+
+
+def test_node_pool_overflow_falls_back_and_matches(gpu_ready):
+    """A node pool too small for the batch's ray trees: the graph path notices after its single sync, the frame is
+    redone with halved batches, and the image is the same."""
+    scene = pt.Scene.example("glossy-reflection")
+    kw = dict(samples=2, rng="hash", size=(200, 120))
+    a, _ = parity.render_gpu(scene, **kw)
+    b, sb = parity.render_gpu(scene, max_batch_paths=48000, node_pool_capacity=50000, **kw)
+    assert np.array_equal(a.buffer, b.buffer)
+    assert sb.retries >= 1
+
+
+@pytest.mark.skipif(not has_reference_assets(), reason="reference textures not synced (tools/sync_assets.py)")
+def test_texture_residency_cache(gpu_ready):
+    """PtTexture.key keeps texels in HBM between scenes: the second upload of a scene copies records only, a
+    records-only blob (cut at off_texels) is accepted while its textures are resident, and renders are identical."""
+    from portrayer_b200 import _ffi
+
+    _ffi.gpu.pt_release_cached_memory()
+    assert _ffi.gpu.pt_resident_texture_bytes() == 0
+    scene = pt.Scene.example("normal-mapping")
+    h = scene.header
+    assert h.n_textures > 0 and h.n_texel_bytes > 1 << 20
+    first = pt.DeviceScene(scene.blob)
+    assert first.uploaded_bytes > h.n_texel_bytes * 0.9  # cold: the texels crossed PCIe
+    resident = _ffi.gpu.pt_resident_texture_bytes()
+    assert resident > 0
+    second = pt.DeviceScene(scene.blob)
+    assert second.uploaded_bytes < h.off_texels + 4096  # warm: records (+ the texture table) only
+    assert _ffi.gpu.pt_resident_texture_bytes() == resident
+    records_only = pt.DeviceScene(scene.blob[: h.off_texels])
+    kw = dict(samples=1, rng="fixed", size=(227, 128))
+    a, _ = parity.render_gpu(scene, dscene=first, **kw)
+    b, _ = parity.render_gpu(scene, dscene=second, **kw)
+    c, _ = parity.render_gpu(scene, dscene=records_only, **kw)
+    ref = parity.render_oracle(scene, **kw)
+    parity.assert_parity(parity.compare(a, ref, "resident textures"))
+    assert np.array_equal(a.buffer, b.buffer) and np.array_equal(a.buffer, c.buffer)
+    for ds in (first, second, records_only):
+        ds.close()
+    # unreferenced now: released on request; a records-only upload must then be refused, loudly
+    _ffi.gpu.pt_release_cached_memory()
+    assert _ffi.gpu.pt_resident_texture_bytes() == 0
+    with pytest.raises(pt.PortrayerError) as err:
+        pt.DeviceScene(scene.blob[: h.off_texels])
+    assert "not resident" in str(err.value)
+
+
+def test_frame_cache_rebinds_between_scenes(gpu_ready):
+    """pt_render keeps frames (buffers + graph) per image geometry and re-binds them to the next scene."""
+    a1, _ = parity.render_gpu(pt.Scene.example("nonhier"), samples=1, rng="fixed", size=(128, 128))
+    b1, _ = parity.render_gpu(pt.Scene.example("primitives"), samples=1, rng="fixed", size=(128, 128))
+    a2, _ = parity.render_gpu(pt.Scene.example("nonhier"), samples=1, rng="fixed", size=(128, 128))
+    b2, _ = parity.render_gpu(pt.Scene.example("primitives"), samples=1, rng="fixed", size=(128, 128))
+    assert np.array_equal(a1.buffer, a2.buffer) and np.array_equal(b1.buffer, b2.buffer)
+    assert not np.array_equal(a1.buffer, b1.buffer)
