@@ -267,8 +267,10 @@ def run_ours(args, rank, world, local_rank):
         """one pass over the workload, device-resident; returns device ms (torch events on the launch stream)"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        for j in jobs:  # all frames of the step go onto the stream back to back; nothing waits for the device here
+            j.frame.enqueue(stream=stream)
         for j in jobs:
-            st = j.frame.render(stream=stream)
+            st = j.frame.finish()
             if collect is not None:
                 collect.append(st)
             if world > 1:
@@ -358,6 +360,9 @@ def run_ours(args, rank, world, local_rank):
         pass
     elif world == 1:
         # cold: nothing cached in the library (first render of a program: textures cross PCIe, buffers are allocated)
+        for j in jobs:  # the device-resident frames / scenes of the timed region hold texture references: drop them
+            j.frame.close()
+            j.dscene.close()
         _ffi.gpu.pt_release_cached_memory()
         torch.cuda.synchronize()
         t0 = time.perf_counter()

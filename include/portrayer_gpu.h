@@ -368,6 +368,11 @@ int pt_frame_set_background(PtFrame* frame, const double* background);          
 int pt_frame_set_background_device(PtFrame* frame, const double* d_background); /* device -> device */
 /* render every owned pixel; outputs stay in HBM. stream: cudaStream_t or NULL for the library stream. */
 int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* user, PtStats* stats);
+/* The same render split in two, so that several frames can be in flight on the device at once: enqueue puts the
+ * whole frame (state copy, graph replays, control-block read-back) on the stream and returns without waiting;
+ * finish waits for it, fills stats and reports device-detected errors.  One render in flight per frame. */
+int pt_frame_enqueue(PtFrame* frame, void* stream);
+int pt_frame_finish(PtFrame* frame, PtStats* stats);
 /* device pointers to the compact outputs, owned-pixel order (see pt_frame_pixel_index) */
 const uint8_t* pt_frame_rgb_device(const PtFrame* frame);     /* owned_pixels * 3 */
 const uint32_t* pt_frame_hit_id_device(const PtFrame* frame); /* owned_pixels * 2 */

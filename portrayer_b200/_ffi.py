@@ -151,6 +151,8 @@ GPU_SYMBOLS = {
     "pt_frame_set_background": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_frame_set_background_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_frame_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PtStats)]),
+    "pt_frame_enqueue": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_frame_finish": (C.c_int, [C.c_void_p, C.POINTER(PtStats)]),
     "pt_frame_rgb_device": (C.c_void_p, [C.c_void_p]),
     "pt_frame_hit_id_device": (C.c_void_p, [C.c_void_p]),
     "pt_frame_hit_t_device": (C.c_void_p, [C.c_void_p]),

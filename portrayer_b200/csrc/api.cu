@@ -151,6 +151,8 @@ void evict_textures(uint64_t need) {
     }
 }
 
+double* g_gamma_lut = nullptr;  // 256 doubles, filled once by the device
+
 uint32_t g_slots_used = 0;  // bitmap of __constant__ FrameState slots in use
 int take_slot() {
     for (int i = 0; i < kStateSlots - 1; ++i)
@@ -209,6 +211,15 @@ struct PtFrame {
     cudaGraphNode_t camera_node[2] = {nullptr, nullptr};
     bool graph_failed = false;
     uint64_t last_use = 0;
+    // a render that has been enqueued but not finished (pt_frame_enqueue / pt_frame_finish)
+    enum { IDLE, IN_FLIGHT, FINISHED } pending = IDLE;
+    cudaStream_t pending_stream = nullptr;
+    std::vector<std::pair<uint32_t, uint32_t>> pending_batches;  // (n_slots, n_paths)
+    int pending_rc = PT_OK;
+    std::string pending_error;
+    PtProgressFn progress = nullptr;  // of the pt_frame_render call in progress
+    void* progress_user = nullptr;
+    PtStats pending_stats{};
 };
 
 namespace {
@@ -258,6 +269,7 @@ void fill_view(PtScene* s) {
     v.lights = reinterpret_cast<const PtLight*>(b + h.off_lights);
     v.textures = s->d_textures;
     v.inst_aabb = s->d_aabb;
+    v.gamma_lut = g_gamma_lut;
     v.ambient[0] = h.ambient[0]; v.ambient[1] = h.ambient[1]; v.ambient[2] = h.ambient[2];
     v.tlas_extent = h.tlas_extent;
     v.n_lights = h.n_lights;
@@ -607,6 +619,9 @@ int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* p
     uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * 4 : batch_paths);
     capacity = std::max<uint64_t>(capacity, batch_paths);
     capacity = std::min<uint64_t>(capacity, 0xFFFFFF00ull);
+    // the shadow kernel's 32-bit work cursor counts (hit, light) pairs
+    capacity = std::min<uint64_t>(capacity, 0xFFFF0000ull / std::max<uint32_t>(scene->h.n_lights, 1));
+    if (capacity < batch_paths) { free_frame(f); return fail(PT_ERR_INVALID, "batch too large for %u lights: lower max_batch_paths", scene->h.n_lights); }
     const uint64_t n_batches = owned ? (owned + slots - 1) / slots : 1;
     f->h_ctl_count = (uint32_t)std::min<uint64_t>(n_batches, 1u << 16);
 
@@ -682,11 +697,9 @@ int render_stream_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void*
     return PT_OK;
 }
 
-// graph path: every batch is one replay of the frame graph; control blocks come back through a pinned ring and
-// are looked at once, after the single synchronisation.  Returns 1 when a batch overflowed the node pool (the
-// caller then redoes the frame on the careful path).
-int render_graph_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void* user, PtStats* stats, uint32_t* launches_out,
-                      uint32_t* batches_out, uint32_t* error_bits_out, bool* overflow) {
+// graph path, part 1: every batch is one replay of the frame graph; control blocks come back through a pinned ring.
+// Nothing here waits for the device.
+int enqueue_graph_path(PtFrame* f, cudaStream_t st) {
     const bool count = (f->params.flags & PT_RENDER_COUNTERS) != 0;
     const int k = count ? 1 : 0;
     int rc = ensure_graph(f, count);
@@ -694,36 +707,35 @@ int render_graph_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void* 
     const uint32_t owned = (uint32_t)f->pixel_index.size();
     const uint32_t S = f->params.samples;
     const uint32_t n_batches = (owned + f->batch_slots - 1) / f->batch_slots;
-    *overflow = false;
-    std::vector<std::pair<uint32_t, uint32_t>> done;  // (n_slots, n_paths) per enqueued batch
+    if (n_batches > f->h_ctl_count) return fail(PT_ERR_INVALID, "frame has more batches than control-block slots");
+    f->pending_batches.clear();
     uint32_t first_slot = 0;
-    for (uint32_t b = 0; b < n_batches;) {
-        // enqueue up to h_ctl_count batches, then synchronise and read their control blocks
-        const uint32_t group = std::min<uint32_t>(f->h_ctl_count, n_batches - b);
-        done.clear();
-        for (uint32_t g = 0; g < group; ++g) {
-            const uint32_t n_slots = std::min(f->batch_slots, owned - first_slot);
-            CUDA_TRY(set_graph_batch(f->exec[k], f->camera_node[k], f->slot, first_slot, n_slots, f->batch_slots, S));
-            CUDA_TRY(cudaGraphLaunch(f->exec[k], st));
-            CUDA_TRY(cudaMemcpyAsync(&f->h_ctl[g], f->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
-            done.emplace_back(n_slots, n_slots * S);
-            first_slot += n_slots;
-        }
-        if (b + group >= n_batches) CUDA_TRY(cudaEventRecord(f->ev_stop, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        CUDA_TRY(cudaGetLastError());
-        for (uint32_t g = 0; g < group; ++g) {
-            const BatchCtl& c = f->h_ctl[g];
-            if (c.error_bits & PT_DEVERR_OVERFLOW) { *overflow = true; return PT_OK; }
-            *error_bits_out |= c.error_bits;
-            accumulate_stats(stats, c, done[g].second);
-            *launches_out += 3 + c.levels_run * 3;
-            ++*batches_out;
-            if (progress) progress(user, done[g].first);
-        }
-        b += group;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        const uint32_t n_slots = std::min(f->batch_slots, owned - first_slot);
+        CUDA_TRY(set_graph_batch(f->exec[k], f->camera_node[k], f->slot, first_slot, n_slots, f->batch_slots, S));
+        CUDA_TRY(cudaGraphLaunch(f->exec[k], st));
+        CUDA_TRY(cudaMemcpyAsync(&f->h_ctl[b], f->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
+        f->pending_batches.emplace_back(n_slots, n_slots * S);
+        first_slot += n_slots;
     }
     return PT_OK;
+}
+
+// graph path, part 2 (after the stream / event has been waited for): read the control blocks.  *overflow = a batch
+// ran out of node pool; the caller then redoes the frame on the careful path.
+void collect_graph_path(PtFrame* f, PtProgressFn progress, void* user, PtStats* stats, uint32_t* launches_out,
+                        uint32_t* batches_out, uint32_t* error_bits_out, bool* overflow) {
+    *overflow = false;
+    for (size_t b = 0; b < f->pending_batches.size(); ++b)
+        if (f->h_ctl[b].error_bits & PT_DEVERR_OVERFLOW) { *overflow = true; return; }
+    for (size_t b = 0; b < f->pending_batches.size(); ++b) {
+        const BatchCtl& c = f->h_ctl[b];
+        *error_bits_out |= c.error_bits;
+        accumulate_stats(stats, c, f->pending_batches[b].second);
+        *launches_out += 3 + c.levels_run * 3;
+        ++*batches_out;
+        if (progress) progress(user, f->pending_batches[b].first);
+    }
 }
 
 }  // namespace
@@ -740,6 +752,11 @@ int pt_init(int device) {
     if (device >= 0) CUDA_TRY(cudaSetDevice(device));
     if (!g_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     kernels_init();
+    if (!g_gamma_lut) {
+        CUDA_TRY(cudaMalloc(&g_gamma_lut, 256 * sizeof(double)));
+        launch_gamma_lut(g_gamma_lut, g_stream);
+        CUDA_TRY(cudaStreamSynchronize(g_stream));
+    }
     CUDA_TRY(cudaGetLastError());
     g_initialised = true;
     return PT_OK;
@@ -772,6 +789,8 @@ void pt_shutdown(void) {
     pt_release_cached_memory();
     if (g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
+    cudaFree(g_gamma_lut);
+    g_gamma_lut = nullptr;
     g_initialised = false;
 }
 
@@ -905,53 +924,12 @@ int pt_frame_set_background_device(PtFrame* frame, const double* d_background) {
     return PT_OK;
 }
 
-int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* user, PtStats* stats) {
-    if (!frame) return fail(PT_ERR_INVALID, "null frame");
-    Lock lock(g_mu);
-    PtFrame* f = frame;
-    if (!f->scene) return fail(PT_ERR_INVALID, "the frame's scene has been freed");
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_stream;
-    if (stats) {
-        const double h2d_ms = stats->h2d_ms, d2h_ms = stats->d2h_ms;
-        const uint64_t h2d_b = stats->h2d_bytes, d2h_b = stats->d2h_bytes;
-        memset(stats, 0, sizeof *stats);
-        stats->h2d_ms = h2d_ms; stats->d2h_ms = d2h_ms; stats->h2d_bytes = h2d_b; stats->d2h_bytes = d2h_b;
-    }
-    uint32_t launches = 0, batches = 0, retries = 0, error_bits = 0;
-    const uint32_t owned = (uint32_t)f->pixel_index.size();
-
-    const FrameState state = frame_state(f);
-    CUDA_TRY(cudaEventRecord(f->ev_start, st));
-    CUDA_TRY(upload_state(f->slot, state, st));
-    int rc = PT_OK;
-    const bool want_stream = (f->params.flags & (PT_RENDER_KERNEL_TIMES | PT_RENDER_NO_GRAPH)) != 0 || !graphs_enabled() ||
-                             f->graph_failed;
-    bool done = owned == 0;
-    if (!done && !want_stream) {
-        bool overflow = false;
-        PtStats scratch{};
-        uint32_t l = 0, b = 0, eb = 0;
-        rc = render_graph_path(f, st, progress, user, stats ? &scratch : nullptr, &l, &b, &eb, &overflow);
-        if (rc == PT_OK && !overflow) {
-            if (stats) {
-                const PtStats keep = *stats;
-                *stats = scratch;
-                stats->h2d_ms = keep.h2d_ms; stats->d2h_ms = keep.d2h_ms; stats->h2d_bytes = keep.h2d_bytes; stats->d2h_bytes = keep.d2h_bytes;
-            }
-            launches = l; batches = b; error_bits = eb;
-            done = true;
-        } else if (rc == PT_OK) {
-            ++retries;  // node pool overflow: redo the frame with per-batch checks
-        } else if (f->graph_failed) {
-            rc = PT_OK;  // no graph support on this driver: fall through to the stream path
-        }
-    }
-    if (rc == PT_OK && !done) {
-        rc = render_stream_path(f, st, progress, user, stats, &launches, &batches, &retries, &error_bits);
-        if (rc == PT_OK) CUDA_TRY(cudaEventRecord(f->ev_stop, st));
-    }
+// the blocking careful render (stream path), also the fallback of the graph path
+static int render_blocking_stream(PtFrame* f, cudaStream_t st, PtProgressFn progress, void* user, PtStats* stats, uint32_t retries0) {
+    uint32_t launches = 0, batches = 0, retries = retries0, error_bits = 0;
+    int rc = render_stream_path(f, st, progress, user, stats, &launches, &batches, &retries, &error_bits);
     if (rc != PT_OK) return rc;
-    if (owned == 0) CUDA_TRY(cudaEventRecord(f->ev_stop, st));
+    CUDA_TRY(cudaEventRecord(f->ev_stop, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
@@ -966,6 +944,97 @@ int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* u
     const int code = device_error_to_code(error_bits);
     if (code != PT_OK) return fail(code, "%s", panic_text(code));
     return PT_OK;
+}
+
+int pt_frame_enqueue(PtFrame* frame, void* stream) {
+    if (!frame) return fail(PT_ERR_INVALID, "null frame");
+    Lock lock(g_mu);
+    PtFrame* f = frame;
+    if (!f->scene) return fail(PT_ERR_INVALID, "the frame's scene has been freed");
+    if (f->pending == PtFrame::IN_FLIGHT) return fail(PT_ERR_INVALID, "the frame already has a render in flight: call pt_frame_finish first");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_stream;
+    f->pending_stream = st;
+    f->pending_stats = PtStats{};
+    f->pending_rc = PT_OK;
+    const uint32_t owned = (uint32_t)f->pixel_index.size();
+    const FrameState state = frame_state(f);
+    CUDA_TRY(cudaEventRecord(f->ev_start, st));
+    CUDA_TRY(upload_state(f->slot, state, st));
+    const bool want_stream = (f->params.flags & (PT_RENDER_KERNEL_TIMES | PT_RENDER_NO_GRAPH)) != 0 || !graphs_enabled() ||
+                             f->graph_failed;
+    if (owned != 0 && !want_stream) {
+        int rc = enqueue_graph_path(f, st);
+        if (rc == PT_OK) {
+            CUDA_TRY(cudaEventRecord(f->ev_stop, st));
+            f->pending = PtFrame::IN_FLIGHT;
+            return PT_OK;
+        }
+        if (!f->graph_failed) return rc;  // a real error; otherwise: no graph support on this driver, use the stream path
+    }
+    // stream path (per-kernel timing, PT_RENDER_NO_GRAPH, fallback) or an empty frame: done synchronously here
+    if (owned == 0) {
+        CUDA_TRY(cudaEventRecord(f->ev_stop, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        f->pending_rc = render_blocking_stream(f, st, f->progress, f->progress_user, &f->pending_stats, 0);
+        if (f->pending_rc != PT_OK) f->pending_error = g_error;
+    }
+    f->pending = PtFrame::FINISHED;
+    return PT_OK;
+}
+
+int pt_frame_finish(PtFrame* frame, PtStats* stats) {
+    if (!frame) return fail(PT_ERR_INVALID, "null frame");
+    Lock lock(g_mu);
+    PtFrame* f = frame;
+    if (f->pending == PtFrame::IDLE) return fail(PT_ERR_INVALID, "no render was enqueued on this frame");
+    const double h2d_ms = stats ? stats->h2d_ms : 0.0, d2h_ms = stats ? stats->d2h_ms : 0.0;
+    const uint64_t h2d_b = stats ? stats->h2d_bytes : 0, d2h_b = stats ? stats->d2h_bytes : 0;
+    int rc = PT_OK;
+    if (f->pending == PtFrame::IN_FLIGHT) {
+        f->pending = PtFrame::IDLE;
+        CUDA_TRY(cudaEventSynchronize(f->ev_stop));
+        CUDA_TRY(cudaGetLastError());
+        PtStats local{};
+        uint32_t launches = 0, batches = 0, error_bits = 0;
+        bool overflow = false;
+        collect_graph_path(f, f->progress, f->progress_user, &local, &launches, &batches, &error_bits, &overflow);
+        if (overflow) {
+            // node pool overflow: redo the frame with per-batch checks (results do not depend on batching)
+            local = PtStats{};
+            CUDA_TRY(cudaEventRecord(f->ev_start, f->pending_stream));
+            rc = render_blocking_stream(f, f->pending_stream, f->progress, f->progress_user, &local, 1);
+        } else {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, f->ev_start, f->ev_stop));
+            local.device_ms = ms;
+            local.batches = batches;
+            local.kernel_launches = launches;
+            local.device_error_bits = error_bits & ~PT_DEVERR_OVERFLOW;
+            const int code = device_error_to_code(error_bits);
+            if (code != PT_OK) rc = fail(code, "%s", panic_text(code));
+        }
+        if (stats) *stats = local;
+    } else {
+        f->pending = PtFrame::IDLE;
+        rc = f->pending_rc;
+        if (rc != PT_OK) g_error = f->pending_error;
+        if (stats) *stats = f->pending_stats;
+    }
+    if (stats) { stats->h2d_ms = h2d_ms; stats->d2h_ms = d2h_ms; stats->h2d_bytes = h2d_b; stats->d2h_bytes = d2h_b; }
+    return rc;
+}
+
+int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* user, PtStats* stats) {
+    if (!frame) return fail(PT_ERR_INVALID, "null frame");
+    Lock lock(g_mu);
+    frame->progress = progress;
+    frame->progress_user = user;
+    int rc = pt_frame_enqueue(frame, stream);
+    if (rc == PT_OK) rc = pt_frame_finish(frame, stats);
+    frame->progress = nullptr;
+    frame->progress_user = nullptr;
+    return rc;
 }
 
 const uint8_t* pt_frame_rgb_device(const PtFrame* frame) { return frame ? frame->d_rgb : nullptr; }

@@ -30,6 +30,7 @@ struct DScene {
     const PtMaterial* materials;
     const PtLight* lights;
     const TextureDev* textures;
+    const double* gamma_lut;  // [256] pow(i / 255, 2.2) computed once on the device (ImageTexture::at, texture.rs:162-168)
     const float4* inst_aabb;  // [2 * n_instances] padded world-space box of every instance (lo, hi), FP32, rounded outward
     double ambient[3];
     double tlas_extent;
@@ -78,7 +79,8 @@ struct BatchCtl {
     uint32_t n_slots;          // owned pixels in the batch
     uint32_t n_paths;          // n_slots * samples
     uint32_t levels_run;       // levels that held at least one ray
-    uint32_t pad_[3];
+    uint32_t cursor[2];        // dynamic work distribution of the current level: next unclaimed item of [0] extend, [1] shadow
+    uint32_t pad_[1];
     unsigned long long rays_shadow, rays_reflect, rays_refract, rays_depth_cut, shaded_hits, texel_lookups;
     unsigned long long work[2][4];  // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates]
 };

@@ -142,7 +142,18 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
     KdStack tlas_stack, blas_stack;
     WorkCounters wc;
     uint32_t err = 0;
-    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+    // Dynamic distribution: a warp claims the next 32 rays when it has finished its last 32 (one atomic per warp
+    // and chunk).  Ray cost varies by orders of magnitude (sky vs. deep kd walks); a static grid-stride split leaves
+    // most of the machine idle while the slowest warps finish.
+    const uint32_t n = end - begin;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->cursor[0], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = begin + base + lane;
+        if (i >= end) continue;
         const V3 o = v3(pool.ox[i], pool.oy[i], pool.oz[i]);
         const V3 d = v3(pool.dx[i], pool.dy[i], pool.dz[i]);
         Hit hit{(double)INFINITY, kNone, 0};
@@ -172,7 +183,14 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
     WorkCounters wc;
     uint32_t err = 0;
     unsigned long long cast = 0;
-    for (unsigned long long j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (unsigned long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {  // dynamic distribution, as in extend_kernel (total < 2^32: n <= pool capacity, lights <= 32... checked on the host)
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->cursor[1], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if ((unsigned long long)base >= total) break;
+        const unsigned long long j = (unsigned long long)base + lane;
+        if (j >= total) continue;
         const uint32_t l = (uint32_t)(j / n);
         const uint32_t i = begin + (uint32_t)(j % n);
         const uint32_t inst = pool.inst[i];
@@ -292,9 +310,8 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int 
                 if (tex_id < 0) {
                     kd[0] = __ldg(&mat->diffuse[0]); kd[1] = __ldg(&mat->diffuse[1]); kd[2] = __ldg(&mat->diffuse[2]);
                 } else if (sh.has_uv) {
-                    texture_at(sc, tex_id, tu, tv, kd);
+                    texture_at_gamma(sc, tex_id, tu, tv, kd);  // texel / 255 then powf(2.2), texture.rs:166
                     ++n_texel;
-                    kd[0] = pow(kd[0], PT_GAMMA); kd[1] = pow(kd[1], PT_GAMMA); kd[2] = pow(kd[2], PT_GAMMA);  // texture.rs:166
                 } else {
                     err |= PT_DEVERR_TEXTURE;  // material.rs:141
                     ok = false;
@@ -450,6 +467,8 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int 
             ctl->level_start[level + 2] = next_end;
             ctl->level = level + 1;
             ctl->levels_run = level + 1;
+            ctl->cursor[0] = 0u;
+            ctl->cursor[1] = 0u;
             const bool more = next_end > end && level + 1 < fs.n_levels;
             if (loop) cudaGraphSetConditional(loop, more ? 1u : 0u);
         }
@@ -687,6 +706,12 @@ __global__ void __launch_bounds__(kBlock) instance_bounds_kernel(const PtInstanc
     out[2 * (size_t)i + 1] = make_float4(fhi[0], fhi[1], fhi[2], 0.f);
 }
 
+// pow(i / 255, 2.2) for the 256 possible texel values, with the device's own pow(): bit-identical to evaluating it per hit
+__global__ void gamma_lut_kernel(double* __restrict__ lut) {
+    const int i = threadIdx.x;
+    lut[i] = pow((double)i / 255.0, PT_GAMMA);
+}
+
 int g_grid_extend[2] = {0, 0}, g_grid_shadow[2] = {0, 0}, g_grid_shade = 0;
 
 template <class K>
@@ -715,6 +740,8 @@ static inline int capped(int grid, uint64_t max_items) {
     const uint64_t need = blocks_for(max_items ? max_items : 1);
     return (uint64_t)grid > need ? (int)need : grid;
 }
+
+void launch_gamma_lut(double* lut, cudaStream_t st) { gamma_lut_kernel<<<1, 256, 0, st>>>(lut); }
 
 void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bounds_scratch, float4* out, cudaStream_t st) {
     if (n_meshes) mesh_bounds_kernel<<<n_meshes, kBlock, 0, st>>>(sc.meshes, sc.tri_pos, n_meshes, mesh_bounds_scratch);

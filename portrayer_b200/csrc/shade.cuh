@@ -210,6 +210,23 @@ PT_D void texture_at(const DScene& sc, int tex, double u, double v, double* rgb)
     rgb[2] = (double)__ldg(p + 2) / 255.0;
 }
 
+// ImageTexture::at (texture.rs:162-168): the same texel, each channel through pow(c, 2.2).  A channel has 256
+// possible values, so the power comes from a table the device filled with its own pow() (gamma_lut_kernel).
+PT_D void texture_at_gamma(const DScene& sc, int tex, double u, double v, double* rgb) {
+    const TextureDev* t = sc.textures + tex;
+    const uint4 rec = __ldg(reinterpret_cast<const uint4*>(t));
+    const uint8_t* texels = reinterpret_cast<const uint8_t*>(((unsigned long long)rec.w << 32) | rec.z);
+    const long long width = rec.x, height = rec.y;
+    const long long x = f64_as_i64(u * (double)(width - 1));
+    const long long y = f64_as_i64(v * (double)(height - 1));
+    const unsigned xi = (unsigned)rem_euclid(x, width);
+    const unsigned yi = (unsigned)rem_euclid(y, height);
+    const uint8_t* p = texels + ((unsigned long long)yi * rec.x + xi) * 3ull;
+    rgb[0] = __ldg(sc.gamma_lut + __ldg(p));
+    rgb[1] = __ldg(sc.gamma_lut + __ldg(p + 1));
+    rgb[2] = __ldg(sc.gamma_lut + __ldg(p + 2));
+}
+
 // refracted_direction, material.rs:27-48
 PT_D bool refracted_direction(V3 ray_dir, V3 normal, double refraction_index, V3& out) {
     const double eta = refraction_index;

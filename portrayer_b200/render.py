@@ -134,6 +134,15 @@ class Frame:
                                   C.cast(cb, C.c_void_p) if cb else None, None, C.byref(stats)))
         return stats
 
+    def enqueue(self, stream: int | None = None) -> None:
+        """put the whole frame on the stream without waiting (pt_frame_enqueue); pair with finish()"""
+        check(gpu.pt_frame_enqueue(self._h, C.c_void_p(stream) if stream else None))
+
+    def finish(self) -> PtStats:
+        stats = PtStats()
+        check(gpu.pt_frame_finish(self._h, C.byref(stats)))
+        return stats
+
     def pixel_index(self) -> np.ndarray:
         out = np.empty(self.owned_pixels, np.uint32)
         check(gpu.pt_frame_pixel_index(self._h, out.ctypes.data))
