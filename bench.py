@@ -42,6 +42,11 @@ WORKLOADS = {
     # configs[3]
     "secondary": dict(frames=["water-glass", "glossy-reflection", "soft-shadows"], samples=16,
                       label="configs[3]: water-glass + glossy-reflection + soft-shadows @ 910x512, SAMPLES=16"),
+    # configs[4]: fixed total work, tiles partitioned across the ranks (strong scaling)
+    "castle": dict(frames=["graphics-castle"], samples=64, size=(3840, 2160), scaling="strong",
+                   label="configs[4]: examples/graphics-castle @ 3840x2160, SAMPLES=64, KD_DEPTH=10"),
+    "castle-hd": dict(frames=["graphics-castle"], samples=4, size=(1920, 1080), scaling="strong",
+                      label="examples/graphics-castle @ native 1920x1080, SAMPLES=4, KD_DEPTH=10"),
 }
 SEED = 1
 
@@ -127,11 +132,35 @@ def build_workload(args, world):
     import portrayer_b200 as pt
 
     wl = WORKLOADS[args.workload]
-    samples = (args.samples or wl["samples"]) * world
+    samples = (args.samples or wl["samples"]) * (1 if wl.get("scaling") == "strong" else world)
     scenes = []
     for name in wl["frames"]:
-        scenes.append(pt.Scene.example(name))
+        sc = pt.Scene.example(name)
+        if wl.get("size"):
+            sc.width, sc.height = wl["size"]
+        scenes.append(sc)
     return wl, samples, scenes
+
+
+def cpu_band_fraction(oracle, make_params, jobs, samples, threads, budget_s):
+    """Fraction of every frame's rows (a centred band) the oracle can render within budget_s: calibrated on a
+    thin band of the first frame.  jobs: (scene, camera, params, background)."""
+    sc, cam, p, bg = jobs[0]
+    band = max(1, sc.height // 64)
+    y1 = (sc.height - band) // 2
+    p_cal = make_params(sc.width, sc.height, samples, "hash", SEED, slice_=(0, y1, sc.width - 1, y1 + band - 1), bg_mode=p.bg_mode)
+    t0 = time.perf_counter()
+    oracle.render(sc.blob, cam, p_cal, bg, threads=threads)
+    est = (time.perf_counter() - t0) * (sc.height / band) * len(jobs)
+    return min(1.0, budget_s / max(est, 1e-6))
+
+
+def band_params(make_params, sc, p, samples, frac):
+    if frac >= 1.0:
+        return p
+    rows = max(1, int(sc.height * frac))
+    y1 = (sc.height - rows) // 2
+    return make_params(sc.width, sc.height, samples, "hash", SEED, slice_=(0, y1, sc.width - 1, y1 + rows - 1), bg_mode=p.bg_mode)
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -153,26 +182,14 @@ def run_reference(args, rank, world):
 
     # bound the step: calibrate on a 1/16 slice of the first frame, then cut every frame to a row band that
     # keeps the whole run (steps + warmup) within ~2-3 minutes
-    sc, cam, p, bg = jobs[0]
-    band = max(1, sc.height // 16)
-    p_cal = make_params(sc.width, sc.height, samples, "hash", SEED, slice_=(0, (sc.height - band) // 2, sc.width - 1, (sc.height - band) // 2 + band - 1), bg_mode=p.bg_mode)
-    t0 = time.perf_counter()
-    oracle.render(sc.blob, cam, p_cal, bg, threads=threads)
-    est_step = (time.perf_counter() - t0) * 16 * len(jobs)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    frac = min(1.0, budget / max(est_step, 1e-6))
-    sample_desc = "full frames" if frac >= 1.0 else f"centre row band = {frac:.3f} of every frame"
+    frac = cpu_band_fraction(oracle, make_params, jobs, samples, threads, 150.0 / max(1, args.steps + args.warmup))
+    sample_desc = "full frames" if frac >= 1.0 else f"centre row band = {frac:.4f} of every frame"
 
     def one_step():
         rays = 0
         t0 = time.perf_counter()
         for sc, cam, p, bg in jobs:
-            if frac >= 1.0:
-                pp = p
-            else:
-                rows = max(1, int(sc.height * frac))
-                y1 = (sc.height - rows) // 2
-                pp = make_params(sc.width, sc.height, samples, "hash", SEED, slice_=(0, y1, sc.width - 1, y1 + rows - 1), bg_mode=p.bg_mode)
+            pp = band_params(make_params, sc, p, samples, frac)
             res = oracle.render(sc.blob, cam, pp, bg, threads=threads)
             assert res.rc == 0
             rays += res.stats.rays
@@ -188,7 +205,7 @@ def run_reference(args, rank, world):
     value = total_rays / total_s / 1e6
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": wl.get("scaling", "weak"),
         "vs_baseline": None, "dtype": "f64", "data": "reference example scenes; deterministic hashed jitter",
         "config": {"workload": wl["label"], "samples": samples, "rng": "hash", "seed": SEED,
                    "note": "reference is Rust (no toolchain here): this is the C port of its render loop (oracle/)"},
@@ -216,10 +233,13 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream().cuda_stream
 
     wl = WORKLOADS[args.workload]
-    samples = (args.samples or wl["samples"]) * world
+    samples = (args.samples or wl["samples"]) * (1 if wl.get("scaling") == "strong" else world)
 
     # ---- scene preparation (host side, stays in the reference's own code in the target design): rank 0 only
     scenes = [pt.Scene.example(name) for name in wl["frames"]] if rank == 0 else [None] * len(wl["frames"])
+    if rank == 0 and wl.get("size"):
+        for sc in scenes:
+            sc.width, sc.height = wl["size"]
     t_bcast0 = time.perf_counter()
     frames_meta = []
     for i, name in enumerate(wl["frames"]):
@@ -460,13 +480,15 @@ def run_ours(args, rank, world, local_rank):
         from oracle import binding as oracle
 
         threads = host_threads()
+        cjobs = [(sc, j.cam, make_params(j.w, j.h, samples, "hash", SEED, bg_mode=j.bg_mode), j.bg) for j, sc in zip(jobs, scenes)]
+        # about 10-25 s of CPU work: whole passes over the workload; a workload too big for that (4K x 64 samples) is
+        # cut to a centred row band of every frame
+        frac = cpu_band_fraction(oracle, make_params, cjobs, samples, threads, 12.0)
         t0 = time.perf_counter()
         c_rays, frames_done = 0, 0
-        # about 10-25 s of CPU work: whole passes over the workload, cut short inside a pass only if it runs long
         while time.perf_counter() - t0 < 10.0:
-            for j, sc in zip(jobs, scenes):
-                p = make_params(j.w, j.h, samples, "hash", SEED, bg_mode=j.bg_mode)
-                res = oracle.render(sc.blob, j.cam, p, j.bg, threads=threads)
+            for sc, cam, p, bg in cjobs:
+                res = oracle.render(sc.blob, cam, band_params(make_params, sc, p, samples, frac), bg, threads=threads)
                 c_rays += res.stats.rays
                 frames_done += 1
                 if time.perf_counter() - t0 > 25.0:
@@ -474,13 +496,14 @@ def run_ours(args, rank, world, local_rank):
             if time.perf_counter() - t0 > 25.0:
                 break
         c_s = time.perf_counter() - t0
+        what = "full frames" if frac >= 1.0 else f"centre row band = {frac:.4f} of every frame"
         cpu = {"value": c_rays / c_s / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-               "sample": f"{frames_done} frame render(s) = {frames_done / len(jobs):.2f} pass(es) over the {len(jobs)}-frame workload, {c_s:.1f} s",
+               "sample": f"{frames_done} frame render(s) ({what}) = {frames_done / len(jobs):.2f} pass(es) over the {len(jobs)}-frame workload, {c_s:.1f} s",
                "note": "C port of the reference's render loop (oracle/); the Rust reference cannot be built here"}
 
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": wl.get("scaling", "weak"), "vs_baseline": None,
         "dtype": "f64",
         "data": "reference example scenes (procedural geometry, reference OBJ/texture assets" +
                 (", stand-ins: " + "; ".join(f"{k}: {v}" for k, v in pt.assets.STAND_INS.items()) if pt.assets.STAND_INS else "") + ")",

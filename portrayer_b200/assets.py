@@ -34,6 +34,9 @@ def _procedural(name: str, size: int = 1024) -> np.ndarray:
     rng = np.random.default_rng(seed)
     base = rng.integers(0, 256, size=(size // 16, size // 16, 3), dtype=np.uint8)
     img = np.kron(base, np.ones((16, 16, 1), dtype=np.uint8))
+    if "shrub" in name.lower():  # hedge-like greens for the castle's maze walls (assets/shrub.png is missing upstream)
+        g = base[..., 1].astype(np.int32)
+        img = np.kron(np.stack([g // 6 + 10, g // 3 + 70, g // 8 + 8], axis=-1).astype(np.uint8), np.ones((16, 16, 1), dtype=np.uint8))
     if "nor" in name.lower():  # keep stand-in normal maps pointing mostly "out of the surface"
         img = (img.astype(np.int32) // 4 + np.array([96, 96, 191])).clip(0, 255).astype(np.uint8)
     return np.ascontiguousarray(img)

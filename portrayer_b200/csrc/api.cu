@@ -618,9 +618,9 @@ int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* p
     const uint64_t batch_paths = slots * p.samples;
     uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * 4 : batch_paths);
     capacity = std::max<uint64_t>(capacity, batch_paths);
-    capacity = std::min<uint64_t>(capacity, 0xFFFFFF00ull);
+    capacity = std::min<uint64_t>(capacity, 0xFFF00000ull);  // head room for the work cursors (every warp overshoots by <= 2 chunks)
     // the shadow kernel's 32-bit work cursor counts (hit, light) pairs
-    capacity = std::min<uint64_t>(capacity, 0xFFFF0000ull / std::max<uint32_t>(scene->h.n_lights, 1));
+    capacity = std::min<uint64_t>(capacity, 0xFFF00000ull / std::max<uint32_t>(scene->h.n_lights, 1));
     if (capacity < batch_paths) { free_frame(f); return fail(PT_ERR_INVALID, "batch too large for %u lights: lower max_batch_paths", scene->h.n_lights); }
     const uint64_t n_batches = owned ? (owned + slots - 1) / slots : 1;
     f->h_ctl_count = (uint32_t)std::min<uint64_t>(n_batches, 1u << 16);

@@ -147,11 +147,13 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
     // most of the machine idle while the slowest warps finish.
     const uint32_t n = end - begin;
     const int lane = threadIdx.x & 31;
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(&ctl->cursor[0], 32u);
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->cursor[0], 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        const uint32_t base = __shfl_sync(0xFFFFFFFFu, next, 0);
         if (base >= n) break;
+        // claim the following chunk now: the atomic's round trip overlaps the walk of this one
+        if (lane == 0) next = atomicAdd(&ctl->cursor[0], 32u);
         const uint32_t i = begin + base + lane;
         if (i >= end) continue;
         const V3 o = v3(pool.ox[i], pool.oy[i], pool.oz[i]);
@@ -184,11 +186,12 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
     uint32_t err = 0;
     unsigned long long cast = 0;
     const int lane = threadIdx.x & 31;
-    for (;;) {  // dynamic distribution, as in extend_kernel (total < 2^32: n <= pool capacity, lights <= 32... checked on the host)
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->cursor[1], 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(&ctl->cursor[1], 32u);
+    for (;;) {  // dynamic distribution, as in extend_kernel (total < 2^32 is guaranteed by the host when it sizes the pool)
+        const uint32_t base = __shfl_sync(0xFFFFFFFFu, next, 0);
         if ((unsigned long long)base >= total) break;
+        if (lane == 0) next = atomicAdd(&ctl->cursor[1], 32u);
         const unsigned long long j = (unsigned long long)base + lane;
         if (j >= total) continue;
         const uint32_t l = (uint32_t)(j / n);

@@ -240,3 +240,18 @@ def test_frame_cache_rebinds_between_scenes(gpu_ready):
     b2, _ = parity.render_gpu(pt.Scene.example("primitives"), samples=1, rng="fixed", size=(128, 128))
     assert np.array_equal(a1.buffer, a2.buffer) and np.array_equal(b1.buffer, b2.buffer)
     assert not np.array_equal(a1.buffer, b1.buffer)
+
+
+# configs[4]: graphics-castle (13 KDMesh instances, dielectrics, glossy lake, ~6.9 k maze cubes) at reduced size
+@pytest.mark.parametrize("kd_depth", [10, 16])
+def test_graphics_castle(gpu_ready, kd_depth):
+    scene = pt.Scene.example("graphics-castle", kd_depth=kd_depth)
+    assert scene.header.n_instances > 6000 and scene.header.n_meshes >= 12
+    kw = dict(samples=1, rng="hash", size=(384, 216))
+    img, stats = parity.render_gpu(scene, **kw)
+    ref = parity.render_oracle(scene, **kw)
+    rep = parity.compare(img, ref, f"graphics-castle kd{kd_depth}")
+    print(rep)
+    parity.assert_parity(rep)
+    assert (stats.rays_primary, stats.rays_shadow, stats.rays_reflect, stats.rays_refract) == \
+           (ref.stats.rays_primary, ref.stats.rays_shadow, ref.stats.rays_reflect, ref.stats.rays_refract)

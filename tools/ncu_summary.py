@@ -13,6 +13,7 @@ from __future__ import annotations
 import collections
 import csv
 import io
+import os
 import subprocess
 import sys
 
@@ -79,35 +80,48 @@ def report(rep: str) -> None:
 
 
 def stalls(rep: str, kernel: str | None) -> None:
-    rows = ncu_page(rep, "source")
-    # the source page is a sequence of per-kernel tables; keep the top source lines by sampled stalls
-    hdr = None
-    cur = None
-    tables = []
-    for r in rows:
-        if r and r[0] in ("#", "Source") or (r and "Source" in r and "# Samples" in " ".join(r)):
-            hdr = r
-            cur = []
-            tables.append((hdr, cur))
-        elif hdr is not None and len(r) == len(hdr):
-            cur.append(r)
-    for hdr, body in tables:
-        cols = {c: i for i, c in enumerate(hdr)}
-        samp = next((c for c in hdr if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)"), None)
-        src = "Source" if "Source" in cols else hdr[1]
-        if samp is None:
+    """Hottest source lines per kernel: warp-stall samples and executed instructions aggregated from the joined
+    CUDA-C / SASS view (needs -lineinfo at compile time and --import-source on at capture time)."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True,
+                         text=True, check=True).stdout
+    fpath, func, hdr = None, None, None
+    agg: dict = {}
+    for r in csv.reader(io.StringIO(out)):
+        if not r:
             continue
-
-        def val(r):
+        if r[0] == "File Path":
+            fpath = r[1]
+        elif r[0] == "Function Name":
+            func = r[1]
+        elif r[0] == "Line No":
+            hdr = r
+        elif hdr is not None and len(r) == len(hdr) and r[0].isdigit():
+            cols = {c: k for k, c in enumerate(hdr)}
+            src_i = hdr.index("Source")
             try:
-                return float(r[cols[samp]].replace(",", ""))
+                samples = float(r[cols["# Samples"]] or 0)
+                insts = float(r[cols["Instructions Executed"]] or 0)
+                wait = float(r[cols.get("stall_wait", 0)] or 0) if "stall_wait" in cols else 0.0
+                long_sb = float(r[cols["stall_long_sb"]] or 0) if "stall_long_sb" in cols else 0.0
             except ValueError:
-                return 0.0
-
-        tot = sum(val(r) for r in body) or 1.0
-        print(f"== table with {len(body)} lines, {tot:.0f} samples ({samp})")
-        for r in sorted(body, key=val, reverse=True)[:25]:
-            print(f"   {val(r) / tot:6.3f}  {r[cols[src]].strip()[:140]}")
+                continue
+            key = (func, os.path.basename(fpath or "?"), int(r[0]))
+            a = agg.setdefault(key, [0.0, 0.0, 0.0, 0.0, r[src_i].strip()])
+            a[0] += samples
+            a[1] += insts
+            a[2] += wait
+            a[3] += long_sb
+    funcs = sorted({k[0] for k in agg})
+    for fn in funcs:
+        if kernel and kernel not in fn:
+            continue
+        rows = [(k, v) for k, v in agg.items() if k[0] == fn]
+        tot_s = sum(v[0] for _, v in rows) or 1.0
+        tot_i = sum(v[1] for _, v in rows) or 1.0
+        print(f"== {fn.replace('ptd::<unnamed>::', '')}: {tot_s:.0f} stall samples, {tot_i:.0f} warp instructions")
+        print(f"   {'samples':>8s} {'insts':>7s} {'wait':>6s} {'longsb':>6s}  file:line  source")
+        for k, v in sorted(rows, key=lambda kv: -kv[1][0])[:40]:
+            print(f"   {v[0] / tot_s:8.3f} {v[1] / tot_i:7.3f} {v[2] / tot_s:6.3f} {v[3] / tot_s:6.3f}  {k[1]}:{k[2]}  {v[4][:110]}")
 
 
 def main() -> None:
