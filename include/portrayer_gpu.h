@@ -297,6 +297,9 @@ typedef struct PtStats {
     /* per-kernel device time and launch counts (only with PT_RENDER_KERNEL_TIMES): extend, shadow, shade */
     double ms_extend, ms_shadow, ms_shade;
     uint32_t n_extend, n_shadow, n_shade, reserved2;
+    /* sum over instance tests of the primitive's own f64 op count (SURVEY 8d P_type: sphere 30, cube 150, plane 25,
+     * cylinder 70, cone 90), per traversal kernel; with the counters above it gives the algorithmic f64 flops */
+    uint64_t k_prim_flops[2];
 } PtStats;
 
 typedef struct PtScene PtScene; /* opaque, library-owned */
@@ -316,6 +319,9 @@ int pt_device_count(void);
 void pt_release_cached_memory(void);
 /* bytes of texels currently resident in the texture cache */
 uint64_t pt_resident_texture_bytes(void);
+/* Measured f64 issue ceiling of this GPU for the library's own instruction mix (separate DMUL + DADD, no FMA):
+ * runs a register-resident microbenchmark for about `milliseconds` and returns TFLOP/s in *tflops_out. */
+int pt_measure_fp64_rate(double milliseconds, double* tflops_out);
 
 /* ---- scene (replaces nothing in the reference: it is the glue's output) ---- */
 /* bytes needed to pack desc; pack it. Pure host code, works without a GPU. */
@@ -362,6 +368,11 @@ uint64_t pt_owned_pixels(const PtRenderParams* params, uint32_t* index_out, uint
 
 int pt_frame_create(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, PtFrame** out);
 void pt_frame_free(PtFrame* frame);
+/* Point an existing frame (buffers, CUDA graph) at another scene and / or camera of the same image geometry:
+ * how a program that renders many scenes at one resolution avoids re-creating frames (pt_render does this
+ * internally).  The scene must have the same light count and reflectivity class as the one the frame was sized for
+ * (else PT_ERR_INVALID: create a new frame).  seed / rng_mode may change too; pass NULL to keep a value. */
+int pt_frame_rebind(PtFrame* frame, PtScene* scene, const PtCamera* camera, const uint64_t* seed, const uint32_t* rng_mode);
 uint64_t pt_frame_owned_pixels(const PtFrame* frame);   /* pixels this rank renders */
 uint64_t pt_frame_background_doubles(const PtFrame* frame); /* doubles expected in the background buffer */
 int pt_frame_set_background(PtFrame* frame, const double* background);          /* host -> device */

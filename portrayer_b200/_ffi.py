@@ -85,6 +85,7 @@ class PtStats(C.Structure):
         ("k_bbox_gates", C.c_uint64 * 2),
         ("ms_extend", C.c_double), ("ms_shadow", C.c_double), ("ms_shade", C.c_double),
         ("n_extend", C.c_uint32), ("n_shadow", C.c_uint32), ("n_shade", C.c_uint32), ("reserved2", C.c_uint32),
+        ("k_prim_flops", C.c_uint64 * 2),
     ]
 
     def as_dict(self) -> dict:
@@ -131,6 +132,7 @@ GPU_SYMBOLS = {
     "pt_device_count": (C.c_int, []),
     "pt_release_cached_memory": (None, []),
     "pt_resident_texture_bytes": (C.c_uint64, []),
+    "pt_measure_fp64_rate": (C.c_int, [C.c_double, C.POINTER(C.c_double)]),
     "pt_scene_blob_size": (C.c_uint64, [C.c_void_p]),
     "pt_scene_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "pt_scene_unpack": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
@@ -146,6 +148,7 @@ GPU_SYMBOLS = {
     "pt_owned_pixels": (C.c_uint64, [C.POINTER(PtRenderParams), C.c_void_p, C.c_uint64]),
     "pt_frame_create": (C.c_int, [C.c_void_p, C.POINTER(PtCamera), C.POINTER(PtRenderParams), C.POINTER(C.c_void_p)]),
     "pt_frame_free": (None, [C.c_void_p]),
+    "pt_frame_rebind": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PtCamera), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "pt_frame_owned_pixels": (C.c_uint64, [C.c_void_p]),
     "pt_frame_background_doubles": (C.c_uint64, [C.c_void_p]),
     "pt_frame_set_background": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -540,6 +540,7 @@ void accumulate_stats(PtStats* stats, const BatchCtl& c, uint32_t n_paths) {
         stats->k_instance_tests[k] += c.work[k][1];
         stats->k_triangle_tests[k] += c.work[k][2];
         stats->k_bbox_gates[k] += c.work[k][3];
+        stats->k_prim_flops[k] += c.work[k][4];
         stats->kd_splits += c.work[k][0];
         stats->instance_tests += c.work[k][1];
         stats->triangle_tests += c.work[k][2];
@@ -779,6 +780,38 @@ void pt_release_cached_memory(void) {
     g_pin.trim();
 }
 
+int pt_measure_fp64_rate(double milliseconds, double* tflops_out) {
+    if (!tflops_out) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
+    int rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    cudaError_t e;
+    double* sink = static_cast<double*>(g_dev.alloc(64, &e));
+    if (!sink) return fail(PT_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int iters = 2048;
+    double best = 0.0;
+    launch_fp64_rate(sink, 256, g_stream);  // warm-up
+    for (int rep = 0; rep < 6; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, g_stream));
+        const double flops = launch_fp64_rate(sink, iters, g_stream);
+        CUDA_TRY(cudaEventRecord(e1, g_stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        if (ms < milliseconds * 0.5 && iters < (1 << 24)) iters *= 2;  // grow until one launch lasts about the requested time
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    g_dev.release(sink);
+    CUDA_TRY(cudaGetLastError());
+    *tflops_out = best;
+    return PT_OK;
+}
+
 uint64_t pt_resident_texture_bytes(void) {
     Lock lock(g_mu);
     return g_texture_bytes;
@@ -899,6 +932,25 @@ int pt_frame_create(PtScene* scene, const PtCamera* camera, const PtRenderParams
     if (rc != PT_OK) { free_frame(f); return rc; }
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     *out = f;
+    return PT_OK;
+}
+
+int pt_frame_rebind(PtFrame* frame, PtScene* scene, const PtCamera* camera, const uint64_t* seed, const uint32_t* rng_mode) {
+    if (!frame) return fail(PT_ERR_INVALID, "null frame");
+    Lock lock(g_mu);
+    if (frame->pending == PtFrame::IN_FLIGHT) return fail(PT_ERR_INVALID, "the frame has a render in flight");
+    if (scene) {
+        if (scene->h.n_lights != frame->n_lights_cap || scene->has_reflective != frame->reflective_cap)
+            return fail(PT_ERR_INVALID, "scene has %u lights / reflective=%d, the frame was sized for %u / %d", scene->h.n_lights,
+                        (int)scene->has_reflective, frame->n_lights_cap, (int)frame->reflective_cap);
+        frame->scene = scene;
+    }
+    if (camera) frame->cam = *camera;
+    if (seed) frame->params.seed = *seed;
+    if (rng_mode) {
+        if (*rng_mode > PT_RNG_HASH) return fail(PT_ERR_INVALID, "bad rng_mode");
+        frame->params.rng_mode = *rng_mode;
+    }
     return PT_OK;
 }
 

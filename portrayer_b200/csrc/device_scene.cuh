@@ -82,7 +82,7 @@ struct BatchCtl {
     uint32_t cursor[2];        // dynamic work distribution of the current level: next unclaimed item of [0] extend, [1] shadow
     uint32_t pad_[1];
     unsigned long long rays_shadow, rays_reflect, rays_refract, rays_depth_cut, shaded_hits, texel_lookups;
-    unsigned long long work[2][4];  // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates]
+    unsigned long long work[2][5];  // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates, prim_flops]
 };
 
 // per-frame constants

@@ -51,15 +51,15 @@ PT_D void background_of(const FrameParams& fp, uint32_t pixel, double* bg) {
 
 // warp-aggregated add of per-thread work counters into the batch control block
 PT_D void flush_counters(BatchCtl* ctl, int kind, const WorkCounters& wc) {
-    unsigned long long v[4] = {wc.kd_splits, wc.instance_tests, wc.triangle_tests, wc.bbox_gates};
+    unsigned long long v[5] = {wc.kd_splits, wc.instance_tests, wc.triangle_tests, wc.bbox_gates, wc.prim_flops};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 5; ++k) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xFFFFFFFFu, v[k], off);
     }
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 5; ++k)
             if (v[k]) atomicAdd(&ctl->work[kind][k], v[k]);
     }
 }
@@ -715,6 +715,19 @@ __global__ void gamma_lut_kernel(double* __restrict__ lut) {
     lut[i] = pow((double)i / 255.0, PT_GAMMA);
 }
 
+// FP64 issue-rate microbenchmark: 8 independent multiply-then-add chains per thread.  Built with -fmad=false like
+// everything else here, so each step is one DMUL and one DADD — the instruction mix of the render kernels — and the
+// result is the no-FMA f64 ceiling that their roofline is quoted against.
+__global__ void __launch_bounds__(256) fp64_rate_kernel(double* __restrict__ sink, int iters, double m, double c) {
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) sink[0] = s;  // never true: keeps the chains alive
+}
+
 int g_grid_extend[2] = {0, 0}, g_grid_shadow[2] = {0, 0}, g_grid_shade = 0;
 
 template <class K>
@@ -742,6 +755,16 @@ static inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 
 static inline int capped(int grid, uint64_t max_items) {
     const uint64_t need = blocks_for(max_items ? max_items : 1);
     return (uint64_t)grid > need ? (int)need : grid;
+}
+
+// returns the flops issued (2 per chain step)
+double launch_fp64_rate(double* sink, int iters, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8;
+    fp64_rate_kernel<<<blocks, 256, 0, st>>>(sink, iters, 0.999999, 1e-9);
+    return (double)blocks * 256.0 * (double)iters * 8.0 * 2.0;
 }
 
 void launch_gamma_lut(double* lut, cudaStream_t st) { gamma_lut_kernel<<<1, 256, 0, st>>>(lut); }

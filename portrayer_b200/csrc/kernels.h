@@ -9,6 +9,7 @@ void kernels_init();
 // copy a frame's constants into __constant__ slot `slot` (stream-ordered)
 cudaError_t upload_state(int slot, const FrameState& state, cudaStream_t st);
 
+double launch_fp64_rate(double* sink, int iters, cudaStream_t st);
 void launch_gamma_lut(double* lut256, cudaStream_t st);
 // upload time: padded FP32 world boxes of all instances (mesh_bounds_scratch: n_meshes * 6 doubles)
 void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bounds_scratch, float4* out, cudaStream_t st);

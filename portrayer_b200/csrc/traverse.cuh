@@ -20,7 +20,20 @@ namespace ptd {
 
 struct WorkCounters {
     uint32_t kd_splits = 0, instance_tests = 0, triangle_tests = 0, bbox_gates = 0;
+    uint32_t prim_flops = 0;  // sum over instance tests of the primitive's own f64 op count (SURVEY 8d P_type)
 };
+// f64 add/mul/div/sqrt count of one analytic ray_hit: sphere 30, cube 150, plane 25, cylinder 70, cone 90;
+// mesh types are accounted through their triangle tests and bbox gates
+PT_D uint32_t prim_flop_count(uint32_t prim) {
+    switch (prim) {
+        case PT_PRIM_SPHERE: return 30u;
+        case PT_PRIM_CUBE: return 150u;
+        case PT_PRIM_PLANE: return 25u;
+        case PT_PRIM_CYLINDER: return 70u;
+        case PT_PRIM_CONE: return 90u;
+        default: return 0u;
+    }
+}
 
 struct Hit {
     double t;
@@ -407,6 +420,7 @@ struct TlasLeaf {
         for (uint32_t k = 0; k < count; ++k) {
             const uint32_t inst = __ldg(sc.tlas_items + first + k);
             ++wc.instance_tests;
+            wc.prim_flops += prim_flop_count(__ldg(&sc.instances[inst].prim));  // counting kernels only (dead code otherwise)
             if (!aabb_may_hit(sc.inst_aabb + 2 * (size_t)inst, rf, s, e)) continue;
             // FlatSceneNode::ray_cast: the ray in object space, direction NOT renormalised (flat_scene.rs:75, ray.rs:130-135)
             const PtInstance* rec = sc.instances + inst;

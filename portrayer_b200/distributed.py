@@ -77,31 +77,71 @@ def device_tensor(ptr: int, shape: tuple, typestr: str = "|u1", device: int = 0)
     return torch.as_tensor(_CudaView(ptr, shape, typestr), device=torch.device("cuda", device))
 
 
+class GatherPlan:
+    """Everything about the exchange step that depends only on the image geometry, computed once: how many pixels
+    every rank owns, the padded message size, and (on ``dst``) the scatter indices — on the device for CUDA tensors,
+    so a step's gather is one NCCL call plus one device-side scatter per rank, with no host work and no D2H."""
+
+    _cache: dict = {}
+
+    def __init__(self, params: PtRenderParams, device: torch.device, dst: int):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.dst = dst
+        self.h, self.w = params.height, params.width
+        self.counts = [int(_ffi.gpu.pt_owned_pixels(C.byref(_with_rank(params, r, self.world)), None, 0)) for r in range(self.world)]
+        self.pad = max(self.counts) if self.counts else 0
+        self.device = device
+        self.send = torch.zeros((self.pad, 3), dtype=torch.uint8, device=device) if self.world > 1 else None
+        self.recv = None
+        self.index = None
+        if self.rank == dst:
+            self.index = [torch.from_numpy(owned_pixel_index(params, r, self.world).astype(np.int64)).to(device) for r in range(self.world)]
+            if self.world > 1:
+                self.recv = [torch.empty((self.pad, 3), dtype=torch.uint8, device=device) for _ in range(self.world)]
+            self.image = torch.zeros((self.h * self.w, 3), dtype=torch.uint8, device=device)
+
+    @classmethod
+    def of(cls, params: PtRenderParams, device: torch.device, dst: int) -> "GatherPlan":
+        key = (params.width, params.height, params.x1, params.y1, params.x2, params.y2, params.tile_w, params.tile_h,
+               dist.get_world_size() if dist.is_initialized() else 1, str(device), dst)
+        plan = cls._cache.get(key)
+        if plan is None:
+            plan = cls._cache[key] = cls(params, device, dst)
+        return plan
+
+
+def gather_image_device(local_rgb: torch.Tensor, params: PtRenderParams, dst: int = 0) -> torch.Tensor | None:
+    """The exchange step, device-resident: every rank's compact [owned, 3] uint8 pixels -> a [H*W, 3] image tensor on
+    ``dst`` (returned there, None elsewhere).  Stream-ordered, no host synchronisation."""
+    plan = GatherPlan.of(params, local_rgb.device, dst)
+    assert local_rgb.shape[0] == plan.counts[plan.rank], (local_rgb.shape, plan.counts[plan.rank])
+    if plan.world == 1:
+        plan.image.index_copy_(0, plan.index[0], local_rgb)
+        return plan.image
+    plan.send[: plan.counts[plan.rank]].copy_(local_rgb)
+    dist.gather(plan.send, plan.recv, dst=dst)
+    if plan.rank != dst:
+        return None
+    for r in range(plan.world):
+        plan.image.index_copy_(0, plan.index[r], plan.recv[r][: plan.counts[r]])
+    return plan.image
+
+
 def gather_image(local_rgb: torch.Tensor, params: PtRenderParams, dst: int = 0, out: np.ndarray | None = None):
-    """Gather every rank's compact [owned, 3] uint8 pixels to ``dst`` and place them into a [H, W, 3] image.
+    """Gather every rank's compact [owned, 3] uint8 pixels to ``dst`` and place them into a [H, W, 3] host image.
     Returns the image on ``dst`` (None elsewhere). ``out`` lets the caller keep pixels outside the slice."""
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    h, w = params.height, params.width
-    counts = [int(_ffi.gpu.pt_owned_pixels(C.byref(_with_rank(params, r, world)), None, 0)) for r in range(world)]
-    assert local_rgb.shape[0] == counts[rank], (local_rgb.shape, counts[rank])
-    if world == 1:
-        pieces = [local_rgb]
-    else:
-        # ranks own slightly different pixel counts: pad to the maximum so one gather moves everything
-        pad = max(counts)
-        send = torch.zeros((pad, 3), dtype=torch.uint8, device=local_rgb.device)
-        send[: counts[rank]] = local_rgb
-        recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-        dist.gather(send, recv, dst=dst)
-        if rank != dst:
-            return None
-        pieces = [recv[r][: counts[r]] for r in range(world)]
-    image = out if out is not None else np.zeros((h, w, 3), np.uint8)
-    flat = image.reshape(-1, 3)
-    for r, piece in enumerate(pieces):
-        flat[owned_pixel_index(params, r, world).astype(np.int64)] = piece.cpu().numpy()
-    return image
+    image_dev = gather_image_device(local_rgb, params, dst)
+    if image_dev is None:
+        return None
+    plan = GatherPlan.of(params, local_rgb.device, dst)
+    host = image_dev.cpu().numpy().reshape(plan.h, plan.w, 3)
+    if out is None:
+        if (params.x1, params.y1, params.x2, params.y2) == (0, 0, plan.w - 1, plan.h - 1):
+            return host
+        out = np.zeros((plan.h, plan.w, 3), np.uint8)
+    out[params.y1:params.y2 + 1, params.x1:params.x2 + 1] = host[params.y1:params.y2 + 1, params.x1:params.x2 + 1]
+    return out
 
 
 def _with_rank(params: PtRenderParams, rank: int, world: int) -> PtRenderParams:

@@ -119,6 +119,14 @@ class Frame:
         self.owned_pixels = gpu.pt_frame_owned_pixels(self._h)
         self.background_doubles = gpu.pt_frame_background_doubles(self._h)
 
+    def rebind(self, dscene: "DeviceScene | None" = None, camera: PtCamera | None = None, seed: int | None = None) -> None:
+        """point this frame at another scene / camera of the same image geometry (pt_frame_rebind)"""
+        check(gpu.pt_frame_rebind(self._h, dscene.handle if dscene is not None else None,
+                                  C.byref(camera) if camera is not None else None,
+                                  C.byref(C.c_uint64(seed)) if seed is not None else None, None))
+        if dscene is not None:
+            self.dscene = dscene
+
     def set_background(self, background: np.ndarray) -> None:
         background = np.ascontiguousarray(background, dtype=np.float64)
         assert background.size == self.background_doubles, (background.size, self.background_doubles)
