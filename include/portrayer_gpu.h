@@ -93,6 +93,16 @@ typedef struct PtKdNode {
     uint32_t b;
 } PtKdNode;
 
+/* PartitionConfig + max depth of KDLeaf::partitioned (src/kdtree/leaf.rs:43-67,89).  The reference's values:
+ * target_max_nodes 3, target_max_merit 3, max_tries 10 (kdscene.rs:30-34, kdmesh.rs:45-49); max_depth = KD_DEPTH /
+ * KD_MESH_DEPTH env or 10 (kdscene.rs:13,36-38; kdmesh.rs:15,51-53). */
+typedef struct PtKdBuildConfig {
+    uint32_t max_depth;
+    uint32_t target_max_nodes;
+    int32_t target_max_merit;
+    uint32_t max_tries;
+} PtKdBuildConfig;
+
 /* What an intersection test needs for one flat instance
  * (FlatSceneNode, src/flat_scene.rs:50-61).  128 bytes, one cache line. */
 typedef struct PtInstance {
@@ -275,6 +285,12 @@ typedef struct PtRenderParams {
 #define PT_RENDER_KERNEL_TIMES 4u /* bracket every extend / shadow / shade launch with CUDA events (fills PtStats.ms_*); uses the stream path */
 #define PT_RENDER_ROW_MAJOR 8u    /* pt_frame_*: device outputs are full-image row-major (W*H entries) instead of compact owned-pixel order; world <= 1 only */
 #define PT_RENDER_NO_GRAPH 16u    /* launch kernel by kernel on the stream (one host check per recursion level) instead of replaying the frame's CUDA graph */
+/* The reference panics ("bug: ray should definitely hit infinite plane", kdtree/node.rs:147,178) when rounding puts a
+ * split-plane crossing outside the ray's range; over 10^9 rays that does happen (README.md:247-248 "occasionally buggy").
+ * By default the call fails with PT_ERR_KD_PLANE_MISS like the panic would.  With this flag the call succeeds: the
+ * offending ray treats that split as a miss of both children (what the device does anyway before it reports), the bit
+ * stays in PtStats.device_error_bits and PtStats.err_* say where it happened. */
+#define PT_RENDER_TOLERATE_KD_PLANE 32u
 
 typedef struct PtStats {
     /* rays = every ray_cast issued against the scene root */
@@ -300,6 +316,10 @@ typedef struct PtStats {
     /* sum over instance tests of the primitive's own f64 op count (SURVEY 8d P_type: sphere 30, cube 150, plane 25,
      * cylinder 70, cone 90), per traversal kernel; with the counters above it gives the algorithmic f64 flops */
     uint64_t k_prim_flops[2];
+    /* location of the first device-detected error (valid when device_error_bits != 0): the PT_DEVERR_* bit, global
+     * pixel index y*W+x, sample, path id (1 = primary; child = parent << 1 | refracted), and
+     * kernel (0 extend, 1 shadow, 2 shade) | recursion level << 8 | light << 16 */
+    uint32_t err_bit, err_pixel, err_sample, err_pathid, err_where, reserved3;
 } PtStats;
 
 typedef struct PtScene PtScene; /* opaque, library-owned */
@@ -319,6 +339,9 @@ int pt_device_count(void);
 void pt_release_cached_memory(void);
 /* bytes of texels currently resident in the texture cache */
 uint64_t pt_resident_texture_bytes(void);
+/* sizeof() of the boundary's structs as this library was compiled, so a binding can check its mirrors:
+ * 0 PtCamera, 1 PtRenderParams, 2 PtStats, 3 PtBlobHeader, 4 PtSceneDesc; anything else -> 0 */
+uint64_t pt_abi_sizeof(int which);
 /* Measured f64 issue ceiling of this GPU for the library's own instruction mix (separate DMUL + DADD, no FMA):
  * runs a register-resident microbenchmark for about `milliseconds` and returns TFLOP/s in *tflops_out. */
 int pt_measure_fp64_rate(double milliseconds, double* tflops_out);
@@ -392,6 +415,32 @@ const double* pt_frame_hit_t_device(const PtFrame* frame);    /* owned_pixels */
 int pt_frame_pixel_index(const PtFrame* frame, uint32_t* index_out);
 /* copy the compact outputs back and scatter them into full-size host images (any may be NULL) */
 int pt_frame_read(PtFrame* frame, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtStats* stats);
+
+/* ---- k-d tree build on the device (the step right before the render loop) ----
+ * Replaces KDLeaf::partitioned (src/kdtree/leaf.rs:89-231) as called by KDTreeScene::from (kdscene.rs:19-44: items =
+ * flat instances, bounds = FlatSceneNode::bounds) and KDMesh::new (kdmesh.rs:37-58: items = triangles, bounds =
+ * Triangle::bounds).  bounds: n x {min x, y, z, max x, y, z} (BoundingBox::min / max of item i), host memory for
+ * pt_kd_build, device memory for pt_kd_build_device.  The result is the reference's tree — same planes, same member
+ * lists in the same order — serialised breadth-first exactly like the records of PtSceneDesc.tlas_nodes / blas_nodes
+ * (front child, then back child; leaf lists in the same order), so it can be copied straight into a scene
+ * description, or spliced into an uploaded scene without leaving the device (pt_scene_set_tlas). */
+typedef struct PtKdTree PtKdTree; /* opaque: the tree's records in device memory */
+int pt_kd_build(const double* bounds, uint32_t n, const PtKdBuildConfig* config, PtKdTree** out);
+int pt_kd_build_device(const double* d_bounds, uint32_t n, const PtKdBuildConfig* config, void* stream, PtKdTree** out);
+void pt_kd_tree_free(PtKdTree* tree);
+uint32_t pt_kd_tree_node_count(const PtKdTree* tree);
+uint32_t pt_kd_tree_item_count(const PtKdTree* tree);
+uint32_t pt_kd_tree_depth(const PtKdTree* tree);          /* depth of the deepest node, root = 0 */
+/* root bounds {min x, y, z, max x, y, z} (KDTreeNode::bounds of the root) and BoundingBox::extent of it
+ * (squared diagonal, bounding_box.rs:95-99) — PtSceneDesc.tlas_extent / PtMesh.extent */
+int pt_kd_tree_root_bounds(const PtKdTree* tree, double bounds6_out[6], double* extent_out);
+/* copy the records to host arrays of pt_kd_tree_node_count / pt_kd_tree_item_count entries (either may be NULL) */
+int pt_kd_tree_download(const PtKdTree* tree, PtKdNode* nodes_out, uint32_t* items_out);
+/* device time of the build (CUDA events) and the number of kernels it launched */
+int pt_kd_tree_build_stats(const PtKdTree* tree, double* device_ms_out, uint32_t* launches_out);
+/* Make `tree` the scene tree of an uploaded scene (device-to-device copy; the tree can be freed afterwards).
+ * Its items must be flat-instance indices of that scene. */
+int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree);
 
 #ifdef __cplusplus
 }

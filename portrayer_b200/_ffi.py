@@ -39,6 +39,8 @@ PT_RNG_FIXED, PT_RNG_HASH = 0, 1
 PT_BG_PER_PIXEL, PT_BG_PER_ROW, PT_BG_CONSTANT = 0, 1, 2
 PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS, PT_RENDER_KERNEL_TIMES = 1, 2, 4
 PT_RENDER_ROW_MAJOR, PT_RENDER_NO_GRAPH = 8, 16
+PT_RENDER_TOLERATE_KD_PLANE = 32
+PT_DEVERR_NORMALMAP, PT_DEVERR_TEXTURE, PT_DEVERR_KD_PLANE, PT_DEVERR_TIR, PT_DEVERR_OVERFLOW = 1, 2, 4, 8, 16
 PT_EPSILON = 0.00001
 PT_MAX_RECURSION_DEPTH = 10
 PT_DEFAULT_SAMPLES = 100
@@ -86,6 +88,8 @@ class PtStats(C.Structure):
         ("ms_extend", C.c_double), ("ms_shadow", C.c_double), ("ms_shade", C.c_double),
         ("n_extend", C.c_uint32), ("n_shadow", C.c_uint32), ("n_shade", C.c_uint32), ("reserved2", C.c_uint32),
         ("k_prim_flops", C.c_uint64 * 2),
+        ("err_bit", C.c_uint32), ("err_pixel", C.c_uint32), ("err_sample", C.c_uint32), ("err_pathid", C.c_uint32),
+        ("err_where", C.c_uint32), ("reserved3", C.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -132,6 +136,7 @@ GPU_SYMBOLS = {
     "pt_device_count": (C.c_int, []),
     "pt_release_cached_memory": (None, []),
     "pt_resident_texture_bytes": (C.c_uint64, []),
+    "pt_abi_sizeof": (C.c_uint64, [C.c_int]),
     "pt_measure_fp64_rate": (C.c_int, [C.c_double, C.POINTER(C.c_double)]),
     "pt_scene_blob_size": (C.c_uint64, [C.c_void_p]),
     "pt_scene_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -161,6 +166,16 @@ GPU_SYMBOLS = {
     "pt_frame_hit_t_device": (C.c_void_p, [C.c_void_p]),
     "pt_frame_pixel_index": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_frame_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PtStats)]),
+    "pt_kd_build": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pt_kd_build_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pt_kd_tree_free": (None, [C.c_void_p]),
+    "pt_kd_tree_node_count": (C.c_uint32, [C.c_void_p]),
+    "pt_kd_tree_item_count": (C.c_uint32, [C.c_void_p]),
+    "pt_kd_tree_depth": (C.c_uint32, [C.c_void_p]),
+    "pt_kd_tree_root_bounds": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "pt_kd_tree_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pt_kd_tree_build_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
+    "pt_scene_set_tlas": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 for _name, (_res, _args) in GPU_SYMBOLS.items():
     _fn = getattr(gpu, _name)  # AttributeError here = the library does not export what the header declares
@@ -188,6 +203,17 @@ HOST_SYMBOLS = {
     "pth_camera": (None, [C.c_void_p, C.c_double, C.c_double, C.POINTER(PtCamera)]),
     "pth_background": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "pth_prepare_seconds": (C.c_double, [C.c_void_p]),
+    "pth_scene_item_count": (C.c_uint64, [C.c_void_p]),
+    "pth_scene_item_bounds": (None, [C.c_void_p, C.c_void_p]),
+    "pth_kd_build": (C.c_void_p, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32]),
+    "pth_kd_tree_free": (None, [C.c_void_p]),
+    "pth_kd_tree_node_count": (C.c_uint64, [C.c_void_p]),
+    "pth_kd_tree_item_count": (C.c_uint64, [C.c_void_p]),
+    "pth_kd_tree_depth": (C.c_uint32, [C.c_void_p]),
+    "pth_kd_tree_extent": (C.c_double, [C.c_void_p]),
+    "pth_kd_tree_build_seconds": (C.c_double, [C.c_void_p]),
+    "pth_kd_tree_nodes": (C.c_void_p, [C.c_void_p]),
+    "pth_kd_tree_items": (C.c_void_p, [C.c_void_p]),
     "pth_image_render": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p,
                                    C.POINTER(PtStats)]),
 }

@@ -24,6 +24,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "kd_build.h"
 #include "kernels.h"
 #include "portrayer_gpu.h"
 
@@ -173,9 +174,17 @@ struct PtScene {
     bool has_reflective = false;
     TextureDev* d_textures = nullptr;
     float4* d_aabb = nullptr;               // padded FP32 world box per instance (conservative cull, traverse.cuh)
+    float4* d_tri_aabb = nullptr;           // padded FP32 object box per triangle + per run of 32 / 1024 (one allocation)
+    uint32_t tri_aabb_l1 = 0, tri_aabb_l2 = 0;  // offsets (in boxes) of the two group levels inside d_tri_aabb
     std::vector<uint64_t> resident_keys;    // textures held in the residency cache (refs to drop)
     std::vector<uint8_t*> private_texels;   // unkeyed textures owned by this scene
     uint64_t h2d_bytes = 0;                 // bytes the upload copied to the device
+    PtKdNode* d_own_tlas_nodes = nullptr;   // pt_scene_set_tlas: a device-built scene tree replacing the blob's
+    uint32_t* d_own_tlas_items = nullptr;
+};
+
+struct PtKdTree {
+    ptd::KdTreeDev* dev = nullptr;
 };
 
 struct PtFrame {
@@ -243,7 +252,8 @@ const char* panic_text(int code) {
     }
 }
 
-int device_error_to_code(uint32_t bits) {
+int device_error_to_code(uint32_t bits, uint32_t flags = 0) {
+    if (flags & PT_RENDER_TOLERATE_KD_PLANE) bits &= ~PT_DEVERR_KD_PLANE;
     if (bits & PT_DEVERR_NORMALMAP) return PT_ERR_NO_TEXCOORD_NORMALMAP;
     if (bits & PT_DEVERR_TEXTURE) return PT_ERR_NO_TEXCOORD_TEXTURE;
     if (bits & PT_DEVERR_KD_PLANE) return PT_ERR_KD_PLANE_MISS;
@@ -251,12 +261,21 @@ int device_error_to_code(uint32_t bits) {
     return PT_OK;
 }
 
+// the reference's panic text + where on the image it fired
+int fail_device_error(int code, const PtStats* st, uint32_t width) {
+    if (!st || !st->err_bit || !width) return fail(code, "%s", panic_text(code));
+    static const char* kKernel[3] = {"extend", "shadow", "shade"};
+    return fail(code, "%s [first at pixel (%u, %u) sample %u path %u, %s kernel, recursion level %u]", panic_text(code),
+                st->err_pixel % width, st->err_pixel / width, st->err_sample, st->err_pathid, kKernel[(st->err_where & 0xFF) % 3],
+                (st->err_where >> 8) & 0xFF);
+}
+
 void fill_view(PtScene* s) {
     const PtBlobHeader& h = s->h;
     DScene& v = s->view;
     unsigned char* b = s->d_records;
-    v.tlas_nodes = reinterpret_cast<const PtKdNode*>(b + h.off_tlas_nodes);
-    v.tlas_items = reinterpret_cast<const uint32_t*>(b + h.off_tlas_items);
+    v.tlas_nodes = s->d_own_tlas_nodes ? s->d_own_tlas_nodes : reinterpret_cast<const PtKdNode*>(b + h.off_tlas_nodes);
+    v.tlas_items = s->d_own_tlas_items ? s->d_own_tlas_items : reinterpret_cast<const uint32_t*>(b + h.off_tlas_items);
     v.instances = reinterpret_cast<const PtInstance*>(b + h.off_instances);
     v.instance_trans = reinterpret_cast<const PtInstanceTrans*>(b + h.off_instance_trans);
     v.meshes = reinterpret_cast<const PtMesh*>(b + h.off_meshes);
@@ -269,6 +288,9 @@ void fill_view(PtScene* s) {
     v.lights = reinterpret_cast<const PtLight*>(b + h.off_lights);
     v.textures = s->d_textures;
     v.inst_aabb = s->d_aabb;
+    v.tri_aabb = s->d_tri_aabb;
+    v.tri_aabb_l1 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1 : nullptr;
+    v.tri_aabb_l2 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2 : nullptr;
     v.gamma_lut = g_gamma_lut;
     v.ambient[0] = h.ambient[0]; v.ambient[1] = h.ambient[1]; v.ambient[2] = h.ambient[2];
     v.tlas_extent = h.tlas_extent;
@@ -287,6 +309,9 @@ void free_scene(PtScene* s) {
     for (uint8_t* p : s->private_texels) g_dev.release(p);
     g_dev.release(s->d_textures);
     g_dev.release(s->d_aabb);
+    g_dev.release(s->d_tri_aabb);
+    g_dev.release(s->d_own_tlas_nodes);
+    g_dev.release(s->d_own_tlas_items);
     g_dev.release(s->d_records);
     delete s;
 }
@@ -372,8 +397,19 @@ int build_instance_bounds(PtScene* s) {
     if (!s->d_aabb) return fail(PT_ERR_CUDA, "instance bounds allocation failed: %s", cudaGetErrorString(e));
     double* scratch = static_cast<double*>(g_dev.alloc(std::max<size_t>(s->h.n_meshes, 1) * 6 * sizeof(double), &e));
     if (!scratch) return fail(PT_ERR_CUDA, "mesh bounds allocation failed: %s", cudaGetErrorString(e));
+    // triangle boxes for the Mesh-fold cull
+    const uint32_t nt = s->h.n_triangles;
+    if (nt) {
+        const uint32_t n1 = (nt + 31u) / 32u, n2 = (n1 + 31u) / 32u;
+        s->tri_aabb_l1 = nt;
+        s->tri_aabb_l2 = nt + n1;
+        s->d_tri_aabb = static_cast<float4*>(g_dev.alloc((size_t)(nt + n1 + n2) * 2 * sizeof(float4), &e));
+        if (!s->d_tri_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "triangle bounds allocation failed: %s", cudaGetErrorString(e)); }
+    }
     fill_view(s);
     launch_instance_bounds(s->view, s->h.n_meshes, scratch, s->d_aabb, g_stream);
+    if (nt) launch_triangle_bounds(s->view.tri_pos, nt, s->d_tri_aabb, s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1,
+                                   s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2, g_stream);
     g_dev.release(scratch);  // stream-ordered reuse: later users of the block run after this kernel on g_stream
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "instance bounds kernel failed: %s", cudaGetErrorString(e));
@@ -550,6 +586,13 @@ void accumulate_stats(PtStats* stats, const BatchCtl& c, uint32_t n_paths) {
     stats->texel_lookups += c.texel_lookups;
     stats->nodes_total += c.pool_count;
     stats->device_error_bits |= c.error_bits & ~PT_DEVERR_OVERFLOW;
+    if (c.err_info[0] && !stats->err_bit) {
+        stats->err_bit = c.err_info[0];
+        stats->err_pixel = c.err_info[1];
+        stats->err_sample = c.err_info[2];
+        stats->err_pathid = c.err_info[3];
+        stats->err_where = c.err_info[4];
+    }
     for (uint32_t d = 0; d + 1 < 16; ++d)
         if (c.level_start[d + 1] > c.level_start[d] && d > stats->max_level) stats->max_level = d;
 }
@@ -812,6 +855,17 @@ int pt_measure_fp64_rate(double milliseconds, double* tflops_out) {
     return PT_OK;
 }
 
+uint64_t pt_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(PtCamera);
+        case 1: return sizeof(PtRenderParams);
+        case 2: return sizeof(PtStats);
+        case 3: return sizeof(PtBlobHeader);
+        case 4: return sizeof(PtSceneDesc);
+        default: return 0;
+    }
+}
+
 uint64_t pt_resident_texture_bytes(void) {
     Lock lock(g_mu);
     return g_texture_bytes;
@@ -993,8 +1047,8 @@ static int render_blocking_stream(PtFrame* f, cudaStream_t st, PtProgressFn prog
         stats->kernel_launches = launches;
         stats->device_error_bits = error_bits & ~PT_DEVERR_OVERFLOW;
     }
-    const int code = device_error_to_code(error_bits);
-    if (code != PT_OK) return fail(code, "%s", panic_text(code));
+    const int code = device_error_to_code(error_bits, f->params.flags);
+    if (code != PT_OK) return fail_device_error(code, stats, f->params.width);
     return PT_OK;
 }
 
@@ -1063,8 +1117,8 @@ int pt_frame_finish(PtFrame* frame, PtStats* stats) {
             local.batches = batches;
             local.kernel_launches = launches;
             local.device_error_bits = error_bits & ~PT_DEVERR_OVERFLOW;
-            const int code = device_error_to_code(error_bits);
-            if (code != PT_OK) rc = fail(code, "%s", panic_text(code));
+            const int code = device_error_to_code(error_bits, f->params.flags);
+            if (code != PT_OK) rc = fail_device_error(code, &local, f->params.width);
         }
         if (stats) *stats = local;
     } else {
@@ -1292,6 +1346,115 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
     if (rc != PT_OK) return rc;
     const int code = device_error_to_code(error_bits);
     if (code != PT_OK) return fail(code, "%s", panic_text(code));
+    return PT_OK;
+}
+
+
+// ------------------------------------------------------------------- k-d tree build (kd_build.cu)
+static int kd_config_ok(const PtKdBuildConfig* c) {
+    if (!c) return fail(PT_ERR_INVALID, "null config");
+    if (c->max_depth > PT_MAX_KD_STACK) return fail(PT_ERR_KD_TOO_DEEP, "%s", panic_text(PT_ERR_KD_TOO_DEEP));
+    return PT_OK;
+}
+
+int pt_kd_build_device(const double* d_bounds, uint32_t n, const PtKdBuildConfig* config, void* stream, PtKdTree** out) {
+    if (!out || (n && !d_bounds)) return fail(PT_ERR_INVALID, "null argument");
+    int rc = kd_config_ok(config);
+    if (rc != PT_OK) return rc;
+    Lock lock(g_mu);
+    rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    ptd::KdTreeDev* dev = nullptr;
+    const cudaError_t e = ptd::kd_build_device(d_bounds, n, *config, stream ? (cudaStream_t)stream : g_stream, &dev);
+    if (e == cudaErrorInvalidValue) return fail(PT_ERR_INVALID, "k-d tree does not fit 30-bit node / item indices");
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "k-d tree build failed: %s", cudaGetErrorString(e));
+    *out = new PtKdTree{dev};
+    return PT_OK;
+}
+
+int pt_kd_build(const double* bounds, uint32_t n, const PtKdBuildConfig* config, PtKdTree** out) {
+    if (!out || (n && !bounds)) return fail(PT_ERR_INVALID, "null argument");
+    int rc = kd_config_ok(config);
+    if (rc != PT_OK) return rc;
+    Lock lock(g_mu);
+    rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    cudaError_t e = cudaSuccess;
+    const size_t bytes = std::max<size_t>((size_t)n * 6 * sizeof(double), 8);
+    double* d_bounds = static_cast<double*>(g_dev.alloc(bytes, &e));
+    if (!d_bounds) return fail(PT_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e));
+    if (n) e = cudaMemcpyAsync(d_bounds, bounds, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, g_stream);
+    if (e != cudaSuccess) { g_dev.release(d_bounds); return fail(PT_ERR_CUDA, "bounds upload failed: %s", cudaGetErrorString(e)); }
+    rc = pt_kd_build_device(d_bounds, n, config, g_stream, out);
+    g_dev.release(d_bounds);
+    return rc;
+}
+
+void pt_kd_tree_free(PtKdTree* tree) {
+    if (!tree) return;
+    Lock lock(g_mu);
+    ptd::kd_tree_release(tree->dev);
+    delete tree;
+}
+uint32_t pt_kd_tree_node_count(const PtKdTree* tree) { return tree ? ptd::kd_tree_node_count(tree->dev) : 0; }
+uint32_t pt_kd_tree_item_count(const PtKdTree* tree) { return tree ? ptd::kd_tree_item_count(tree->dev) : 0; }
+uint32_t pt_kd_tree_depth(const PtKdTree* tree) { return tree ? ptd::kd_tree_depth(tree->dev) : 0; }
+
+int pt_kd_tree_root_bounds(const PtKdTree* tree, double bounds6_out[6], double* extent_out) {
+    if (!tree) return fail(PT_ERR_INVALID, "null tree");
+    const double* b = ptd::kd_tree_root_bounds(tree->dev);
+    if (bounds6_out) memcpy(bounds6_out, b, 6 * sizeof(double));
+    if (extent_out) {
+        // (max - min).magnitude_squared(), bounding_box.rs:95-99: x*x + y*y + z*z, left to right, no fused multiply-add
+        const volatile double dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+        const volatile double xx = dx * dx, yy = dy * dy, zz = dz * dz;
+        const volatile double xy = xx + yy;
+        *extent_out = xy + zz;
+    }
+    return PT_OK;
+}
+
+int pt_kd_tree_download(const PtKdTree* tree, PtKdNode* nodes_out, uint32_t* items_out) {
+    if (!tree) return fail(PT_ERR_INVALID, "null tree");
+    Lock lock(g_mu);
+    const uint32_t nn = ptd::kd_tree_node_count(tree->dev), ni = ptd::kd_tree_item_count(tree->dev);
+    if (nodes_out && nn) CUDA_TRY(cudaMemcpy(nodes_out, ptd::kd_tree_nodes_device(tree->dev), (size_t)nn * sizeof(PtKdNode), cudaMemcpyDeviceToHost));
+    if (items_out && ni) CUDA_TRY(cudaMemcpy(items_out, ptd::kd_tree_items_device(tree->dev), (size_t)ni * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return PT_OK;
+}
+
+int pt_kd_tree_build_stats(const PtKdTree* tree, double* device_ms_out, uint32_t* launches_out) {
+    if (!tree) return fail(PT_ERR_INVALID, "null tree");
+    if (device_ms_out) *device_ms_out = ptd::kd_tree_device_ms(tree->dev);
+    if (launches_out) *launches_out = ptd::kd_tree_launches(tree->dev);
+    return PT_OK;
+}
+
+int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree) {
+    if (!scene || !tree) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
+    const uint32_t nn = ptd::kd_tree_node_count(tree->dev), ni = ptd::kd_tree_item_count(tree->dev);
+    if (ptd::kd_tree_depth(tree->dev) > PT_MAX_KD_STACK) return fail(PT_ERR_KD_TOO_DEEP, "%s", panic_text(PT_ERR_KD_TOO_DEEP));
+    cudaError_t e = cudaSuccess;
+    PtKdNode* d_nodes = static_cast<PtKdNode*>(g_dev.alloc(std::max<size_t>(nn, 1) * sizeof(PtKdNode), &e));
+    uint32_t* d_items = d_nodes ? static_cast<uint32_t*>(g_dev.alloc(std::max<size_t>(ni, 1) * sizeof(uint32_t), &e)) : nullptr;
+    if (!d_nodes || !d_items) { g_dev.release(d_nodes); return fail(PT_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(d_nodes, ptd::kd_tree_nodes_device(tree->dev), (size_t)nn * sizeof(PtKdNode), cudaMemcpyDeviceToDevice, g_stream);
+    if (e == cudaSuccess && ni)
+        e = cudaMemcpyAsync(d_items, ptd::kd_tree_items_device(tree->dev), (size_t)ni * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    if (e != cudaSuccess) { g_dev.release(d_nodes); g_dev.release(d_items); return fail(PT_ERR_CUDA, "tree copy failed: %s", cudaGetErrorString(e)); }
+    g_dev.release(scene->d_own_tlas_nodes);
+    g_dev.release(scene->d_own_tlas_items);
+    scene->d_own_tlas_nodes = d_nodes;
+    scene->d_own_tlas_items = d_items;
+    double extent = 0.0;
+    pt_kd_tree_root_bounds(tree, nullptr, &extent);
+    scene->h.tlas_extent = extent;
+    scene->h.tlas_depth = ptd::kd_tree_depth(tree->dev);
+    scene->h.n_tlas_nodes = nn;
+    scene->h.n_tlas_items = ni;
+    fill_view(scene);
     return PT_OK;
 }
 

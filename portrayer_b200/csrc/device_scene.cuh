@@ -32,6 +32,10 @@ struct DScene {
     const TextureDev* textures;
     const double* gamma_lut;  // [256] pow(i / 255, 2.2) computed once on the device (ImageTexture::at, texture.rs:162-168)
     const float4* inst_aabb;  // [2 * n_instances] padded world-space box of every instance (lo, hi), FP32, rounded outward
+    // padded object-space FP32 box of every triangle, of every aligned run of 32 and of 1024 triangles (Mesh fold cull)
+    const float4* tri_aabb;
+    const float4* tri_aabb_l1;
+    const float4* tri_aabb_l2;
     double ambient[3];
     double tlas_extent;
     uint32_t n_lights;
@@ -81,6 +85,10 @@ struct BatchCtl {
     uint32_t levels_run;       // levels that held at least one ray
     uint32_t cursor[2];        // dynamic work distribution of the current level: next unclaimed item of [0] extend, [1] shadow
     uint32_t pad_[1];
+    // where the first device-detected error of the batch happened (the reference's panic location):
+    // [0] PT_DEVERR_* bit (0 = none), [1] global pixel, [2] sample, [3] path id, [4] kernel (0 extend, 1 shadow, 2 shade)
+    // | level << 8 | light << 16, [5] reserved
+    uint32_t err_info[6];
     unsigned long long rays_shadow, rays_reflect, rays_refract, rays_depth_cut, shaded_hits, texel_lookups;
     unsigned long long work[2][5];  // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates, prim_flops]
 };

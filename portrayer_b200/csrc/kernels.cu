@@ -64,6 +64,16 @@ PT_D void flush_counters(BatchCtl* ctl, int kind, const WorkCounters& wc) {
     }
 }
 
+// first device-detected error of the batch: where the reference would have panicked (cold path)
+PT_D void record_error(const FrameParams& fp, const NodePool& pool, BatchCtl* ctl, uint32_t bits, uint32_t node, uint32_t where) {
+    if (atomicCAS(&ctl->err_info[0], 0u, bits) != 0u) return;
+    const uint32_t root = pool.root[node];
+    ctl->err_info[1] = fp.pixel_index ? fp.pixel_index[ctl->first_slot + root / fp.samples] : ctl->first_slot + root;
+    ctl->err_info[2] = root % fp.samples;
+    ctl->err_info[3] = pool.pathid[node];
+    ctl->err_info[4] = where;
+}
+
 // ------------------------------------------------------------------ camera
 // path p of the batch = (owned pixel slot, sample); Camera::ray_at, camera.rs:48-84
 // Block 0 also resets the batch control block: nothing in this kernel reads it, and every later kernel of the
@@ -159,7 +169,9 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
         const V3 o = v3(pool.ox[i], pool.oy[i], pool.oz[i]);
         const V3 d = v3(pool.dx[i], pool.dy[i], pool.dz[i]);
         Hit hit{(double)INFINITY, kNone, 0};
+        const uint32_t err_before = err;
         const bool found = scene_cast<false>(sc, o, d, hit, tlas_stack, blas_stack, err, wc);
+        if (err != err_before) record_error(fs.fp, pool, ctl, err & ~err_before, i, 0u | level << 8);
         pool.t[i] = found ? hit.t : (double)INFINITY;
         pool.inst[i] = found ? hit.inst : kNone;
         pool.sub[i] = found ? hit.sub : 0u;
@@ -210,7 +222,9 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
         const double light_dist = magnitude(hit_to_light);
         const V3 light_dir = hit_to_light / light_dist;
         Hit hit{(double)INFINITY, kNone, 0};
+        const uint32_t err_before = err;
         const bool occluded = scene_cast<true>(sc, hit_point, light_dir, hit, tlas_stack, blas_stack, err, wc);
+        if (err != err_before) record_error(fp, pool, ctl, err & ~err_before, i, 1u | level << 8 | l << 16);
         pool.occl[(size_t)l * pool.capacity + i] = occluded ? 1 : 0;
         ++cast;
     }
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int 
     const uint32_t n = end - begin;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (n + stride - 1) / stride;  // every lane runs the same number of rounds (warp_alloc is collective)
-    uint32_t err = 0;
+    uint32_t err = 0, err_seen = 0;
     unsigned long long n_shaded = 0, n_reflect = 0, n_refract = 0, n_cut = 0, n_texel = 0;
 
     for (uint32_t r = 0; r < rounds; ++r) {
@@ -400,6 +414,10 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int 
                 }
             }
 
+            if (err & ~err_seen & ~PT_DEVERR_OVERFLOW) {
+                record_error(fp, pool, ctl, err & ~err_seen & ~PT_DEVERR_OVERFLOW, i, 2u | level << 8);
+                err_seen = err;
+            }
             // depth cut-off: a child at depth > max_depth is bg whatever it hits (material.rs:102-104)
             if (level + 1 > fp.max_depth) {
                 if (want0) { c0 = kChildBg; ++n_cut; want0 = false; }
@@ -709,6 +727,52 @@ __global__ void __launch_bounds__(kBlock) instance_bounds_kernel(const PtInstanc
     out[2 * (size_t)i + 1] = make_float4(fhi[0], fhi[1], fhi[2], 0.f);
 }
 
+// FP32 box of every triangle (object space), rounded outward and padded by 1e-5 of the triangle's largest
+// coordinate magnitude and extent: the per-triangle cull of Mesh folds (traverse.cuh mesh_fold).
+__global__ void __launch_bounds__(kBlock) triangle_bounds_kernel(const PtTriPos* __restrict__ tri_pos, uint32_t n, float4* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* v = reinterpret_cast<const double*>(tri_pos + k);
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    double mag = 0.0;
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        const double x = v[c];
+        if (!isfinite(x)) finite = false;
+        lo[c % 3] = fmin(lo[c % 3], x);
+        hi[c % 3] = fmax(hi[c % 3], x);
+        mag = fmax(mag, fabs(x));
+    }
+    double diag = 0.0;
+    for (int c = 0; c < 3; ++c) diag = fmax(diag, hi[c] - lo[c]);
+    const double g = 1e-5 * mag + 1e-5 * diag + 1e-30;
+    float flo[3], fhi[3];
+    for (int c = 0; c < 3; ++c) {
+        flo[c] = __double2float_rd(lo[c] - g);
+        fhi[c] = __double2float_ru(hi[c] + g);
+        if (!finite) { flo[c] = -INFINITY; fhi[c] = INFINITY; }  // never cull what cannot be bounded
+    }
+    out[2 * (size_t)k] = make_float4(flo[0], flo[1], flo[2], 0.f);
+    out[2 * (size_t)k + 1] = make_float4(fhi[0], fhi[1], fhi[2], 0.f);
+}
+
+// union of every aligned run of 32 boxes of `in` (n boxes) -> out[ceil(n / 32)]
+__global__ void __launch_bounds__(kBlock) group_bounds_kernel(const float4* __restrict__ in, uint32_t n, float4* __restrict__ out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_groups = (n + 31u) / 32u;
+    if (g >= n_groups) return;
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+    const uint32_t end = min(n, (g + 1u) * 32u);
+    for (uint32_t k = g * 32u; k < end; ++k) {
+        const float4 a = in[2 * (size_t)k], b = in[2 * (size_t)k + 1];
+        lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+        hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
+    }
+    out[2 * (size_t)g] = lo;
+    out[2 * (size_t)g + 1] = hi;
+}
+
 // pow(i / 255, 2.2) for the 256 possible texel values, with the device's own pow(): bit-identical to evaluating it per hit
 __global__ void gamma_lut_kernel(double* __restrict__ lut) {
     const int i = threadIdx.x;
@@ -774,6 +838,15 @@ void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bo
     if (sc.n_instances)
         instance_bounds_kernel<<<blocks_for(sc.n_instances), kBlock, 0, st>>>(sc.instances, sc.instance_trans, sc.n_instances,
                                                                             mesh_bounds_scratch, out);
+}
+
+// tri_aabb[n], l1[ceil(n / 32)], l2[ceil(n / 1024)]
+void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, float4* l1, float4* l2, cudaStream_t st) {
+    if (!n) return;
+    const uint32_t n1 = (n + 31u) / 32u, n2 = (n1 + 31u) / 32u;
+    triangle_bounds_kernel<<<blocks_for(n), kBlock, 0, st>>>(tri_pos, n, tri_aabb);
+    group_bounds_kernel<<<blocks_for(n1), kBlock, 0, st>>>(tri_aabb, n, l1);
+    group_bounds_kernel<<<blocks_for(n2), kBlock, 0, st>>>(l1, n1, l2);
 }
 
 cudaError_t upload_state(int slot, const FrameState& state, cudaStream_t st) {

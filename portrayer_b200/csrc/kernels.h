@@ -14,6 +14,9 @@ void launch_gamma_lut(double* lut256, cudaStream_t st);
 // upload time: padded FP32 world boxes of all instances (mesh_bounds_scratch: n_meshes * 6 doubles)
 void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bounds_scratch, float4* out, cudaStream_t st);
 
+// upload time: padded FP32 object-space boxes of all triangles + of every aligned run of 32 / 1024 of them
+void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, float4* l1, float4* l2, cudaStream_t st);
+
 // stream path: one launch per call; batch / level bookkeeping lives in the device control block
 void launch_camera(int slot, uint32_t first_slot, uint32_t n_slots, uint32_t samples, cudaStream_t st);
 void launch_load_rays(int slot, uint32_t first, uint32_t n_paths, cudaStream_t st);

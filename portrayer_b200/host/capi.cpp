@@ -15,6 +15,15 @@ struct PthScene {
     ExampleScene example;
     std::vector<uint8_t> blob;
     double prepare_seconds = 0.0;
+    std::vector<double> item_bounds;  // n x 6: FlatSceneNode::bounds of every flat instance
+};
+
+struct PthKdTree {
+    std::vector<PtKdNode> nodes;
+    std::vector<uint32_t> items;
+    uint32_t depth = 0;
+    double extent = 0.0;
+    double seconds = 0.0;
 };
 
 namespace {
@@ -23,18 +32,28 @@ thread_local std::string g_error;
 PthScene* finish(ExampleScene ex, int64_t kd_depth, int linear_tlas) {
     auto out = std::make_unique<PthScene>();
     auto t0 = std::chrono::steady_clock::now();
+    auto keep_bounds = [&out](const std::vector<FlatSceneNode>& nodes) {
+        out->item_bounds.reserve(nodes.size() * 6);
+        for (const FlatSceneNode& n : nodes) {
+            const BoundingBox b = n.bounds();
+            for (double v : {b.min().x, b.min().y, b.min().z, b.max().x, b.max().y, b.max().z}) out->item_bounds.push_back(v);
+        }
+    };
     if (ex.prebuilt) {
         out->blob = pack_scene(*ex.prebuilt);
+        keep_bounds(ex.prebuilt->nodes);
     } else {
         FlatScene flat = FlatScene::from(ex.scene);
         if (linear_tlas) {
             // one unpartitioned leaf: the flat_scene feature's linear fold (flat_scene.rs:71-99, ray.rs:87-99)
             KDTreeScene kd = KDTreeScene::from(std::move(flat), 0);
             out->blob = pack_scene(kd);
+            keep_bounds(kd.nodes);
         } else {
             KDTreeScene kd = kd_depth < 0 ? KDTreeScene::from(std::move(flat))
                                           : KDTreeScene::from(std::move(flat), static_cast<size_t>(kd_depth));
             out->blob = pack_scene(kd);
+            keep_bounds(kd.nodes);
         }
     }
     out->prepare_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -112,6 +131,39 @@ PthScene* pth_synthetic_triangles_build(uint64_t n_triangles, uint64_t seed, int
     });
 }
 void pth_scene_free(PthScene* s) { delete s; }
+
+uint64_t pth_scene_item_count(const PthScene* s) { return s->item_bounds.size() / 6; }
+void pth_scene_item_bounds(const PthScene* s, double* out) {
+    std::copy(s->item_bounds.begin(), s->item_bounds.end(), out);
+}
+
+PthKdTree* pth_kd_build(const double* bounds, uint64_t n, uint32_t max_depth, uint32_t target_max_nodes,
+                        int32_t target_max_merit, uint32_t max_tries) {
+    try {
+        auto out = std::make_unique<PthKdTree>();
+        auto t0 = std::chrono::steady_clock::now();
+        PartitionConfig conf{target_max_nodes, target_max_merit, max_tries};
+        auto root = build_kdtree(static_cast<size_t>(n), [bounds](size_t i) {
+            const double* b = bounds + i * 6;
+            return BoundingBox(Vec3{b[0], b[1], b[2]}, Vec3{b[3], b[4], b[5]});
+        }, max_depth, conf);
+        out->depth = serialise_kd_tree(*root, out->nodes, out->items);
+        out->extent = root->extent();
+        out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return out.release();
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return nullptr;
+    }
+}
+void pth_kd_tree_free(PthKdTree* t) { delete t; }
+uint64_t pth_kd_tree_node_count(const PthKdTree* t) { return t->nodes.size(); }
+uint64_t pth_kd_tree_item_count(const PthKdTree* t) { return t->items.size(); }
+uint32_t pth_kd_tree_depth(const PthKdTree* t) { return t->depth; }
+double pth_kd_tree_extent(const PthKdTree* t) { return t->extent; }
+double pth_kd_tree_build_seconds(const PthKdTree* t) { return t->seconds; }
+const PtKdNode* pth_kd_tree_nodes(const PthKdTree* t) { return t->nodes.data(); }
+const uint32_t* pth_kd_tree_items(const PthKdTree* t) { return t->items.data(); }
 
 uint64_t pth_blob_size(const PthScene* s) { return s->blob.size(); }
 const void* pth_blob_data(const PthScene* s) { return s->blob.data(); }

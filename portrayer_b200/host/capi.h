@@ -44,6 +44,25 @@ void pth_background(const PthScene* s, uint32_t width, uint32_t height, double* 
 /* seconds spent in FlatScene::from + KDTreeScene::from + pack */
 double pth_prepare_seconds(const PthScene* s);
 
+/* world-space bounds of the scene tree's items = FlatSceneNode::bounds of every flat instance (flat_scene.rs:63-69),
+ * n x {min x, y, z, max x, y, z}: the input of the scene-tree build (kdscene.rs:24-28) */
+uint64_t pth_scene_item_count(const PthScene* s);
+void pth_scene_item_bounds(const PthScene* s, double* out);
+
+/* KDLeaf::partitioned on the host (the C++ mirror of leaf.rs:89-231) over n items given by their bounds,
+ * serialised like the boundary's PtKdNode / leaf-item records: the comparison arm of pt_kd_build. */
+typedef struct PthKdTree PthKdTree;
+PthKdTree* pth_kd_build(const double* bounds, uint64_t n, uint32_t max_depth, uint32_t target_max_nodes,
+                        int32_t target_max_merit, uint32_t max_tries);
+void pth_kd_tree_free(PthKdTree* t);
+uint64_t pth_kd_tree_node_count(const PthKdTree* t);
+uint64_t pth_kd_tree_item_count(const PthKdTree* t);
+uint32_t pth_kd_tree_depth(const PthKdTree* t);
+double pth_kd_tree_extent(const PthKdTree* t);      /* BoundingBox::extent of the root */
+double pth_kd_tree_build_seconds(const PthKdTree* t);
+const PtKdNode* pth_kd_tree_nodes(const PthKdTree* t);
+const uint32_t* pth_kd_tree_items(const PthKdTree* t);
+
 /* Image::render through the C++ mirror (the call an example's main() makes). rgb_inout = W*H*3. */
 int pth_image_render(const PthScene* s, uint32_t width, uint32_t height, uint32_t samples, uint32_t rng_mode,
                      uint64_t seed, uint8_t* rgb_inout, PtStats* stats);

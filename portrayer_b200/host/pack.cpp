@@ -70,6 +70,17 @@ TreeOut serialise_tree(const KDIndexTree& root) {
     return out;
 }
 
+}  // namespace
+
+uint32_t serialise_kd_tree(const KDIndexTree& root, std::vector<PtKdNode>& nodes_out, std::vector<uint32_t>& items_out) {
+    TreeOut t = serialise_tree(root);
+    nodes_out = std::move(t.nodes);
+    items_out = std::move(t.items);
+    return t.depth;
+}
+
+namespace {
+
 struct Builder {
     std::vector<PtKdNode> tlas_nodes, blas_nodes;
     std::vector<uint32_t> tlas_items, blas_items;

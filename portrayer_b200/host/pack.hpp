@@ -22,4 +22,8 @@ std::vector<uint8_t> pack_scene(const KDTreeScene& scene);
 std::vector<uint8_t> pack_scene(const std::vector<FlatSceneNode>& nodes, const KDIndexTree& root,
                                 const std::vector<Light>& lights, Rgb ambient);
 
+// Breadth-first serialisation of a tree into the PtKdNode / leaf-item records of the boundary (front child, then back
+// child; leaf lists in visiting order).  Returns the depth of the deepest node (root = 0).
+uint32_t serialise_kd_tree(const KDIndexTree& root, std::vector<PtKdNode>& nodes_out, std::vector<uint32_t>& items_out);
+
 }  // namespace portrayer

@@ -65,6 +65,10 @@ class DeviceScene:
     def handle(self) -> C.c_void_p:
         return self._h
 
+    def set_tlas(self, tree) -> None:
+        """make a device-built tree (kdbuild.KdTree) the scene tree of this uploaded scene"""
+        check(gpu.pt_scene_set_tlas(self._h, tree.handle))
+
     @property
     def uploaded_bytes(self) -> int:
         """host -> device bytes of the upload (records + textures that were not already resident)"""

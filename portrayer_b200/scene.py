@@ -83,6 +83,25 @@ class Scene:
             return np.ascontiguousarray(bg[:, 0, :])
         return None
 
+    def item_bounds(self) -> np.ndarray:
+        """FlatSceneNode::bounds of every flat instance (flat_scene.rs:63-69): [n, 6] = min xyz, max xyz — the input of
+        the scene-tree build (kdscene.rs:24-28)."""
+        n = host.pth_scene_item_count(self._h)
+        out = np.empty((n, 6), dtype=np.float64)
+        if n:
+            host.pth_scene_item_bounds(self._h, out.ctypes.data)
+        return out
+
+    def section(self, name: str, dtype, width: int) -> np.ndarray:
+        """a record section of the blob as an [n, width] array view, e.g. section('tri_pos', np.float64, 9)"""
+        h = self.header
+        n = getattr(h, {"tlas_nodes": "n_tlas_nodes", "tlas_items": "n_tlas_items", "blas_nodes": "n_blas_nodes",
+                        "blas_items": "n_blas_items", "tri_pos": "n_triangles"}[name])
+        off = getattr(h, "off_" + name)
+        dt = np.dtype(dtype)
+        return np.frombuffer(self.blob, dtype=dt, count=n * width, offset=off).reshape(n, width) if width > 1 else \
+            np.frombuffer(self.blob, dtype=dt, count=n, offset=off)
+
     def close(self) -> None:
         if self._h:
             self.blob = None

@@ -33,6 +33,12 @@ def test_struct_sizes_match_the_header(native_libraries):
     assert C.sizeof(_ffi.PtCamera) == 23 * 8
     assert C.sizeof(_ffi.PtRenderParams) == 88
     assert C.sizeof(_ffi.PtBlobHeader) % 8 == 0
+    # and against the compiled library itself
+    assert _ffi.gpu.pt_abi_sizeof(0) == C.sizeof(_ffi.PtCamera)
+    assert _ffi.gpu.pt_abi_sizeof(1) == C.sizeof(_ffi.PtRenderParams)
+    assert _ffi.gpu.pt_abi_sizeof(2) == C.sizeof(_ffi.PtStats)
+    assert _ffi.gpu.pt_abi_sizeof(3) == C.sizeof(_ffi.PtBlobHeader)
+    assert _ffi.gpu.pt_abi_sizeof(99) == 0
 
 
 def test_error_strings_are_the_reference_panics(native_libraries):

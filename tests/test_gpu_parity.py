@@ -58,6 +58,41 @@ def test_big_scene(gpu_ready, kd_depth):
     assert stats.rays == ref.stats.rays
 
 
+# configs[2], synthetic half: N random instances on a grid (TLAS stress, deep scene tree) and one KDMesh of N random
+# triangles (BLAS stress), generator of SURVEY 8d M3b, trees as deep as ceil(log2(N / 3))
+@pytest.mark.parametrize("kind,n,depth", [("instances", 10_000, 12), ("instances", 100_000, 16), ("triangles", 100_000, 16)])
+def test_synthetic_kd_stress(gpu_ready, kind, n, depth):
+    scene = pt.Scene.synthetic_instances(n, kd_depth=depth) if kind == "instances" else pt.Scene.synthetic_triangles(n, kd_mesh_depth=depth)
+    assert max(scene.header.tlas_depth, scene.header.blas_max_depth) == depth
+    kw = dict(samples=1, rng="hash", size=(330, 170))
+    img, stats = parity.render_gpu(scene, **kw)
+    ref = parity.render_oracle(scene, **kw)
+    assert ref.rc == 0
+    rep = parity.compare(img, ref, f"synthetic {kind} {n}")
+    print(rep)
+    parity.assert_parity(rep)
+    assert rep["hit_t_bit_identical"]
+    assert stats.rays == ref.stats.rays
+
+
+# the linear Mesh fold skips runs of triangles whose FP32 boxes the ray certainly misses (traverse.cuh mesh_fold): its
+# result, and the number of triangle tests the reference's fold makes, must be those of the oracle's plain fold —
+# closest hit and any hit
+def test_mesh_fold_counters_match_sequential_fold(gpu_ready):
+    from portrayer_b200 import _ffi
+
+    for name in ("nonhier", "soft-shadows"):
+        scene = pt.Scene.example(name)
+        kw = dict(samples=1, rng="hash", size=(200, 120))
+        img, stats = parity.render_gpu(scene, flags=_ffi.PT_RENDER_COUNTERS, **kw)
+        ref = parity.render_oracle(scene, **kw)
+        parity.assert_parity(parity.compare(img, ref, name))
+        assert np.array_equal(img.hit_id, ref.hit_id) and np.array_equal(img.hit_t, ref.hit_t)
+        assert stats.triangle_tests == ref.stats.triangle_tests and stats.triangle_tests > 0
+        assert stats.bbox_gates == ref.stats.bbox_gates
+        assert stats.instance_tests == ref.stats.instance_tests and stats.kd_splits == ref.stats.kd_splits
+
+
 # configs[3]: secondary-ray-bound recursion with hashed jitter, glossy + area-light + dielectric RNG dimensions
 @pytest.mark.parametrize("name,samples", [("glossy-reflection", 4), ("soft-shadows", 2)])
 def test_secondary_ray_scenes(gpu_ready, name, samples):
@@ -255,3 +290,26 @@ def test_graphics_castle(gpu_ready, kd_depth):
     parity.assert_parity(rep)
     assert (stats.rays_primary, stats.rays_shadow, stats.rays_reflect, stats.rays_refract) == \
            (ref.stats.rays_primary, ref.stats.rays_shadow, ref.stats.rays_reflect, ref.stats.rays_refract)
+
+
+# configs[4] at full size holds one ray on which the reference's kd walk panics (see tests/test_oracle_kats.py): the
+# device fails with the reference's panic text and says where; with PT_RENDER_TOLERATE_KD_PLANE the frame is finished,
+# the event stays visible in the stats, and every other sample is the oracle's
+@pytest.mark.skipif(not has_reference_assets(), reason="reference assets not synced")
+def test_castle_kd_plane_panic_device(gpu_ready):
+    from portrayer_b200 import _ffi
+    from test_oracle_kats import CASTLE_PANIC_PIXEL
+
+    scene = pt.Scene.example("graphics-castle")
+    w, h = 3840, 2160
+    x, y = CASTLE_PANIC_PIXEL
+    kw = dict(samples=64, rng="hash", seed=1, size=(w, h), slice_=(x - 1, y, x, y))
+    with pytest.raises(pt.PortrayerError) as err:
+        parity.render_gpu(scene, **kw)
+    assert err.value.code == _ffi.PT_ERR_KD_PLANE_MISS
+    assert "bug: ray should definitely hit infinite plane" in str(err.value) and f"pixel ({x}, {y}) sample 57" in str(err.value)
+    img, stats = parity.render_gpu(scene, flags=_ffi.PT_RENDER_TOLERATE_KD_PLANE, **kw)
+    assert stats.device_error_bits == _ffi.PT_DEVERR_KD_PLANE and stats.err_bit == _ffi.PT_DEVERR_KD_PLANE
+    assert (stats.err_pixel % w, stats.err_pixel // w, stats.err_sample) == (x, y, 57)
+    ref = parity.render_oracle(scene, samples=64, rng="hash", seed=1, size=(w, h), slice_=(x - 1, y, x - 1, y))
+    assert ref.rc == 0 and np.array_equal(img.buffer[y, x - 1], ref.rgb[y, x - 1])

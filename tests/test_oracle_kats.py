@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import portrayer_b200 as pt
+from conftest import has_reference_assets
 from oracle import binding as oracle
 
 
@@ -71,3 +72,26 @@ def test_mesh_equivalence():
     assert (id_a[:, 0] != 0xFFFFFFFF).sum() > n // 10  # the sweep really crosses the castle
     # the kd walk tests far fewer triangles than the linear scan
     assert st_b.triangle_tests * 5 < st_a.triangle_tests
+
+
+# The reference's kd walk panics when rounding puts a split-plane crossing outside the ray's range
+# (.expect("bug: ray should definitely hit infinite plane"), kdtree/node.rs:147,178; README.md:247-248 calls the
+# kd-tree "occasionally buggy").  The 4K x 64-sample graphics-castle frame of BASELINE.json configs[4] holds one such
+# ray under the hashed jitter of seed 1 (found by the device, which reports where the panic fires): the restatement
+# panics on exactly that pixel and not on its neighbour.  tests/test_gpu_parity.py checks the device against this.
+CASTLE_PANIC_PIXEL = (1784, 1742)
+
+
+@pytest.mark.skipif(not has_reference_assets(), reason="reference assets not synced (tools/sync_assets.py)")
+def test_castle_kd_plane_panic_is_reproduced(native_libraries):
+    from portrayer_b200 import _ffi
+    from portrayer_b200.render import _background_arg, make_params
+
+    scene = pt.Scene.example("graphics-castle")
+    w, h = 3840, 2160
+    bg, bg_mode = _background_arg(scene, w, h)
+    x, y = CASTLE_PANIC_PIXEL
+    for px, expect in (((x, y), _ffi.PT_ERR_KD_PLANE_MISS), ((x - 1, y), 0)):
+        p = make_params(w, h, 64, "hash", 1, slice_=(px[0], px[1], px[0], px[1]), bg_mode=bg_mode)
+        res = oracle.render(scene.blob, scene.camera(w, h), p, bg, threads=1)
+        assert res.rc == expect
