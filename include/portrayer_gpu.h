@@ -436,8 +436,9 @@ uint32_t pt_kd_tree_depth(const PtKdTree* tree);          /* depth of the deepes
 int pt_kd_tree_root_bounds(const PtKdTree* tree, double bounds6_out[6], double* extent_out);
 /* copy the records to host arrays of pt_kd_tree_node_count / pt_kd_tree_item_count entries (either may be NULL) */
 int pt_kd_tree_download(const PtKdTree* tree, PtKdNode* nodes_out, uint32_t* items_out);
-/* device time of the build (CUDA events) and the number of kernels it launched */
-int pt_kd_tree_build_stats(const PtKdTree* tree, double* device_ms_out, uint32_t* launches_out);
+/* device time of the build (CUDA events), the number of kernels it launched, and the bytes the build has to move at
+ * the least (its HBM roofline numerator: members x passes, see kd_build.cu); any may be NULL */
+int pt_kd_tree_build_stats(const PtKdTree* tree, double* device_ms_out, uint32_t* launches_out, uint64_t* algorithmic_bytes_out);
 /* Make `tree` the scene tree of an uploaded scene (device-to-device copy; the tree can be freed afterwards).
  * Its items must be flat-instance indices of that scene. */
 int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree);

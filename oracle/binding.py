@@ -20,7 +20,8 @@ lib = C.CDLL(_LIB)
 class OracleStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "rays_depth_cut", "kd_splits",
-        "instance_tests", "triangle_tests", "bbox_gates", "shaded_hits", "texel_lookups")]
+        "instance_tests", "triangle_tests", "bbox_gates", "shaded_hits", "texel_lookups",
+        "shadow_kd_splits", "shadow_instance_tests", "shadow_triangle_tests", "shadow_bbox_gates")]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

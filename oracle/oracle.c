@@ -758,7 +758,13 @@ static void hit_color(Ctx* cx, const PtMaterial* mat, const double* background, 
         Isect sh;
         uint32_t sh_inst;
         cx->st.rays_shadow++;
-        if (!scene_ray_cast(cx, &shadow_ray, &shadow_range, &sh, &sh_inst)) { /* material.rs:174-179 */
+        const OracleStats before = cx->st;
+        const int shadowed = scene_ray_cast(cx, &shadow_ray, &shadow_range, &sh, &sh_inst); /* material.rs:174-179 */
+        cx->st.shadow_kd_splits += cx->st.kd_splits - before.kd_splits;
+        cx->st.shadow_instance_tests += cx->st.instance_tests - before.instance_tests;
+        cx->st.shadow_triangle_tests += cx->st.triangle_tests - before.triangle_tests;
+        cx->st.shadow_bbox_gates += cx->st.bbox_gates - before.bbox_gates;
+        if (!shadowed) {
             double normal_light = fmax(dot(normal, light_dir), 0.0);
             double diffuse[3] = {kd[0] * light->color[0] * normal_light, kd[1] * light->color[1] * normal_light,
                                  kd[2] * light->color[2] * normal_light};
@@ -979,6 +985,8 @@ static void stats_add(OracleStats* a, const OracleStats* b) {
     a->kd_splits += b->kd_splits; a->instance_tests += b->instance_tests;
     a->triangle_tests += b->triangle_tests; a->bbox_gates += b->bbox_gates;
     a->shaded_hits += b->shaded_hits; a->texel_lookups += b->texel_lookups;
+    a->shadow_kd_splits += b->shadow_kd_splits; a->shadow_instance_tests += b->shadow_instance_tests;
+    a->shadow_triangle_tests += b->shadow_triangle_tests; a->shadow_bbox_gates += b->shadow_bbox_gates;
 }
 
 int oracle_render(const void* blob, uint64_t bytes, const PtCamera* cam, const PtRenderParams* params,

@@ -13,6 +13,9 @@ typedef struct OracleStats {
     uint64_t rays_primary, rays_shadow, rays_reflect, rays_refract, rays_depth_cut;
     uint64_t kd_splits, instance_tests, triangle_tests, bbox_gates;
     uint64_t shaded_hits, texel_lookups;
+    /* the share of the four work counters above spent inside shadow-ray casts (material.rs:174-179); the rest belongs
+     * to primary / reflected / refracted rays — what the device's closest-hit kernel must reproduce exactly */
+    uint64_t shadow_kd_splits, shadow_instance_tests, shadow_triangle_tests, shadow_bbox_gates;
 } OracleStats;
 
 /* The pixel loop of src/render.rs:127-150 on n_threads host threads.

@@ -174,7 +174,7 @@ GPU_SYMBOLS = {
     "pt_kd_tree_depth": (C.c_uint32, [C.c_void_p]),
     "pt_kd_tree_root_bounds": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "pt_kd_tree_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "pt_kd_tree_build_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
+    "pt_kd_tree_build_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "pt_scene_set_tlas": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 for _name, (_res, _args) in GPU_SYMBOLS.items():

@@ -174,6 +174,7 @@ struct PtScene {
     bool has_reflective = false;
     TextureDev* d_textures = nullptr;
     float4* d_aabb = nullptr;               // padded FP32 world box per instance (conservative cull, traverse.cuh)
+    float4* d_leaf_aabb = nullptr;          // d_aabb gathered into scene-tree leaf order
     float4* d_tri_aabb = nullptr;           // padded FP32 object box per triangle + per run of 32 / 1024 (one allocation)
     uint32_t tri_aabb_l1 = 0, tri_aabb_l2 = 0;  // offsets (in boxes) of the two group levels inside d_tri_aabb
     std::vector<uint64_t> resident_keys;    // textures held in the residency cache (refs to drop)
@@ -288,6 +289,7 @@ void fill_view(PtScene* s) {
     v.lights = reinterpret_cast<const PtLight*>(b + h.off_lights);
     v.textures = s->d_textures;
     v.inst_aabb = s->d_aabb;
+    v.leaf_aabb = s->d_leaf_aabb;
     v.tri_aabb = s->d_tri_aabb;
     v.tri_aabb_l1 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1 : nullptr;
     v.tri_aabb_l2 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2 : nullptr;
@@ -310,6 +312,7 @@ void free_scene(PtScene* s) {
     g_dev.release(s->d_textures);
     g_dev.release(s->d_aabb);
     g_dev.release(s->d_tri_aabb);
+    g_dev.release(s->d_leaf_aabb);
     g_dev.release(s->d_own_tlas_nodes);
     g_dev.release(s->d_own_tlas_items);
     g_dev.release(s->d_records);
@@ -406,8 +409,11 @@ int build_instance_bounds(PtScene* s) {
         s->d_tri_aabb = static_cast<float4*>(g_dev.alloc((size_t)(nt + n1 + n2) * 2 * sizeof(float4), &e));
         if (!s->d_tri_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "triangle bounds allocation failed: %s", cudaGetErrorString(e)); }
     }
+    s->d_leaf_aabb = static_cast<float4*>(g_dev.alloc(std::max<size_t>(s->h.n_tlas_items, 1) * 2 * sizeof(float4), &e));
+    if (!s->d_leaf_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e)); }
     fill_view(s);
     launch_instance_bounds(s->view, s->h.n_meshes, scratch, s->d_aabb, g_stream);
+    launch_gather_leaf_boxes(s->d_aabb, s->view.tlas_items, s->h.n_tlas_items, s->d_leaf_aabb, g_stream);
     if (nt) launch_triangle_bounds(s->view.tri_pos, nt, s->d_tri_aabb, s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1,
                                    s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2, g_stream);
     g_dev.release(scratch);  // stream-ordered reuse: later users of the block run after this kernel on g_stream
@@ -1423,10 +1429,11 @@ int pt_kd_tree_download(const PtKdTree* tree, PtKdNode* nodes_out, uint32_t* ite
     return PT_OK;
 }
 
-int pt_kd_tree_build_stats(const PtKdTree* tree, double* device_ms_out, uint32_t* launches_out) {
+int pt_kd_tree_build_stats(const PtKdTree* tree, double* device_ms_out, uint32_t* launches_out, uint64_t* algorithmic_bytes_out) {
     if (!tree) return fail(PT_ERR_INVALID, "null tree");
     if (device_ms_out) *device_ms_out = ptd::kd_tree_device_ms(tree->dev);
     if (launches_out) *launches_out = ptd::kd_tree_launches(tree->dev);
+    if (algorithmic_bytes_out) *algorithmic_bytes_out = ptd::kd_tree_algorithmic_bytes(tree->dev);
     return PT_OK;
 }
 
@@ -1454,6 +1461,12 @@ int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree) {
     scene->h.tlas_depth = ptd::kd_tree_depth(tree->dev);
     scene->h.n_tlas_nodes = nn;
     scene->h.n_tlas_items = ni;
+    float4* d_leaf = static_cast<float4*>(g_dev.alloc(std::max<size_t>(ni, 1) * 2 * sizeof(float4), &e));
+    if (!d_leaf) return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e));
+    g_dev.release(scene->d_leaf_aabb);
+    scene->d_leaf_aabb = d_leaf;
+    launch_gather_leaf_boxes(scene->d_aabb, d_items, ni, d_leaf, g_stream);
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
     fill_view(scene);
     return PT_OK;
 }

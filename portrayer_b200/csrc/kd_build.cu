@@ -59,6 +59,7 @@ struct LevelState {
     uint32_t* counts;          // [K][4] front, back, shared, (unused)
     uint8_t* status;           // [K] 0 = leaf, 1 = still searching, 2 = plane fixed
     uint32_t* n_searching;     // [1] nodes with status 1
+    uint32_t* tries_used;      // [1] tries of this level in which at least one node was still searching
 };
 
 __global__ void transpose_bounds_kernel(const double* __restrict__ aos, uint32_t n, double* __restrict__ soa) {
@@ -145,6 +146,7 @@ template <bool ALL>
 __global__ void __launch_bounds__(kB) count_kernel(const uint32_t* __restrict__ items, const uint32_t* __restrict__ owner, uint32_t m,
                                                    const double* __restrict__ bmin, const double* __restrict__ bmax, LevelState st) {
     if (!ALL && *st.n_searching == 0u) return;
+    if (!ALL && blockIdx.x == 0 && threadIdx.x == 0) ++*st.tries_used;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint32_t k = 0xFFFFFFFFu, cls = 3u;
@@ -431,6 +433,8 @@ struct KdTreeDev {
     double root_bounds[6] = {0, 0, 0, 0, 0, 0};
     uint32_t launches = 0;
     float device_ms = 0.f;
+    uint64_t bytes = 0;   // algorithmic bytes of the build (see the level loop)
+    uint32_t tries = 0;   // plane-search rounds that did work, summed over levels
 };
 
 #define KD_TRY(expr)                                  \
@@ -525,8 +529,10 @@ cudaError_t kd_build_device(const double* d_bounds_aos, uint32_t n, const PtKdBu
 
         LevelState ls{seg[cur].as<uint32_t>(), klo.as<unsigned long long>(), khi.as<unsigned long long>(), plane.as<double>(),
                       pmin.as<double>(), pmax.as<double>(), counts.as<uint32_t>(), status.as<uint8_t>(),
-                      reinterpret_cast<uint32_t*>(scalars.as<unsigned long long>() + 8)};
+                      reinterpret_cast<uint32_t*>(scalars.as<unsigned long long>() + 8),
+                      reinterpret_cast<uint32_t*>(scalars.as<unsigned long long>() + 3)};
         KD_TRY(cudaMemsetAsync(ls.n_searching, 0, 4, st));
+        KD_TRY(cudaMemsetAsync(ls.tries_used, 0, 8, st));
         if (depth_left > 0 && M > 0) {
             init_keys_kernel<<<blocks(K), kB, 0, st>>>(ls.klo, ls.khi, K);
             bounds_kernel<<<blocks(M), kB, 0, st>>>(d_items, d_owner, M, bmin, bmax, ls.klo, ls.khi);
@@ -553,8 +559,19 @@ cudaError_t kd_build_device(const double* d_bounds_aos, uint32_t n, const PtKdBu
         KD_TRY(exclusive_scan(LeafLoad{ls.status, ls.seg}, K, tiles, d_tot + 1, leaf_pfx.as<unsigned long long>(), st));
         KD_TRY(exclusive_scan(ClassLoad{cls.as<uint8_t>()}, M, tiles, d_tot + 2, item_pfx.as<unsigned long long>(), st));
         launches += 9;
-        KD_TRY(cudaMemcpyAsync(h_scalars, d_tot, 2 * 8, cudaMemcpyDeviceToHost, st));
+        KD_TRY(cudaMemcpyAsync(h_scalars, d_tot, 4 * 8, cudaMemcpyDeviceToHost, st));
         KD_TRY(cudaStreamSynchronize(st));
+        {
+            // bytes this level has to move at the very least (the build's roofline numerator): per member 4 B id + 4 B
+            // owner + 2 x 8 B bounds for the bounds pass, for every try that still had a searching node and for the final
+            // classification (+ 1 B class out); class in + 8 B prefix out for the scan; id, owner, class, prefix in and
+            // one or two (id, owner) pairs out for the scatter; per node 16 B record out + ~60 B of state
+            const uint64_t tries = (uint32_t)h_scalars[3];
+            const uint64_t m = M, mn = h_scalars[0] & 0xFFFFFFFFull;
+            tree->bytes += (depth_left > 0 ? m * 24 * (1 + tries) : 0) + m * 25 + m * 9 + m * 17 + (mn + (uint32_t)h_scalars[1]) * 8 +
+                           (uint64_t)K * 76;
+            tree->tries += tries;
+        }
         const uint32_t n_split = (uint32_t)(h_scalars[0] >> 32);
         const uint64_t m_next = h_scalars[0] & 0xFFFFFFFFull;
         const uint32_t leaf_members = (uint32_t)h_scalars[1];
@@ -625,6 +642,8 @@ uint32_t kd_tree_item_count(const KdTreeDev* t) { return t->n_items; }
 uint32_t kd_tree_depth(const KdTreeDev* t) { return t->depth; }
 uint32_t kd_tree_launches(const KdTreeDev* t) { return t->launches; }
 float kd_tree_device_ms(const KdTreeDev* t) { return t->device_ms; }
+uint64_t kd_tree_algorithmic_bytes(const KdTreeDev* t) { return t->bytes; }
+uint32_t kd_tree_tries(const KdTreeDev* t) { return t->tries; }
 const double* kd_tree_root_bounds(const KdTreeDev* t) { return t->root_bounds; }
 const PtKdNode* kd_tree_nodes_device(const KdTreeDev* t) { return t->nodes.as<PtKdNode>(); }
 const uint32_t* kd_tree_items_device(const KdTreeDev* t) { return t->items.as<uint32_t>(); }

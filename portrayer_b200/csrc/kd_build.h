@@ -18,6 +18,8 @@ uint32_t kd_tree_item_count(const KdTreeDev* t);
 uint32_t kd_tree_depth(const KdTreeDev* t);
 uint32_t kd_tree_launches(const KdTreeDev* t);
 float kd_tree_device_ms(const KdTreeDev* t);
+uint64_t kd_tree_algorithmic_bytes(const KdTreeDev* t);
+uint32_t kd_tree_tries(const KdTreeDev* t);
 const double* kd_tree_root_bounds(const KdTreeDev* t);  // min xyz, max xyz
 const PtKdNode* kd_tree_nodes_device(const KdTreeDev* t);
 const uint32_t* kd_tree_items_device(const KdTreeDev* t);

@@ -727,6 +727,16 @@ __global__ void __launch_bounds__(kBlock) instance_bounds_kernel(const PtInstanc
     out[2 * (size_t)i + 1] = make_float4(fhi[0], fhi[1], fhi[2], 0.f);
 }
 
+// instance boxes in scene-tree leaf order (TlasLeaf reads them sequentially)
+__global__ void __launch_bounds__(kBlock) gather_leaf_boxes_kernel(const float4* __restrict__ inst_aabb, const uint32_t* __restrict__ items,
+                                                                  uint32_t n_items, float4* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_items) return;
+    const uint32_t inst = items[j];
+    out[2 * (size_t)j] = inst_aabb[2 * (size_t)inst];
+    out[2 * (size_t)j + 1] = inst_aabb[2 * (size_t)inst + 1];
+}
+
 // FP32 box of every triangle (object space), rounded outward and padded by 1e-5 of the triangle's largest
 // coordinate magnitude and extent: the per-triangle cull of Mesh folds (traverse.cuh mesh_fold).
 __global__ void __launch_bounds__(kBlock) triangle_bounds_kernel(const PtTriPos* __restrict__ tri_pos, uint32_t n, float4* __restrict__ out) {
@@ -838,6 +848,10 @@ void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bo
     if (sc.n_instances)
         instance_bounds_kernel<<<blocks_for(sc.n_instances), kBlock, 0, st>>>(sc.instances, sc.instance_trans, sc.n_instances,
                                                                             mesh_bounds_scratch, out);
+}
+
+void launch_gather_leaf_boxes(const float4* inst_aabb, const uint32_t* items, uint32_t n_items, float4* out, cudaStream_t st) {
+    if (n_items) gather_leaf_boxes_kernel<<<blocks_for(n_items), kBlock, 0, st>>>(inst_aabb, items, n_items, out);
 }
 
 // tri_aabb[n], l1[ceil(n / 32)], l2[ceil(n / 1024)]

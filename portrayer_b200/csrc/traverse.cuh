@@ -295,33 +295,6 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
     }
 }
 
-// leaf of a KDMesh tree: RayHit for [Triangle] with a shrinking clone of the range (ray.rs:50-63)
-template <bool ANY>
-struct BlasLeaf {
-    const uint32_t* __restrict__ items;
-    const PtTriPos* __restrict__ tris;
-    V3 o, d;
-    double t;
-    uint32_t tri;
-    uint32_t n_tests;
-    PT_D bool operator()(uint32_t first, uint32_t count, double s, double e) {
-        bool found = false;
-        for (uint32_t k = 0; k < count; ++k) {
-            const uint32_t idx = __ldg(items + first + k);
-            ++n_tests;
-            double tt;
-            if (triangle_t(tris + idx, o, d, s, e, tt, nullptr)) {
-                e = tt;
-                t = tt;
-                tri = idx;
-                found = true;
-                if (ANY) return true;
-            }
-        }
-        return found;
-    }
-};
-
 // ------------------------------------------------------------------ conservative FP32 cull
 // Before an instance is tested exactly (f64, object space) its padded world-space bounding box
 // (DScene::inst_aabb, built at upload by instance_bounds_kernel) is slab-tested in FP32.  The test
@@ -358,6 +331,37 @@ PT_D bool aabb_may_hit(const float4* __restrict__ bb, const RayF& r, double s, d
     const float sf = (float)s * 0.9999f, ef = (float)e * 1.0001f;  // s, e > 0
     return !(tn > tf) && !(tf < sf) && !(tn > ef);
 }
+
+// leaf of a KDMesh tree: RayHit for [Triangle] with a shrinking clone of the range (ray.rs:50-63).  A triangle whose
+// padded FP32 box (DScene::tri_aabb) the ray certainly misses inside [s, e) is rejected on the FP32 pipe; the others
+// get the exact f64 test — same accepted hits, same order.
+template <bool ANY>
+struct BlasLeaf {
+    const uint32_t* __restrict__ items;
+    const PtTriPos* __restrict__ tris;
+    const float4* __restrict__ boxes;
+    V3 o, d;
+    RayF rf;
+    double t;
+    uint32_t tri;
+    uint32_t n_tests;
+    PT_D bool operator()(uint32_t first, uint32_t count, double s, double e) {
+        bool found = false;
+        for (uint32_t k = 0; k < count; ++k) {
+            const uint32_t idx = __ldg(items + first + k);
+            ++n_tests;
+            double tt;
+            if (aabb_may_hit(boxes + 2 * (size_t)idx, rf, s, e) && triangle_t(tris + idx, o, d, s, e, tt, nullptr)) {
+                e = tt;
+                t = tt;
+                tri = idx;
+                found = true;
+                if (ANY) return true;
+            }
+        }
+        return found;
+    }
+};
 
 // Mesh::ray_hit's fold over EVERY triangle of the mesh in index order with a shrinking range (mesh.rs:157-167,
 // ray.rs:50-63), minus the triangles that certainly miss: every triangle has an FP32 box (DScene::tri_aabb), every
@@ -420,12 +424,8 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     }
     const PtMesh* mesh = sc.meshes + mesh_id;
     const uint32_t tri_first = __ldg(&mesh->tri_first);
-    if (prim == PT_PRIM_TRIANGLE) {
-        ++wc.triangle_tests;
-        return triangle_t(sc.tri_pos + tri_first, o, d, s, e, t, nullptr);
-    }
-    ++wc.bbox_gates;
-    if (!bbox_gate(mesh, o, d, s, e)) return false;
+    if (prim == PT_PRIM_TRIANGLE) return triangle_t(sc.tri_pos + tri_first, o, d, s, e, t, nullptr);
+    if (!bbox_gate(mesh, o, d, s, e)) return false;  // counted by the caller, like the Triangle test above
     if (prim == PT_PRIM_MESH) {  // fold over every triangle in index order, mesh.rs:157-167
         uint32_t n_tests = 0;
         const bool found = mesh_fold<ANY>(sc, tri_first, __ldg(&mesh->tri_count), o, d, s, e, t, sub, n_tests);
@@ -433,7 +433,8 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
         return found;
     }
     // KDMesh: KDTreeNode<Triangle>::ray_hit on a clone of the range (node.rs:33-51)
-    BlasLeaf<ANY> leaf{sc.blas_items + __ldg(&mesh->item_first), sc.tri_pos + tri_first, o, d, 0.0, 0, 0};
+    BlasLeaf<ANY> leaf{sc.blas_items + __ldg(&mesh->item_first), sc.tri_pos + tri_first, sc.tri_aabb + 2 * (size_t)tri_first, o, d,
+                       make_rayf(o, d), 0.0, 0, 0};
     const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), __ldg(&mesh->extent), o, d, s, e, blas_stack, leaf,
                              err, wc.kd_splits);
     wc.triangle_tests += leaf.n_tests;
@@ -441,7 +442,17 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     return hit;
 }
 
-// leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99)
+// leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99).
+//
+// Two phases per run of 32 candidates, so that the lanes of a warp do the same thing at the same time:
+//   1. every lane slab-tests the run's 32 padded boxes in FP32 (DScene::leaf_aabb: the instance boxes copied into leaf
+//      order, read sequentially) and keeps the survivors as a bit mask — a tight, branch-free loop;
+//   2. the survivors are tested exactly (f64, object space) in list order.
+// A one-phase loop (test a box, then maybe the primitive) makes the whole warp wait whenever ANY lane has a survivor:
+// with ~10 % survivors per lane that is almost every iteration, and ncu showed 8 of 32 lanes active on
+// graphics-castle (62 candidates per leaf).  The mask is built with the range as it was at the start of the run — a
+// superset of what the shrinking range would let through — and each survivor is culled again against the current
+// range before its f64 test, so the accepted hits and their order are unchanged.
 template <bool ANY>
 struct TlasLeaf {
     const DScene& sc;
@@ -453,26 +464,42 @@ struct TlasLeaf {
     WorkCounters& wc;
     PT_D bool operator()(uint32_t first, uint32_t count, double s, double e) {
         bool found = false;
-        for (uint32_t k = 0; k < count; ++k) {
-            const uint32_t inst = __ldg(sc.tlas_items + first + k);
-            ++wc.instance_tests;
-            wc.prim_flops += prim_flop_count(__ldg(&sc.instances[inst].prim));  // counting kernels only (dead code otherwise)
-            if (!aabb_may_hit(sc.inst_aabb + 2 * (size_t)inst, rf, s, e)) continue;
-            // FlatSceneNode::ray_cast: the ray in object space, direction NOT renormalised (flat_scene.rs:75, ray.rs:130-135)
-            const PtInstance* rec = sc.instances + inst;
-            double m[12];
-            load_doubles12(rec->invtrans, m);
-            const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&rec->prim));
-            const V3 lo = xf_point(m, o), ld = xf_dir(m, d);
-            double t;
-            uint32_t sub;
-            if (primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc)) {
-                e = t;  // flat_scene.rs:92
-                hit.t = t;
-                hit.inst = inst;
-                hit.sub = sub;
-                found = true;
-                if (ANY) return true;
+        const float4* __restrict__ boxes = sc.leaf_aabb + 2 * (size_t)first;
+        const uint32_t* __restrict__ items = sc.tlas_items + first;
+        for (uint32_t base = 0; base < count; base += 32u) {
+            const uint32_t n = min(32u, count - base);
+            uint32_t mask = 0u;
+            for (uint32_t j = 0; j < n; ++j) {
+                if (aabb_may_hit(boxes + 2 * (size_t)(base + j), rf, s, e)) mask |= 1u << j;
+                {   // counting kernels only (dead code otherwise): the reference's work for this candidate, culled or not
+                    const uint32_t prim = __ldg(&sc.instances[__ldg(items + base + j)].prim);
+                    ++wc.instance_tests;
+                    wc.prim_flops += prim_flop_count(prim);
+                    wc.bbox_gates += (prim == PT_PRIM_MESH || prim == PT_PRIM_KDMESH) ? 1u : 0u;  // mesh.rs:153, kdmesh.rs:67
+                    wc.triangle_tests += prim == PT_PRIM_TRIANGLE ? 1u : 0u;
+                }
+            }
+            while (mask) {
+                const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
+                mask &= mask - 1u;
+                if (found && !aabb_may_hit(boxes + 2 * (size_t)(base + j), rf, s, e)) continue;  // the range has shrunk since phase 1
+                const uint32_t inst = __ldg(items + base + j);
+                // FlatSceneNode::ray_cast: the ray in object space, direction NOT renormalised (flat_scene.rs:75, ray.rs:130-135)
+                const PtInstance* rec = sc.instances + inst;
+                double m[12];
+                load_doubles12(rec->invtrans, m);
+                const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&rec->prim));
+                const V3 lo = xf_point(m, o), ld = xf_dir(m, d);
+                double t;
+                uint32_t sub;
+                if (primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc)) {
+                    e = t;  // flat_scene.rs:92
+                    hit.t = t;
+                    hit.inst = inst;
+                    hit.sub = sub;
+                    found = true;
+                    if (ANY) return true;
+                }
             }
         }
         return found;

@@ -72,8 +72,14 @@ class KdTree:
     def build_stats(self) -> tuple[float, int]:
         """(device milliseconds, kernel launches) of the build"""
         ms, n = C.c_double(), C.c_uint32()
-        check(gpu.pt_kd_tree_build_stats(self._h, C.byref(ms), C.byref(n)))
+        check(gpu.pt_kd_tree_build_stats(self._h, C.byref(ms), C.byref(n), None))
         return ms.value, n.value
+
+    def algorithmic_bytes(self) -> int:
+        """bytes the build has to move at the least (members x passes): the numerator of its HBM roofline"""
+        b = C.c_uint64()
+        check(gpu.pt_kd_tree_build_stats(self._h, None, None, C.byref(b)))
+        return b.value
 
     def download(self) -> tuple[np.ndarray, np.ndarray]:
         nodes = np.empty(self.node_count, KD_NODE_DTYPE)
