@@ -307,13 +307,25 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    n_streams = max(1, min(args.streams, len(jobs)))
+    side_streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
+    all_streams = [stream] + [s_.cuda_stream for s_ in side_streams]
 
     def step(collect=None):
         """one pass over the workload, device-resident; returns device ms (torch events on the launch stream)"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for j in jobs:  # all frames of the step go onto the stream back to back; nothing waits for the device here
-            j.frame.enqueue(stream=stream)
+        # all frames of the step are enqueued before anything waits for the device, round-robin over n_streams CUDA
+        # streams: the frames are independent (own node pool, control block, __constant__ slot), and a 910x512 frame's
+        # kernels are only a few waves each, so the tail of one frame's launch overlaps the next frame's
+        for side in side_streams:
+            side.wait_event(e0)
+        for k, j in enumerate(jobs):
+            j.frame.enqueue(stream=all_streams[k % len(all_streams)])
+        for side in side_streams:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            torch.cuda.current_stream().wait_event(ev)
         for j in jobs:
             st = j.frame.finish()
             if collect is not None:
@@ -556,6 +568,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": wl["label"], "frames_per_step": len(jobs), "samples": samples, "rng": "hash", "seed": SEED,
                    "rays_per_step": rays_per_step, "ms_per_frame": total_ms / args.steps / len(jobs),
                    "l2": "flushed between timed steps (256 MB write)", "tile": "32x32 interleaved over ranks",
+                   "streams": n_streams,
                    "parallelism": f"tiles x{world}", "scene_broadcast_ms": scene_broadcast_ms,
                    "reference_panics_tolerated": panics},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(r[1].item()), "roofline": roofline, "roofline_fp64": roofline_fp64,
@@ -572,6 +585,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="configs1")
     ap.add_argument("--samples", type=int, default=0, help="samples per pixel at N=1 (default: the workload's)")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the frames of a step are spread over (1 = back to back on one)")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e and cpu_baseline legs (for runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

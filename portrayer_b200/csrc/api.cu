@@ -1371,7 +1371,10 @@ int pt_kd_build_device(const double* d_bounds, uint32_t n, const PtKdBuildConfig
     rc = ensure_init();
     if (rc != PT_OK) return rc;
     ptd::KdTreeDev* dev = nullptr;
-    const cudaError_t e = ptd::kd_build_device(d_bounds, n, *config, stream ? (cudaStream_t)stream : g_stream, &dev);
+    ptd::KdAllocator al;
+    al.alloc = [](size_t bytes, cudaError_t* err) { return g_dev.alloc(bytes, err); };
+    al.release = [](void* p) { g_dev.release(p); };
+    const cudaError_t e = ptd::kd_build_device(d_bounds, n, *config, al, stream ? (cudaStream_t)stream : g_stream, &dev);
     if (e == cudaErrorInvalidValue) return fail(PT_ERR_INVALID, "k-d tree does not fit 30-bit node / item indices");
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "k-d tree build failed: %s", cudaGetErrorString(e));
     *out = new PtKdTree{dev};

@@ -385,26 +385,29 @@ __global__ void __launch_bounds__(kB) scatter_kernel(EmitArgs a, const uint32_t*
 }
 
 // ------------------------------------------------------------------ host side
+// Device scratch and result buffers come from the caller's caching allocator (api.cu's arena: no cudaMalloc /
+// cudaFree — which synchronise the device — once a process has built a tree of a similar size).
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    const KdAllocator* al = nullptr;
     cudaError_t reserve(size_t bytes, bool keep, cudaStream_t st) {
         if (bytes <= cap) return cudaSuccess;
-        size_t want = std::max(bytes, cap + cap / 2);
-        void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, want);
-        if (e != cudaSuccess) return e;
+        const size_t want = std::max(bytes, cap * 2);
+        cudaError_t e = cudaSuccess;
+        void* q = al->alloc(want, &e);
+        if (!q) return e == cudaSuccess ? cudaErrorMemoryAllocation : e;
         if (keep && p && cap) {
             e = cudaMemcpyAsync(q, p, cap, cudaMemcpyDeviceToDevice, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         }
-        if (p) cudaFree(p);
+        if (p) al->release(p);
         p = q;
         cap = want;
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) al->release(p);
         p = nullptr;
         cap = 0;
     }
@@ -428,6 +431,7 @@ cudaError_t exclusive_scan(Load load, uint32_t n, DevBuf& tiles, unsigned long l
 }  // namespace
 
 struct KdTreeDev {
+    KdAllocator al{};
     DevBuf nodes, items;
     uint32_t n_nodes = 0, n_items = 0, depth = 0;
     double root_bounds[6] = {0, 0, 0, 0, 0, 0};
@@ -443,10 +447,19 @@ struct KdTreeDev {
         if (e_ != cudaSuccess) { err = e_; goto done; } \
     } while (0)
 
-cudaError_t kd_build_device(const double* d_bounds_aos, uint32_t n, const PtKdBuildConfig& cfg, cudaStream_t st, KdTreeDev** out) {
+cudaError_t kd_build_device(const double* d_bounds_aos, uint32_t n, const PtKdBuildConfig& cfg, const KdAllocator& al, cudaStream_t st,
+                            KdTreeDev** out) {
     cudaError_t err = cudaSuccess;
     KdTreeDev* tree = new KdTreeDev();
+    tree->al = al;
+    tree->nodes.al = tree->items.al = &tree->al;
     DevBuf soa, items[2], owner[2], seg[2], cls, item_pfx, node_pfx, leaf_pfx, tiles, klo, khi, plane, pmin, pmax, counts, status, scalars;
+    DevBuf* const all_scratch[] = {&soa, &items[0], &items[1], &owner[0], &owner[1], &seg[0], &seg[1], &cls, &item_pfx, &node_pfx,
+                                   &leaf_pfx, &tiles, &klo, &khi, &plane, &pmin, &pmax, &counts, &status, &scalars};
+    for (DevBuf* b : all_scratch) b->al = &tree->al;
+    // first guesses that spare the level loop most re-allocations: a level rarely holds more than ~2n members (shared
+    // members are duplicated) or more than n nodes; buffers still grow geometrically when a scene needs more
+    const size_t m_guess = std::max<size_t>(2 * (size_t)n, 1024), k_guess = std::max<size_t>(n, 1024);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t launches = 0;
     // pinned scalars read back once per level: [0] node scan total, [1] leaf scan total, [2..7] root bound keys
@@ -472,10 +485,19 @@ cudaError_t kd_build_device(const double* d_bounds_aos, uint32_t n, const PtKdBu
 
     KD_TRY(soa.reserve((size_t)n * 6 * 8, false, st));
     transpose_bounds_kernel<<<blocks(n), kB, 0, st>>>(d_bounds_aos, n, soa.as<double>());
-    KD_TRY(items[0].reserve((size_t)n * 4, false, st));
-    KD_TRY(owner[0].reserve((size_t)n * 4, false, st));
+    for (int b = 0; b < 2; ++b) {
+        KD_TRY(items[b].reserve(m_guess * 4, false, st));
+        KD_TRY(owner[b].reserve(m_guess * 4, false, st));
+        KD_TRY(seg[b].reserve((k_guess + 1) * 4, false, st));
+    }
+    KD_TRY(cls.reserve(m_guess, false, st));
+    KD_TRY(item_pfx.reserve((m_guess + 1) * 8, false, st));
+    for (DevBuf* b : {&klo, &khi, &plane, &pmin, &pmax, &node_pfx, &leaf_pfx}) KD_TRY(b->reserve((k_guess + 1) * 8, false, st));
+    KD_TRY(counts.reserve(k_guess * 16, false, st));
+    KD_TRY(status.reserve(k_guess, false, st));
+    KD_TRY(tree->nodes.reserve(2 * k_guess * sizeof(PtKdNode), false, st));
+    KD_TRY(tree->items.reserve(m_guess * 4, false, st));
     iota_kernel<<<blocks(n), kB, 0, st>>>(items[0].as<uint32_t>(), owner[0].as<uint32_t>(), n);
-    KD_TRY(seg[0].reserve(2 * 4, false, st));
     {
         const uint32_t seg0[2] = {0u, n};
         KD_TRY(cudaMemcpyAsync(seg[0].p, seg0, sizeof seg0, cudaMemcpyHostToDevice, st));
@@ -615,9 +637,7 @@ done:
         if (err == cudaSuccess) cudaEventElapsedTime(&tree->device_ms, ev0, ev1);
     }
     tree->launches = launches;
-    for (DevBuf* b : {&soa, &items[0], &items[1], &owner[0], &owner[1], &seg[0], &seg[1], &cls, &item_pfx, &node_pfx, &leaf_pfx, &tiles,
-                      &klo, &khi, &plane, &pmin, &pmax, &counts, &status, &scalars})
-        b->release();
+    for (DevBuf* b : all_scratch) b->release();
     if (h_scalars) cudaFreeHost(h_scalars);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);

@@ -10,8 +10,15 @@ namespace ptd {
 
 struct KdTreeDev;
 
+// the caller's device allocator (stream-ordered reuse is fine: everything runs on the one stream given to the build)
+struct KdAllocator {
+    void* (*alloc)(size_t bytes, cudaError_t* err) = nullptr;
+    void (*release)(void* p) = nullptr;
+};
+
 // d_bounds_aos: n x {min x, y, z, max x, y, z} in device memory.  Blocking (one small read-back per tree level).
-cudaError_t kd_build_device(const double* d_bounds_aos, uint32_t n, const PtKdBuildConfig& cfg, cudaStream_t st, KdTreeDev** out);
+cudaError_t kd_build_device(const double* d_bounds_aos, uint32_t n, const PtKdBuildConfig& cfg, const KdAllocator& al, cudaStream_t st,
+                            KdTreeDev** out);
 void kd_tree_release(KdTreeDev* t);
 uint32_t kd_tree_node_count(const KdTreeDev* t);
 uint32_t kd_tree_item_count(const KdTreeDev* t);
