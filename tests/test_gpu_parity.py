@@ -45,6 +45,25 @@ def test_textured_scenes(gpu_ready, name):
     parity.assert_parity(_report(name, samples=1, rng="fixed"))
 
 
+# the other example programs of the reference (examples/*.rs beyond BASELINE.json's configs): deep hierarchies,
+# instancing through shared nodes, a Triangle as a primitive, flat + smooth + textured meshes, a dielectric glossy mesh,
+# constant backgrounds.  Native size for the small ones, half size where a linear 5 804-triangle Mesh makes the oracle slow.
+@pytest.mark.parametrize("name,samples,rng,scale", [
+    ("simple", 1, "fixed", 1), ("hier", 1, "fixed", 1), ("instance", 1, "fixed", 1), ("nonhier2", 1, "fixed", 1),
+    ("macho-cows", 1, "fixed", 1), ("simple-cows", 1, "fixed", 1), ("single-triangle", 1, "fixed", 1),
+    ("smooth-shading", 1, "hash", 2), ("primitives-simple", 1, "fixed", 1), ("four-shapes", 1, "fixed", 2),
+    ("antialiasing", 4, "hash", 1), ("fish", 2, "hash", 2), ("graphics-poster", 2, "hash", 1),
+    ("cube-mapping", 1, "fixed", 1), ("entering-the-mirror-dimension", 2, "hash", 2), ("transmission-refraction", 2, "hash", 2),
+])
+def test_more_example_scenes(gpu_ready, name, samples, rng, scale):
+    if name in ("fish", "cube-mapping", "transmission-refraction") and not has_reference_assets():
+        pytest.skip("reference textures not synced")
+    scene = pt.Scene.example(name)
+    rep = _report(name, samples=samples, rng=rng, size=(scene.width // scale, scene.height // scale))
+    parity.assert_parity(rep)
+    assert rep["hit_t_bit_identical"]
+
+
 # configs[2]: kd-tree traversal stress, at reduced size so the oracle finishes in seconds
 @pytest.mark.parametrize("kd_depth", [10, 18])
 def test_big_scene(gpu_ready, kd_depth):

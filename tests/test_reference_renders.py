@@ -15,11 +15,13 @@ from conftest import has_reference_assets
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_renders")
 FACTOR = 7
-TEXTURED = {"normal-mapping", "normal-mapping-left", "normal-mapping-right", "water-glass"}
+TEXTURED = {"normal-mapping", "normal-mapping-left", "normal-mapping-right", "water-glass", "transmission-refraction"}
 # (example, samples, max mean-abs-error in LSB, min PSNR dB).  big-scene's random scene needs the re-implemented
 # rand-0.7 StdRng (host/rand07.hpp) to reproduce upstream's object placement: agreement there pins it.
 CASES = [
     ("primitives", 4, 0.8, 45.0),
+    ("primitives-simple", 4, 0.8, 45.0),
+    ("smooth-shading", 2, 0.8, 44.0),
     ("glossy-reflection", 8, 0.8, 45.0),
     ("soft-shadows", 8, 0.8, 45.0),
     ("normal-mapping", 4, 1.0, 44.0),
@@ -31,6 +33,10 @@ CASES = [
     # rings in that patch (about 1.7 % of the image); everywhere else agreement is as tight as the other scenes.
     ("water-glass", 8, 1.2, 33.0),
     ("big-scene", 1, 0.8, 44.0),
+    # mirrors (reflectivity 1.0 / 0.9), with_children, three-angle rotated_xzy
+    ("entering-the-mirror-dimension", 4, 0.8, 44.0),
+    # dielectric glass pane + water cube around textured KDMesh fish, normal-mapped cubes
+    ("transmission-refraction", 4, 0.8, 46.0),
 ]
 
 

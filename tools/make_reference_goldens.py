@@ -19,11 +19,15 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 FACTOR = 7
 # reference render -> example scene program of the host mirror
 RENDERS = {
+    "01a_primitives-simple.png": "primitives-simple",
     "01b_primitives.png": "primitives",
+    "02_smooth-shading.png": "smooth-shading",
     "04a_normal-mapping.png": "normal-mapping",
     "04b_normal-mapping-left.png": "normal-mapping-left",
     "04c_normal-mapping-right.png": "normal-mapping-right",
     "06a_water-glass.png": "water-glass",
+    "06b_transmission-refraction.png": "transmission-refraction",
+    "entering-the-mirror-dimension.png": "entering-the-mirror-dimension",
     "07_glossy-reflection.png": "glossy-reflection",
     "08_soft-shadows.png": "soft-shadows",
     "09a_kdtree.png": "big-scene",
