@@ -73,6 +73,11 @@ def main():
     if os.path.exists(mp):
         with open(mp) as f:
             peak, src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "traffic_kd_build.json")
+    if os.path.exists(tp) and args.n == 1_000_000 and args.kind == "instances":  # the capture is of exactly this build
+        with open(tp) as f:
+            traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for k, v in json.load(f).items() if not k.startswith("_"))
     best = min(dev_ms)
     achieved = abytes / (best * 1e-3) / 1e9
     line = {
@@ -88,7 +93,7 @@ def main():
                                                    "sample": "the whole build, once (C++ mirror of KDLeaf::partitioned)"},
         "identical_to_host_tree": same,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "algorithmic_bytes": int(abytes), "peak_source": src, "traffic": None},
+                     "algorithmic_bytes": int(abytes), "peak_source": src, "traffic": traffic},
     }
     print(json.dumps(line))
 

@@ -2,6 +2,7 @@
 """Summarise ncu output into the small text files kept under profiles/.
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv          > profiles/rNN_launches.txt
+    python tools/ncu_summary.py traffic  gpurun_out/launches.csv "how"    > profiles/traffic.json
     python tools/ncu_summary.py report   gpurun_out/prof.ncu-rep          > profiles/rNN_kernels.txt
     python tools/ncu_summary.py stalls   gpurun_out/prof.ncu-rep [kernel] > profiles/rNN_stalls.txt
 
@@ -50,8 +51,11 @@ def launches(path: str) -> None:
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     hdr = rows[0]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    mi = hdr.index("Metric Name")
     agg = collections.defaultdict(lambda: [0, 0.0])
     for r in rows[1:]:
+        if r[mi] != "gpu__time_duration.sum":
+            continue
         try:
             v = float(r[vi].replace(",", ""))
         except ValueError:
@@ -65,6 +69,34 @@ def launches(path: str) -> None:
     print(f"{'kernel':58s} {'n':>5s} {'total_us':>10s} {'share':>7s} {'avg_us':>8s}")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{k[:58]:58s} {v[0]:5d} {v[1]:10.1f} {v[1] / tot:7.3f} {v[1] / v[0]:8.1f}")
+
+
+def traffic(path: str, source: str) -> None:
+    """dram__bytes_read/write.sum per launch, averaged per kernel, as the JSON bench.py reads (profiles/traffic.json)."""
+    import json
+
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi, ui, mi, ii = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Metric Unit", "Metric Name", "ID"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
+    per = collections.defaultdict(lambda: collections.defaultdict(float))
+    ids = collections.defaultdict(set)
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+        except ValueError:
+            continue
+        name = r[ki].split("(")[0].replace("void ", "").replace("ptd::<unnamed>::", "").split("<")[0]
+        per[name][r[mi]] += v
+        ids[name].add(r[ii])
+    out = {}
+    for name, m in sorted(per.items()):
+        n = max(len(ids[name]), 1)
+        rd, wr = m.get("dram__bytes_read.sum", 0.0) / n, m.get("dram__bytes_write.sum", 0.0) / n
+        out[name] = {"launches": n, "dram_bytes_per_launch": rd + wr, "dram_read_bytes_per_launch": rd,
+                     "dram_write_bytes_per_launch": wr, "avg_us_under_ncu": m.get("gpu__time_duration.sum", 0.0) / n}
+    out["_source"] = source
+    print(json.dumps(out, indent=1))
 
 
 def report(rep: str) -> None:
@@ -128,6 +160,8 @@ def main() -> None:
     mode = sys.argv[1]
     if mode == "launches":
         launches(sys.argv[2])
+    elif mode == "traffic":
+        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else sys.argv[2])
     elif mode == "report":
         report(sys.argv[2])
     elif mode == "stalls":
