@@ -29,6 +29,8 @@ import time
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
+# stdout carries exactly ONE JSON line (rank 0): NCCL's version banner / debug lines go to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 sys.path.insert(0, REPO)
 
 WORKLOADS = {
@@ -307,6 +309,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    same_geometry = len({(j.w, j.h) for j in jobs}) == 1
     n_streams = max(1, min(args.streams, len(jobs)))
     side_streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
     all_streams = [stream] + [s_.cuda_stream for s_ in side_streams]
@@ -330,8 +333,14 @@ def run_ours(args, rank, world, local_rank):
             st = j.frame.finish()
             if collect is not None:
                 collect.append(st)
-            if world > 1:
-                ptd.gather_image_device(j.rgb_dev, j.params, dst=0)  # NCCL gather + device-side un-tiling on rank 0
+        if world > 1:
+            # the exchange step: NCCL gather of every rank's RGB8 tiles + device-side un-tiling on rank 0, one call
+            # for all frames of the step that share a geometry (the exchange is latency-bound)
+            if same_geometry:
+                ptd.gather_images_device([j.rgb_dev for j in jobs], jobs[0].params, dst=0)
+            else:
+                for j in jobs:
+                    ptd.gather_image_device(j.rgb_dev, j.params, dst=0)
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)

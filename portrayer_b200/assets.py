@@ -55,7 +55,10 @@ def _decode(path: str) -> np.ndarray | None:
 def load_texture(path: str) -> np.ndarray:
     """RGB8 array for an example's texture path ("assets/earth.jpg")."""
     name = os.path.basename(path)
-    img = _decode(os.path.join(ASSETS_DIR, name))
+    rel = path.split("assets/", 1)[1] if "assets/" in path else name  # "assets/robot-alarm-clock/wallpaper.jpg" keeps its sub-directory
+    img = _decode(os.path.join(ASSETS_DIR, rel))
+    if img is None:
+        img = _decode(os.path.join(ASSETS_DIR, name))
     if img is None and name == "earth_cube.png":
         earth = _decode(os.path.join(ASSETS_DIR, "earth.jpg"))
         if earth is not None:  # montage -mode concatenate -tile 4x3 (make-cube-map.sh:12)

@@ -34,7 +34,7 @@ constexpr int kBlock = 128;
 #define PT_EXTEND_MIN_BLOCKS 4
 #endif
 #ifndef PT_SHADOW_MIN_BLOCKS
-#define PT_SHADOW_MIN_BLOCKS 5
+#define PT_SHADOW_MIN_BLOCKS 4
 #endif
 #ifndef PT_SHADE_MIN_BLOCKS
 #define PT_SHADE_MIN_BLOCKS 5

@@ -42,9 +42,12 @@ def _worker(rank, world, port, out_path):
     index = ptd.owned_pixel_index(params)
     local = torch.from_numpy(res.rgb.reshape(-1, 3)[index.astype(np.int64)].copy())
     image = ptd.gather_image(local, params, dst=0)
+    # several frames of one geometry in one exchange (what a benchmark step does): frame 1 = frame 0 inverted
+    multi = ptd.gather_images_device([local, 255 - local], params, dst=0)
     if rank == 0:
         full = oracle.render(blob, ref_scene.camera(w, h), make_params(w, h, 2, "hash", 7, bg_mode=bg_mode), bg, threads=2)
-        np.save(out_path, np.stack([image, full.rgb]))
+        multi = multi.numpy().reshape(2, h, w, 3)
+        np.save(out_path, np.stack([image, full.rgb, multi[0], 255 - multi[1]]))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -52,8 +55,9 @@ def _worker(rank, world, port, out_path):
 def test_two_rank_tiles_gather_to_rank0(tmp_path):
     out = str(tmp_path / "img.npy")
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    gathered, full = np.load(out)
+    gathered, full, multi0, multi1 = np.load(out)
     assert np.array_equal(gathered, full), "the gathered 2-rank image must be bit-identical to the 1-rank image"
+    assert np.array_equal(multi0, full) and np.array_equal(multi1, full), "the batched multi-frame exchange must agree"
 
 
 def test_tile_partition_is_a_partition():

@@ -54,9 +54,10 @@ def test_textured_scenes(gpu_ready, name):
     ("smooth-shading", 1, "hash", 2), ("primitives-simple", 1, "fixed", 1), ("four-shapes", 1, "fixed", 2),
     ("antialiasing", 4, "hash", 1), ("fish", 2, "hash", 2), ("graphics-poster", 2, "hash", 1),
     ("cube-mapping", 1, "fixed", 1), ("entering-the-mirror-dimension", 2, "hash", 2), ("transmission-refraction", 2, "hash", 2),
+    ("robot-alarm-clock", 2, "hash", 4),
 ])
 def test_more_example_scenes(gpu_ready, name, samples, rng, scale):
-    if name in ("fish", "cube-mapping", "transmission-refraction") and not has_reference_assets():
+    if name in ("fish", "cube-mapping", "transmission-refraction", "robot-alarm-clock") and not has_reference_assets():
         pytest.skip("reference textures not synced")
     scene = pt.Scene.example(name)
     rep = _report(name, samples=samples, rng=rng, size=(scene.width // scale, scene.height // scale))

@@ -28,6 +28,8 @@ RENDERS = {
     "06a_water-glass.png": "water-glass",
     "06b_transmission-refraction.png": "transmission-refraction",
     "entering-the-mirror-dimension.png": "entering-the-mirror-dimension",
+    # upstream published four colour variants; the example source as shipped is the green one
+    "10_robot-alarm-clock_green.png": "robot-alarm-clock",
     "07_glossy-reflection.png": "glossy-reflection",
     "08_soft-shadows.png": "soft-shadows",
     "09a_kdtree.png": "big-scene",
