@@ -80,8 +80,42 @@ ExampleScene mesh_equivalence(bool kd) {
     return ex;
 }
 
+// Degenerate inputs the render loop must survive exactly like the reference:
+//   edge-empty        no geometry at all: every ray returns the background (ray.rs:146); one light that is never used
+//   edge-no-lights    geometry but no lights: ambient only, no shadow rays (material.rs:149 iterates an empty Vec)
+//   edge-degenerate   a zero-area triangle, a plane scaled to zero width and a sphere scaled flat: the reference's
+//                     arithmetic produces NaN / inf there (0 / 0 in Cramer's rule, singular inverses) and every
+//                     comparison with them is false, i.e. "no hit" — the device must agree bit for bit
+ExampleScene edge_scene(int which) {
+    auto mat = Arc(Material{.diffuse = {0.8, 0.3, 0.2}, .specular = {0.3, 0.3, 0.3}, .shininess = 25.0});
+    std::vector<NodeRef> nodes;
+    std::vector<Light> lights = {Light{.position = {3.0, 5.0, 8.0}, .color = {0.9, 0.9, 0.9}}};
+    if (which == 1) {
+        nodes.push_back(SceneNode::from(Geometry(Sphere{}, mat)).scaled(1.5).into());
+        nodes.push_back(SceneNode::from(Geometry(Cube{}, mat)).scaled({6.0, 0.2, 6.0}).translated({0.0, -1.6, 0.0}).into());
+        lights.clear();
+    } else if (which == 2) {
+        nodes.push_back(SceneNode::from(Geometry(Triangle::flat({-1.0, 0.0, 0.0}, {1.0, 0.0, 0.0}, {3.0, 0.0, 0.0}), mat)).into());
+        nodes.push_back(SceneNode::from(Geometry(Plane{}, mat)).scaled({0.0, 1.0, 4.0}).rotated_x(Radians::from_degrees(90.0)).into());
+        nodes.push_back(SceneNode::from(Geometry(Sphere{}, mat)).scaled({1.0, 0.0, 1.0}).translated({0.0, 1.0, 0.0}).into());
+        nodes.push_back(SceneNode::from(Geometry(Cylinder{}, mat)).scaled(0.8).translated({-2.0, 0.0, 0.0}).into());
+        nodes.push_back(SceneNode::from(Geometry(Cone{}, mat)).scaled(0.8).translated({2.0, 0.0, 0.0}).into());
+    }
+    ExampleScene ex;
+    ex.name = which == 0 ? "edge-empty" : which == 1 ? "edge-no-lights" : "edge-degenerate";
+    ex.scene = HierScene{.root = SceneNode::from(std::move(nodes)).into(), .lights = lights, .ambient = {0.3, 0.3, 0.3}};
+    ex.cam = CameraSettings{.eye = {0.0, 1.0, 9.0}, .center = {0.0, 0.0, 0.0}, .up = Vec3::up(), .fovy = Radians::from_degrees(40.0)};
+    ex.width = 203;  // neither a multiple of the 32x32 tile nor of the 8x4 warp block
+    ex.height = 117;
+    ex.background = sky_gradient;
+    return ex;
+}
+
 }  // namespace
 
+PORTRAYER_EXAMPLE(edge_empty, "edge-empty") { return edge_scene(0); }
+PORTRAYER_EXAMPLE(edge_no_lights, "edge-no-lights") { return edge_scene(1); }
+PORTRAYER_EXAMPLE(edge_degenerate, "edge-degenerate") { return edge_scene(2); }
 PORTRAYER_EXAMPLE(kat_edge_case, "kat-edge-case") { return edge_case(false); }
 PORTRAYER_EXAMPLE(kat_edge_case_flipped, "kat-edge-case-flipped") { return edge_case(true); }
 PORTRAYER_EXAMPLE(kat_mesh_eq_mesh, "kat-mesh-equivalence-mesh") { return mesh_equivalence(false); }

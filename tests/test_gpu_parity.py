@@ -65,6 +65,26 @@ def test_more_example_scenes(gpu_ready, name, samples, rng, scale):
     assert rep["hit_t_bit_identical"]
 
 
+# degenerate inputs (host/examples/kats.cpp): no geometry at all, no lights, zero-area / zero-scale primitives whose
+# arithmetic runs through NaN and inf; at an image size that is neither a multiple of the 32x32 tile nor of the 8x4
+# warp block, and at 1x1 and 1-pixel-wide images
+@pytest.mark.parametrize("name", ["edge-empty", "edge-no-lights", "edge-degenerate"])
+@pytest.mark.parametrize("size", [None, (1, 1), (37, 1), (1, 53)])
+def test_degenerate_scenes_and_ragged_images(gpu_ready, name, size):
+    scene = pt.Scene.example(name)
+    kw = dict(samples=3, rng="hash", size=size or (scene.width, scene.height))
+    img, stats = parity.render_gpu(scene, **kw)
+    ref = parity.render_oracle(scene, **kw)
+    assert ref.rc == 0
+    rep = parity.compare(img, ref, name)
+    assert rep["rgb_exact"] == 1.0 and rep["hit_id_mismatches"] == 0 and rep["hit_t_bit_identical"], rep
+    assert stats.rays == ref.stats.rays
+    if name == "edge-empty":
+        assert stats.rays_shadow == 0 and np.all(img.hit_id[..., 0] == 0xFFFFFFFF)
+    if name == "edge-no-lights":
+        assert stats.rays_shadow == 0 and stats.rays_primary > 0
+
+
 # configs[2]: kd-tree traversal stress, at reduced size so the oracle finishes in seconds
 @pytest.mark.parametrize("kd_depth", [10, 18])
 def test_big_scene(gpu_ready, kd_depth):
