@@ -443,6 +443,40 @@ int pt_kd_tree_build_stats(const PtKdTree* tree, double* device_ms_out, uint32_t
  * Its items must be flat-instance indices of that scene. */
 int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree);
 
+/* ---- scene flattening on the device (feeds the tree build) ----
+ * Replaces FlatScene::from (src/flat_scene.rs:18-46) + FlatSceneNode::new (:101-108) + FlatSceneNode::bounds (:63-69).
+ * The glue hands over the scene graph as it is — one PtHierNode per distinct SceneNode (a node shared through
+ * Arc<SceneNode> appears once and is referenced from several child lists: instancing), child lists concatenated in
+ * `children`, one PtGeometryRec per Geometry — and gets back, in the reference's breadth-first instance order, the
+ * PtInstance / PtInstanceTrans records of PtSceneDesc and the world bounds of every instance (the input of
+ * pt_kd_build_device), all resident in HBM. */
+typedef struct PtHierNode {
+    double trans[16];     /* SceneNode::trans(), row-major 4x4 (scene.rs:35,151-205) */
+    uint32_t geometry;    /* index into geometries, 0xFFFFFFFF = none (scene.rs:24) */
+    uint32_t first_child; /* this node's children are children[first_child .. first_child + child_count) */
+    uint32_t child_count;
+    uint32_t reserved;
+} PtHierNode; /* 144 bytes */
+typedef struct PtGeometryRec {
+    double bounds[6];     /* primitive.bounds(): min x, y, z, max x, y, z in object space (primitive.rs:63-77) */
+    uint32_t prim;        /* PtPrimType */
+    uint32_t mesh;        /* as PtInstance.mesh */
+    uint32_t material;    /* as PtInstance.material */
+    uint32_t reserved;
+} PtGeometryRec; /* 64 bytes */
+typedef struct PtFlatScene PtFlatScene; /* opaque: the flat instances in device memory */
+int pt_flatten(const PtHierNode* nodes, uint32_t n_nodes, const uint32_t* children, uint32_t n_children, uint32_t root,
+               const PtGeometryRec* geometries, uint32_t n_geometries, PtFlatScene** out);
+void pt_flat_free(PtFlatScene* flat);
+uint32_t pt_flat_instance_count(const PtFlatScene* flat);
+const double* pt_flat_bounds_device(const PtFlatScene* flat); /* n x 6 doubles, device memory */
+/* copy the records to host arrays of pt_flat_instance_count entries (any may be NULL); bounds_out: n x 6 */
+int pt_flat_download(const PtFlatScene* flat, PtInstance* instances_out, PtInstanceTrans* trans_out, double* bounds_out);
+int pt_flat_build_stats(const PtFlatScene* flat, double* device_ms_out, uint32_t* launches_out);
+/* Make `flat` the instances and `tree` (built over pt_flat_bounds_device) the scene tree of an uploaded scene whose
+ * blob carried the meshes, materials, lights and textures (device-to-device copies; both can be freed afterwards). */
+int pt_scene_set_instances(PtScene* scene, const PtFlatScene* flat, const PtKdTree* tree);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,6 +176,13 @@ GPU_SYMBOLS = {
     "pt_kd_tree_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pt_kd_tree_build_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "pt_scene_set_tlas": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_flatten": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "pt_flat_free": (None, [C.c_void_p]),
+    "pt_flat_instance_count": (C.c_uint32, [C.c_void_p]),
+    "pt_flat_bounds_device": (C.c_void_p, [C.c_void_p]),
+    "pt_flat_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pt_flat_build_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
+    "pt_scene_set_instances": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 for _name, (_res, _args) in GPU_SYMBOLS.items():
     _fn = getattr(gpu, _name)  # AttributeError here = the library does not export what the header declares
@@ -203,8 +210,11 @@ HOST_SYMBOLS = {
     "pth_camera": (None, [C.c_void_p, C.c_double, C.c_double, C.POINTER(PtCamera)]),
     "pth_background": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "pth_prepare_seconds": (C.c_double, [C.c_void_p]),
+    "pth_flatten_seconds": (C.c_double, [C.c_void_p]),
     "pth_scene_item_count": (C.c_uint64, [C.c_void_p]),
     "pth_scene_item_bounds": (None, [C.c_void_p, C.c_void_p]),
+    "pth_scene_hierarchy_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "pth_scene_hierarchy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pth_kd_build": (C.c_void_p, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32]),
     "pth_kd_tree_free": (None, [C.c_void_p]),
     "pth_kd_tree_node_count": (C.c_uint64, [C.c_void_p]),

@@ -24,6 +24,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "flatten.h"
 #include "kd_build.h"
 #include "kernels.h"
 #include "portrayer_gpu.h"
@@ -182,10 +183,15 @@ struct PtScene {
     uint64_t h2d_bytes = 0;                 // bytes the upload copied to the device
     PtKdNode* d_own_tlas_nodes = nullptr;   // pt_scene_set_tlas: a device-built scene tree replacing the blob's
     uint32_t* d_own_tlas_items = nullptr;
+    PtInstance* d_own_instances = nullptr;  // pt_scene_set_instances: device-flattened instances replacing the blob's
+    PtInstanceTrans* d_own_instance_trans = nullptr;
 };
 
 struct PtKdTree {
     ptd::KdTreeDev* dev = nullptr;
+};
+struct PtFlatScene {
+    ptd::FlatSceneDev* dev = nullptr;
 };
 
 struct PtFrame {
@@ -277,8 +283,9 @@ void fill_view(PtScene* s) {
     unsigned char* b = s->d_records;
     v.tlas_nodes = s->d_own_tlas_nodes ? s->d_own_tlas_nodes : reinterpret_cast<const PtKdNode*>(b + h.off_tlas_nodes);
     v.tlas_items = s->d_own_tlas_items ? s->d_own_tlas_items : reinterpret_cast<const uint32_t*>(b + h.off_tlas_items);
-    v.instances = reinterpret_cast<const PtInstance*>(b + h.off_instances);
-    v.instance_trans = reinterpret_cast<const PtInstanceTrans*>(b + h.off_instance_trans);
+    v.instances = s->d_own_instances ? s->d_own_instances : reinterpret_cast<const PtInstance*>(b + h.off_instances);
+    v.instance_trans = s->d_own_instance_trans ? s->d_own_instance_trans
+                                               : reinterpret_cast<const PtInstanceTrans*>(b + h.off_instance_trans);
     v.meshes = reinterpret_cast<const PtMesh*>(b + h.off_meshes);
     v.blas_nodes = reinterpret_cast<const PtKdNode*>(b + h.off_blas_nodes);
     v.blas_items = reinterpret_cast<const uint32_t*>(b + h.off_blas_items);
@@ -315,6 +322,8 @@ void free_scene(PtScene* s) {
     g_dev.release(s->d_leaf_aabb);
     g_dev.release(s->d_own_tlas_nodes);
     g_dev.release(s->d_own_tlas_items);
+    g_dev.release(s->d_own_instances);
+    g_dev.release(s->d_own_instance_trans);
     g_dev.release(s->d_records);
     delete s;
 }
@@ -1472,6 +1481,103 @@ int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree) {
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     fill_view(scene);
     return PT_OK;
+}
+
+
+// ------------------------------------------------------------------- scene flattening (flatten.cu)
+int pt_flatten(const PtHierNode* nodes, uint32_t n_nodes, const uint32_t* children, uint32_t n_children, uint32_t root,
+               const PtGeometryRec* geometries, uint32_t n_geometries, PtFlatScene** out) {
+    if (!out || !nodes || n_nodes == 0 || root >= n_nodes || (n_children && !children) || (n_geometries && !geometries))
+        return fail(PT_ERR_INVALID, "null or empty argument");
+    for (uint32_t i = 0; i < n_nodes; ++i) {  // the device trusts these indices
+        const PtHierNode& n = nodes[i];
+        if ((uint64_t)n.first_child + n.child_count > n_children) return fail(PT_ERR_INVALID, "node %u: child range outside the child list", i);
+        if (n.geometry != 0xFFFFFFFFu && n.geometry >= n_geometries) return fail(PT_ERR_INVALID, "node %u: geometry index out of range", i);
+    }
+    for (uint32_t i = 0; i < n_children; ++i)
+        if (children[i] >= n_nodes) return fail(PT_ERR_INVALID, "child %u: node index out of range", i);
+    Lock lock(g_mu);
+    int rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    cudaError_t e = cudaSuccess;
+    const size_t nb = (size_t)n_nodes * sizeof(PtHierNode), cb = std::max<size_t>((size_t)n_children * 4, 4),
+                 gb = std::max<size_t>((size_t)n_geometries * sizeof(PtGeometryRec), 8);
+    PtHierNode* d_nodes = static_cast<PtHierNode*>(g_dev.alloc(nb, &e));
+    uint32_t* d_children = d_nodes ? static_cast<uint32_t*>(g_dev.alloc(cb, &e)) : nullptr;
+    PtGeometryRec* d_geoms = d_children ? static_cast<PtGeometryRec*>(g_dev.alloc(gb, &e)) : nullptr;
+    auto cleanup = [&] { g_dev.release(d_nodes); g_dev.release(d_children); g_dev.release(d_geoms); };
+    if (!d_geoms) { cleanup(); return fail(PT_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(d_nodes, nodes, nb, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess && n_children) e = cudaMemcpyAsync(d_children, children, (size_t)n_children * 4, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess && n_geometries)
+        e = cudaMemcpyAsync(d_geoms, geometries, (size_t)n_geometries * sizeof(PtGeometryRec), cudaMemcpyHostToDevice, g_stream);
+    if (e != cudaSuccess) { cleanup(); return fail(PT_ERR_CUDA, "hierarchy upload failed: %s", cudaGetErrorString(e)); }
+    ptd::KdAllocator al;
+    al.alloc = [](size_t bytes, cudaError_t* err) { return g_dev.alloc(bytes, err); };
+    al.release = [](void* p) { g_dev.release(p); };
+    ptd::FlatSceneDev* dev = nullptr;
+    e = ptd::flatten_device(d_nodes, n_nodes, d_children, n_children, root, d_geoms, /*max_levels=*/n_nodes, al, g_stream, &dev);
+    cleanup();
+    if (e == cudaErrorInvalidValue) return fail(PT_ERR_INVALID, "the hierarchy has a cycle or expands to more than 2^31 instances");
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "flatten failed: %s", cudaGetErrorString(e));
+    *out = new PtFlatScene{dev};
+    return PT_OK;
+}
+
+void pt_flat_free(PtFlatScene* flat) {
+    if (!flat) return;
+    Lock lock(g_mu);
+    ptd::flat_release(flat->dev);
+    delete flat;
+}
+uint32_t pt_flat_instance_count(const PtFlatScene* flat) { return flat ? ptd::flat_instance_count(flat->dev) : 0; }
+const double* pt_flat_bounds_device(const PtFlatScene* flat) { return flat ? ptd::flat_bounds_device(flat->dev) : nullptr; }
+
+int pt_flat_download(const PtFlatScene* flat, PtInstance* instances_out, PtInstanceTrans* trans_out, double* bounds_out) {
+    if (!flat) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
+    const size_t n = ptd::flat_instance_count(flat->dev);
+    if (!n) return PT_OK;
+    if (instances_out) CUDA_TRY(cudaMemcpy(instances_out, ptd::flat_instances_device(flat->dev), n * sizeof(PtInstance), cudaMemcpyDeviceToHost));
+    if (trans_out) CUDA_TRY(cudaMemcpy(trans_out, ptd::flat_trans_device(flat->dev), n * sizeof(PtInstanceTrans), cudaMemcpyDeviceToHost));
+    if (bounds_out) CUDA_TRY(cudaMemcpy(bounds_out, ptd::flat_bounds_device(flat->dev), n * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    return PT_OK;
+}
+
+int pt_flat_build_stats(const PtFlatScene* flat, double* device_ms_out, uint32_t* launches_out) {
+    if (!flat) return fail(PT_ERR_INVALID, "null argument");
+    if (device_ms_out) *device_ms_out = ptd::flat_device_ms(flat->dev);
+    if (launches_out) *launches_out = ptd::flat_launches(flat->dev);
+    return PT_OK;
+}
+
+int pt_scene_set_instances(PtScene* scene, const PtFlatScene* flat, const PtKdTree* tree) {
+    if (!scene || !flat || !tree) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
+    const uint32_t n = ptd::flat_instance_count(flat->dev);
+    cudaError_t e = cudaSuccess;
+    PtInstance* d_inst = static_cast<PtInstance*>(g_dev.alloc(std::max<size_t>(n, 1) * sizeof(PtInstance), &e));
+    PtInstanceTrans* d_tr = d_inst ? static_cast<PtInstanceTrans*>(g_dev.alloc(std::max<size_t>(n, 1) * sizeof(PtInstanceTrans), &e)) : nullptr;
+    if (!d_tr) { g_dev.release(d_inst); return fail(PT_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    if (n) {
+        e = cudaMemcpyAsync(d_inst, ptd::flat_instances_device(flat->dev), (size_t)n * sizeof(PtInstance), cudaMemcpyDeviceToDevice, g_stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_tr, ptd::flat_trans_device(flat->dev), (size_t)n * sizeof(PtInstanceTrans), cudaMemcpyDeviceToDevice, g_stream);
+    }
+    if (e != cudaSuccess) { g_dev.release(d_inst); g_dev.release(d_tr); return fail(PT_ERR_CUDA, "instance copy failed: %s", cudaGetErrorString(e)); }
+    g_dev.release(scene->d_own_instances);
+    g_dev.release(scene->d_own_instance_trans);
+    scene->d_own_instances = d_inst;
+    scene->d_own_instance_trans = d_tr;
+    scene->h.n_instances = n;
+    // the FP32 instance boxes depend on the instances: rebuild them, then splice the tree in (which re-gathers the leaf boxes)
+    g_dev.release(scene->d_aabb);
+    g_dev.release(scene->d_leaf_aabb);
+    g_dev.release(scene->d_tri_aabb);
+    scene->d_aabb = scene->d_leaf_aabb = scene->d_tri_aabb = nullptr;
+    int rc = build_instance_bounds(scene);
+    if (rc != PT_OK) return rc;
+    return pt_scene_set_tlas(scene, tree);
 }
 
 }  // extern "C"

@@ -15,7 +15,9 @@ struct PthScene {
     ExampleScene example;
     std::vector<uint8_t> blob;
     double prepare_seconds = 0.0;
+    double flatten_seconds = 0.0;     // FlatScene::from alone (matrix products, inverses)
     std::vector<double> item_bounds;  // n x 6: FlatSceneNode::bounds of every flat instance
+    std::unique_ptr<HierarchyExport> hierarchy;  // built on demand
 };
 
 struct PthKdTree {
@@ -44,6 +46,7 @@ PthScene* finish(ExampleScene ex, int64_t kd_depth, int linear_tlas) {
         keep_bounds(ex.prebuilt->nodes);
     } else {
         FlatScene flat = FlatScene::from(ex.scene);
+        out->flatten_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (linear_tlas) {
             // one unpartitioned leaf: the flat_scene feature's linear fold (flat_scene.rs:71-99, ray.rs:87-99)
             KDTreeScene kd = KDTreeScene::from(std::move(flat), 0);
@@ -132,9 +135,34 @@ PthScene* pth_synthetic_triangles_build(uint64_t n_triangles, uint64_t seed, int
 }
 void pth_scene_free(PthScene* s) { delete s; }
 
+double pth_flatten_seconds(const PthScene* s) { return s->flatten_seconds; }
 uint64_t pth_scene_item_count(const PthScene* s) { return s->item_bounds.size() / 6; }
 void pth_scene_item_bounds(const PthScene* s, double* out) {
     std::copy(s->item_bounds.begin(), s->item_bounds.end(), out);
+}
+
+static const HierarchyExport* hierarchy_of(const PthScene* s) {
+    if (s->example.prebuilt) return nullptr;
+    auto* m = const_cast<PthScene*>(s);
+    if (!m->hierarchy) m->hierarchy = std::make_unique<HierarchyExport>(export_hierarchy(s->example.scene));
+    return m->hierarchy.get();
+}
+int pth_scene_hierarchy_sizes(const PthScene* s, uint32_t* n_nodes, uint32_t* n_children, uint32_t* n_geometries, uint32_t* root) {
+    const HierarchyExport* h = hierarchy_of(s);
+    if (!h) return -1;
+    *n_nodes = static_cast<uint32_t>(h->nodes.size());
+    *n_children = static_cast<uint32_t>(h->children.size());
+    *n_geometries = static_cast<uint32_t>(h->geometries.size());
+    *root = h->root;
+    return 0;
+}
+int pth_scene_hierarchy(const PthScene* s, PtHierNode* nodes_out, uint32_t* children_out, PtGeometryRec* geometries_out) {
+    const HierarchyExport* h = hierarchy_of(s);
+    if (!h) return -1;
+    std::copy(h->nodes.begin(), h->nodes.end(), nodes_out);
+    std::copy(h->children.begin(), h->children.end(), children_out);
+    std::copy(h->geometries.begin(), h->geometries.end(), geometries_out);
+    return 0;
 }
 
 PthKdTree* pth_kd_build(const double* bounds, uint64_t n, uint32_t max_depth, uint32_t target_max_nodes,

@@ -46,8 +46,15 @@ double pth_prepare_seconds(const PthScene* s);
 
 /* world-space bounds of the scene tree's items = FlatSceneNode::bounds of every flat instance (flat_scene.rs:63-69),
  * n x {min x, y, z, max x, y, z}: the input of the scene-tree build (kdscene.rs:24-28) */
+/* seconds spent in FlatScene::from alone (flat_scene.rs:18-46: products, inverses) */
+double pth_flatten_seconds(const PthScene* s);
 uint64_t pth_scene_item_count(const PthScene* s);
 void pth_scene_item_bounds(const PthScene* s, double* out);
+
+/* the scene GRAPH in the records pt_flatten takes (include/portrayer_gpu.h): sizes, then the arrays.
+ * Returns -1 for the hand-built known-answer scenes, which have no graph. */
+int pth_scene_hierarchy_sizes(const PthScene* s, uint32_t* n_nodes, uint32_t* n_children, uint32_t* n_geometries, uint32_t* root);
+int pth_scene_hierarchy(const PthScene* s, PtHierNode* nodes_out, uint32_t* children_out, PtGeometryRec* geometries_out);
 
 /* KDLeaf::partitioned on the host (the C++ mirror of leaf.rs:89-231) over n items given by their bounds,
  * serialised like the boundary's PtKdNode / leaf-item records: the comparison arm of pt_kd_build. */

@@ -260,6 +260,74 @@ std::vector<uint8_t> pack_scene(const std::vector<FlatSceneNode>& nodes, const K
     return blob;
 }
 
+HierarchyExport export_hierarchy(const HierScene& scene) {
+    // ids exactly as Builder::add_instance hands them out: walk the flat instances in order
+    FlatScene flat = FlatScene::from(scene);
+    std::map<const void*, uint32_t> material_ids;
+    std::map<std::pair<const void*, int>, uint32_t> mesh_ids;
+    auto mesh_key = [](const Primitive& p) {
+        const void* key_ptr = p.kind == PrimKind::Mesh       ? static_cast<const void*>(p.mesh.get())
+                              : p.kind == PrimKind::KDMesh   ? static_cast<const void*>(p.kdmesh.get())
+                                                             : static_cast<const void*>(p.triangle.get());
+        const int key_tag = p.kind == PrimKind::Mesh ? (p.shading == Shading::Smooth ? 1 : 0) : 2;
+        return std::make_pair(key_ptr, key_tag);
+    };
+    auto is_mesh_kind = [](PrimKind k) { return k == PrimKind::Triangle || k == PrimKind::Mesh || k == PrimKind::KDMesh; };
+    for (const FlatSceneNode& n : flat.root) {
+        const Primitive& p = n.geometry.primitive;
+        if (is_mesh_kind(p.kind)) mesh_ids.emplace(mesh_key(p), static_cast<uint32_t>(mesh_ids.size()));
+        material_ids.emplace(n.geometry.material.get(), static_cast<uint32_t>(material_ids.size()));
+    }
+
+    HierarchyExport out;
+    std::map<const SceneNode*, uint32_t> node_ids;
+    std::deque<const SceneNode*> queue;
+    auto id_of = [&](const SceneNode* n) {
+        auto it = node_ids.find(n);
+        if (it != node_ids.end()) return it->second;
+        const uint32_t id = static_cast<uint32_t>(out.nodes.size());
+        node_ids[n] = id;
+        out.nodes.push_back(PtHierNode{});
+        queue.push_back(n);
+        return id;
+    };
+    out.root = id_of(scene.root.get());
+    while (!queue.empty()) {
+        const SceneNode* n = queue.front();
+        queue.pop_front();
+        PtHierNode rec{};
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) rec.trans[r * 4 + c] = n->trans().m[r][c];
+        rec.geometry = 0xFFFFFFFFu;
+        if (n->geometry()) {
+            const Geometry& g = *n->geometry();
+            PtGeometryRec gr{};
+            const BoundingBox b = g.primitive.bounds();
+            gr.bounds[0] = b.min().x; gr.bounds[1] = b.min().y; gr.bounds[2] = b.min().z;
+            gr.bounds[3] = b.max().x; gr.bounds[4] = b.max().y; gr.bounds[5] = b.max().z;
+            switch (g.primitive.kind) {
+                case PrimKind::Sphere: gr.prim = PT_PRIM_SPHERE; break;
+                case PrimKind::Plane: gr.prim = PT_PRIM_PLANE; break;
+                case PrimKind::Cube: gr.prim = PT_PRIM_CUBE; break;
+                case PrimKind::Cylinder: gr.prim = PT_PRIM_CYLINDER; break;
+                case PrimKind::Cone: gr.prim = PT_PRIM_CONE; break;
+                case PrimKind::Triangle: gr.prim = PT_PRIM_TRIANGLE; break;
+                case PrimKind::Mesh: gr.prim = PT_PRIM_MESH; break;
+                case PrimKind::KDMesh: gr.prim = PT_PRIM_KDMESH; break;
+            }
+            gr.mesh = is_mesh_kind(g.primitive.kind) ? mesh_ids.at(mesh_key(g.primitive)) : 0xFFFFFFFFu;
+            gr.material = material_ids.at(g.material.get());
+            rec.geometry = static_cast<uint32_t>(out.geometries.size());
+            out.geometries.push_back(gr);
+        }
+        rec.first_child = static_cast<uint32_t>(out.children.size());
+        rec.child_count = static_cast<uint32_t>(n->children().size());
+        for (const NodeRef& c : n->children()) out.children.push_back(id_of(c.get()));
+        out.nodes[node_ids[n]] = rec;
+    }
+    return out;
+}
+
 std::vector<uint8_t> pack_scene(const KDTreeScene& scene) {
     return pack_scene(scene.nodes, *scene.root, scene.lights, scene.ambient);
 }

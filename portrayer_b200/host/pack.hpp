@@ -22,6 +22,18 @@ std::vector<uint8_t> pack_scene(const KDTreeScene& scene);
 std::vector<uint8_t> pack_scene(const std::vector<FlatSceneNode>& nodes, const KDIndexTree& root,
                                 const std::vector<Light>& lights, Rgb ambient);
 
+// The scene GRAPH as the boundary's pt_flatten takes it (include/portrayer_gpu.h): one PtHierNode per distinct
+// SceneNode (shared nodes once: instancing), concatenated child lists, one PtGeometryRec per node that carries
+// geometry.  mesh / material ids are the ones pack_scene assigns (first appearance in flat-instance order), so the
+// device-flattened records can be compared with, and used next to, a packed blob of the same scene.
+struct HierarchyExport {
+    std::vector<PtHierNode> nodes;
+    std::vector<uint32_t> children;
+    std::vector<PtGeometryRec> geometries;
+    uint32_t root = 0;
+};
+HierarchyExport export_hierarchy(const HierScene& scene);
+
 // Breadth-first serialisation of a tree into the PtKdNode / leaf-item records of the boundary (front child, then back
 // child; leaf lists in visiting order).  Returns the depth of the deepest node (root = 0).
 uint32_t serialise_kd_tree(const KDIndexTree& root, std::vector<PtKdNode>& nodes_out, std::vector<uint32_t>& items_out);

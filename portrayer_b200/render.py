@@ -69,6 +69,10 @@ class DeviceScene:
         """make a device-built tree (kdbuild.KdTree) the scene tree of this uploaded scene"""
         check(gpu.pt_scene_set_tlas(self._h, tree.handle))
 
+    def set_instances(self, flat, tree) -> None:
+        """make device-flattened instances (flatten.FlatScene) and a tree built over their bounds the scene's"""
+        check(gpu.pt_scene_set_instances(self._h, flat.handle, tree.handle))
+
     @property
     def uploaded_bytes(self) -> int:
         """host -> device bytes of the upload (records + textures that were not already resident)"""

@@ -47,6 +47,31 @@ def main():
     scene_s = time.perf_counter() - t0
     cfg = kdbuild.config(depth)
 
+    # the step before: FlatScene::from on the device (pt_flatten) vs the host mirror, same scene graph
+    flat_line = None
+    if args.kind == "instances":
+        from portrayer_b200 import flatten
+
+        hier = flatten.hierarchy_of(scene)
+        flatten.FlatScene.build(hier).close()  # warm-up
+        f_ms, f_e2e = [], []
+        for _ in range(args.reps):
+            t0 = time.perf_counter()
+            fl = flatten.FlatScene.build(hier)
+            f_e2e.append((time.perf_counter() - t0) * 1e3)
+            f_ms.append(fl.build_stats()[0])
+            n_inst = fl.instance_count
+            _inst, _trans, f_bounds = fl.download() if _ == 0 else (None, None, None)
+            if _ == 0:
+                same_bounds = bool(np.array_equal(f_bounds, bounds))
+            fl.close()
+        fbytes = len(hier.nodes) * 144 + len(hier.children) * 4 + n_inst * (64 + 128 + 96 + 48)
+        flat_line = {"device_ms": min(f_ms), "e2e_ms": min(f_e2e), "host_ms": _ffi.host.pth_flatten_seconds(scene._h) * 1e3,
+                     "instances": int(n_inst), "bounds_identical_to_host": same_bounds,
+                     "algorithmic_bytes": int(fbytes), "achieved_gbs": fbytes / (min(f_ms) * 1e-3) / 1e9,
+                     "path": "pt_flatten (host graph in: H2D of nodes / children / geometries, level-parallel flatten); "
+                             "e2e = wall clock of the call"}
+
     kdbuild.KdTree.build(bounds, cfg).close()  # warm-up: allocator, module load
     dev_ms, e2e_ms = [], []
     tree = None
@@ -92,6 +117,7 @@ def main():
         "cpu_baseline": None if host is None else {"value": host.seconds * 1e3, "unit": "ms", "cores": 1, "kind": "port",
                                                    "sample": "the whole build, once (C++ mirror of KDLeaf::partitioned)"},
         "identical_to_host_tree": same,
+        "flatten": flat_line,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "algorithmic_bytes": int(abytes), "peak_source": src, "traffic": traffic},
     }
