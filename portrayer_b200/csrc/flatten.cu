@@ -94,22 +94,35 @@ struct EntryLoad {  // entry -> (has geometry, number of children)
     }
 };
 
-// phase 2 of a level: instance records of the entries that carry geometry, and the entries of the next level
-__global__ void __launch_bounds__(kB) level_emit_kernel(const PtHierNode* __restrict__ nodes, const uint32_t* __restrict__ children,
+// the entries of the next level, one thread per CHILD (a root with 10^6 children is one entry): entry j belongs to
+// the parent whose child range [pfx[i], pfx[i + 1]) holds j — remaining.push_back((total_trans, child)), flat_scene.rs:40-42
+__global__ void __launch_bounds__(kB) level_children_kernel(const PtHierNode* __restrict__ nodes, const uint32_t* __restrict__ children,
+                                                            const uint32_t* __restrict__ entry_node, const unsigned long long* __restrict__ pfx,
+                                                            uint32_t n_entries, uint32_t n_next, uint32_t* __restrict__ next_node,
+                                                            uint32_t* __restrict__ next_parent) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_next) return;
+    uint32_t lo = 0, hi = n_entries;  // last i with child_base(i) <= j
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)(pfx[mid] & 0xFFFFFFFFull) <= j) lo = mid;
+        else hi = mid;
+    }
+    const PtHierNode& node = nodes[entry_node[lo]];
+    next_node[j] = children[node.first_child + (j - (uint32_t)(pfx[lo] & 0xFFFFFFFFull))];
+    next_parent[j] = lo;
+}
+
+// phase 2 of a level: instance records of the entries that carry geometry
+__global__ void __launch_bounds__(kB) level_emit_kernel(const PtHierNode* __restrict__ nodes,
                                                         const PtGeometryRec* __restrict__ geoms, const uint32_t* __restrict__ entry_node,
                                                         const Mat4d* __restrict__ total, const unsigned long long* __restrict__ pfx,
                                                         uint32_t n_entries, uint32_t instance_base, PtInstance* __restrict__ instances,
-                                                        PtInstanceTrans* __restrict__ inst_trans, double* __restrict__ bounds,
-                                                        uint32_t* __restrict__ next_node, uint32_t* __restrict__ next_parent) {
+                                                        PtInstanceTrans* __restrict__ inst_trans, double* __restrict__ bounds) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_entries) return;
     const PtHierNode& node = nodes[entry_node[i]];
     const unsigned long long p = pfx[i];
-    const uint32_t child_base = (uint32_t)(p & 0xFFFFFFFFull);
-    for (uint32_t c = 0; c < node.child_count; ++c) {  // remaining.push_back((total_trans, child)), flat_scene.rs:40-42
-        next_node[child_base + c] = children[node.first_child + c];
-        next_parent[child_base + c] = i;
-    }
     if (node.geometry == 0xFFFFFFFFu) return;
     const uint32_t slot = instance_base + (uint32_t)(p >> 32);
     const PtGeometryRec& g = geoms[node.geometry];
@@ -216,12 +229,17 @@ cudaError_t flatten_device(const PtHierNode* d_nodes, uint32_t n_nodes, const ui
         FL_TRY(flat->bounds.reserve((size_t)(n_inst + level_instances) * 6 * sizeof(double), true, st));
         FL_TRY(entry_node[cur ^ 1].reserve(std::max<size_t>(n_next, 1) * 4, false, st));
         FL_TRY(entry_parent[cur ^ 1].reserve(std::max<size_t>(n_next, 1) * 4, false, st));
-        level_emit_kernel<<<blocks(n_entries), kB, 0, st>>>(d_nodes, d_children, d_geoms, entry_node[cur].as<uint32_t>(),
-                                                            total[cur].as<Mat4d>(), pfx.as<unsigned long long>(), n_entries, n_inst,
+        level_emit_kernel<<<blocks(n_entries), kB, 0, st>>>(d_nodes, d_geoms, entry_node[cur].as<uint32_t>(), total[cur].as<Mat4d>(),
+                                                            pfx.as<unsigned long long>(), n_entries, n_inst,
                                                             flat->instances.as<PtInstance>(), flat->inst_trans.as<PtInstanceTrans>(),
-                                                            flat->bounds.as<double>(), entry_node[cur ^ 1].as<uint32_t>(),
-                                                            entry_parent[cur ^ 1].as<uint32_t>());
+                                                            flat->bounds.as<double>());
         ++launches;
+        if (n_next) {
+            level_children_kernel<<<blocks(n_next), kB, 0, st>>>(d_nodes, d_children, entry_node[cur].as<uint32_t>(),
+                                                                 pfx.as<unsigned long long>(), n_entries, (uint32_t)n_next,
+                                                                 entry_node[cur ^ 1].as<uint32_t>(), entry_parent[cur ^ 1].as<uint32_t>());
+            ++launches;
+        }
         FL_TRY(cudaGetLastError());
         n_inst += level_instances;
         if (n_next == 0) break;
