@@ -297,6 +297,7 @@ void fill_view(PtScene* s) {
     v.textures = s->d_textures;
     v.inst_aabb = s->d_aabb;
     v.leaf_aabb = s->d_leaf_aabb;
+    v.leaf_grp_aabb = s->d_leaf_aabb ? s->d_leaf_aabb + 2 * (size_t)s->h.n_tlas_items : nullptr;
     v.tri_aabb = s->d_tri_aabb;
     v.tri_aabb_l1 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1 : nullptr;
     v.tri_aabb_l2 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2 : nullptr;
@@ -401,6 +402,9 @@ int bind_textures(PtScene* s, const PtTexture* tex, const unsigned char* texel_s
     return PT_OK;
 }
 
+// boxes behind DScene::leaf_aabb + leaf_grp_aabb: one per leaf position, one per aligned run of 8 positions
+size_t leaf_box_count(uint32_t n_items) { return std::max<size_t>((size_t)n_items + ((size_t)n_items + 7) / 8, 1); }
+
 // instance boxes for the FP32 cull, computed on the device from the uploaded records
 int build_instance_bounds(PtScene* s) {
     const uint32_t n = s->h.n_instances;
@@ -418,7 +422,7 @@ int build_instance_bounds(PtScene* s) {
         s->d_tri_aabb = static_cast<float4*>(g_dev.alloc((size_t)(nt + n1 + n2) * 2 * sizeof(float4), &e));
         if (!s->d_tri_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "triangle bounds allocation failed: %s", cudaGetErrorString(e)); }
     }
-    s->d_leaf_aabb = static_cast<float4*>(g_dev.alloc(std::max<size_t>(s->h.n_tlas_items, 1) * 2 * sizeof(float4), &e));
+    s->d_leaf_aabb = static_cast<float4*>(g_dev.alloc(leaf_box_count(s->h.n_tlas_items) * 2 * sizeof(float4), &e));
     if (!s->d_leaf_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e)); }
     fill_view(s);
     launch_instance_bounds(s->view, s->h.n_meshes, scratch, s->d_aabb, g_stream);
@@ -1473,7 +1477,7 @@ int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree) {
     scene->h.tlas_depth = ptd::kd_tree_depth(tree->dev);
     scene->h.n_tlas_nodes = nn;
     scene->h.n_tlas_items = ni;
-    float4* d_leaf = static_cast<float4*>(g_dev.alloc(std::max<size_t>(ni, 1) * 2 * sizeof(float4), &e));
+    float4* d_leaf = static_cast<float4*>(g_dev.alloc(leaf_box_count(ni) * 2 * sizeof(float4), &e));
     if (!d_leaf) return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e));
     g_dev.release(scene->d_leaf_aabb);
     scene->d_leaf_aabb = d_leaf;

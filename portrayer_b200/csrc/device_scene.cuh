@@ -33,6 +33,7 @@ struct DScene {
     const double* gamma_lut;  // [256] pow(i / 255, 2.2) computed once on the device (ImageTexture::at, texture.rs:162-168)
     const float4* inst_aabb;  // [2 * n_instances] padded world-space box of every instance (lo, hi), FP32, rounded outward
     const float4* leaf_aabb;  // [2 * n_tlas_items] inst_aabb gathered into scene-tree leaf order: leaf_aabb[j] = inst_aabb[tlas_items[j]]
+    const float4* leaf_grp_aabb;  // [2 * ceil(n_tlas_items / 8)] union of leaf_aabb over every aligned run of 8 leaf positions
     // padded object-space FP32 box of every triangle, of every aligned run of 32 and of 1024 triangles (Mesh fold cull)
     const float4* tri_aabb;
     const float4* tri_aabb_l1;

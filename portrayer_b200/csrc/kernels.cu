@@ -767,14 +767,14 @@ __global__ void __launch_bounds__(kBlock) triangle_bounds_kernel(const PtTriPos*
     out[2 * (size_t)k + 1] = make_float4(fhi[0], fhi[1], fhi[2], 0.f);
 }
 
-// union of every aligned run of 32 boxes of `in` (n boxes) -> out[ceil(n / 32)]
-__global__ void __launch_bounds__(kBlock) group_bounds_kernel(const float4* __restrict__ in, uint32_t n, float4* __restrict__ out) {
+// union of every aligned run of `run` boxes of `in` (n boxes) -> out[ceil(n / run)]
+__global__ void __launch_bounds__(kBlock) group_bounds_kernel(const float4* __restrict__ in, uint32_t n, uint32_t run, float4* __restrict__ out) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_groups = (n + 31u) / 32u;
+    const uint32_t n_groups = (n + run - 1u) / run;
     if (g >= n_groups) return;
     float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
-    const uint32_t end = min(n, (g + 1u) * 32u);
-    for (uint32_t k = g * 32u; k < end; ++k) {
+    const uint32_t end = min(n, (g + 1u) * run);
+    for (uint32_t k = g * run; k < end; ++k) {
         const float4 a = in[2 * (size_t)k], b = in[2 * (size_t)k + 1];
         lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
         hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
@@ -850,8 +850,11 @@ void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bo
                                                                             mesh_bounds_scratch, out);
 }
 
+// out: n_items leaf-ordered boxes followed by ceil(n_items / 8) run boxes
 void launch_gather_leaf_boxes(const float4* inst_aabb, const uint32_t* items, uint32_t n_items, float4* out, cudaStream_t st) {
-    if (n_items) gather_leaf_boxes_kernel<<<blocks_for(n_items), kBlock, 0, st>>>(inst_aabb, items, n_items, out);
+    if (!n_items) return;
+    gather_leaf_boxes_kernel<<<blocks_for(n_items), kBlock, 0, st>>>(inst_aabb, items, n_items, out);
+    group_bounds_kernel<<<blocks_for((n_items + 7u) / 8u), kBlock, 0, st>>>(out, n_items, 8u, out + 2 * (size_t)n_items);
 }
 
 // tri_aabb[n], l1[ceil(n / 32)], l2[ceil(n / 1024)]
@@ -859,8 +862,8 @@ void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aab
     if (!n) return;
     const uint32_t n1 = (n + 31u) / 32u, n2 = (n1 + 31u) / 32u;
     triangle_bounds_kernel<<<blocks_for(n), kBlock, 0, st>>>(tri_pos, n, tri_aabb);
-    group_bounds_kernel<<<blocks_for(n1), kBlock, 0, st>>>(tri_aabb, n, l1);
-    group_bounds_kernel<<<blocks_for(n2), kBlock, 0, st>>>(l1, n1, l2);
+    group_bounds_kernel<<<blocks_for(n1), kBlock, 0, st>>>(tri_aabb, n, 32u, l1);
+    group_bounds_kernel<<<blocks_for(n2), kBlock, 0, st>>>(l1, n1, 32u, l2);
 }
 
 cudaError_t upload_state(int slot, const FrameState& state, cudaStream_t st) {

@@ -14,7 +14,8 @@ void launch_gamma_lut(double* lut256, cudaStream_t st);
 // upload time: padded FP32 world boxes of all instances (mesh_bounds_scratch: n_meshes * 6 doubles)
 void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bounds_scratch, float4* out, cudaStream_t st);
 
-// upload time: the instance boxes gathered into scene-tree leaf order (out: 2 * n_items float4)
+// upload time: the instance boxes gathered into scene-tree leaf order + the union box of every aligned run of 8 of
+// them (out: 2 * (n_items + ceil(n_items / 8)) float4)
 void launch_gather_leaf_boxes(const float4* inst_aabb, const uint32_t* items, uint32_t n_items, float4* out, cudaStream_t st);
 // upload time: padded FP32 object-space boxes of all triangles + of every aligned run of 32 / 1024 of them
 void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, float4* l1, float4* l2, cudaStream_t st);
