@@ -55,9 +55,12 @@ def test_textured_scenes(gpu_ready, name):
     ("antialiasing", 4, "hash", 1), ("fish", 2, "hash", 2), ("graphics-poster", 2, "hash", 1),
     ("cube-mapping", 1, "fixed", 1), ("entering-the-mirror-dimension", 2, "hash", 2), ("transmission-refraction", 2, "hash", 2),
     ("robot-alarm-clock", 2, "hash", 4),
+    # the last two of the reference's 28 examples: two area lights + 8 linear Meshes (3 uses of monkey.obj, one a flat
+    # dielectric), a cube-mapped texture on a Cube, glass ball; 5 KDMeshes (one instanced 3x), glossy dielectric lake
+    ("monkeys-making-monkeys", 2, "hash", 6), ("graphics-temple", 2, "hash", 1),
 ])
 def test_more_example_scenes(gpu_ready, name, samples, rng, scale):
-    if name in ("fish", "cube-mapping", "transmission-refraction", "robot-alarm-clock") and not has_reference_assets():
+    if name in ("fish", "cube-mapping", "transmission-refraction", "robot-alarm-clock", "monkeys-making-monkeys", "graphics-temple") and not has_reference_assets():
         pytest.skip("reference textures not synced")
     scene = pt.Scene.example(name)
     rep = _report(name, samples=samples, rng=rng, size=(scene.width // scale, scene.height // scale))

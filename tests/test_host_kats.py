@@ -29,3 +29,35 @@ def test_every_reference_example_used_by_the_configs_builds(native_libraries):
     for name in sorted(need):
         sc = pt.Scene.example(name)
         assert sc.header.n_instances > 0 and sc.header.n_tlas_nodes > 0 and sc.width > 0
+
+
+# "every examples/*.rs renders unchanged" -> every one of the 28 has a scene program here
+REFERENCE_EXAMPLES = [
+    "antialiasing", "big-scene", "cube-mapping", "entering-the-mirror-dimension", "fish", "four-shapes", "glossy-reflection",
+    "graphics-castle", "graphics-poster", "graphics-temple", "hier", "instance", "macho-cows", "monkeys-making-monkeys", "nonhier",
+    "nonhier2", "normal-mapping", "primitives-simple", "primitives", "robot-alarm-clock", "simple-cows", "simple", "single-triangle",
+    "smooth-shading", "soft-shadows", "texture-mapping", "transmission-refraction", "water-glass",
+]
+
+
+def test_all_28_reference_examples_are_registered(native_libraries):
+    import portrayer_b200 as pt
+
+    assert len(REFERENCE_EXAMPLES) == 28
+    missing = set(REFERENCE_EXAMPLES) - set(pt.example_names())
+    assert not missing, missing
+
+
+def test_last_two_examples_build_with_the_expected_instance_counts(native_libraries):
+    """examples/monkeys-making-monkeys.rs: 3 + 3 + 5 + 5 + 6 + 1 + 3 geometry nodes; examples/graphics-temple.rs: 1 + 1 + 2 + 0
+    (its unfinished maze floor emits nothing) + (16 columns x 5 + ceiling + 5 idol cubes) + (ceiling + 3 puppets) + 3."""
+    import portrayer_b200 as pt
+    from conftest import has_reference_assets
+    import pytest
+
+    if not has_reference_assets():
+        pytest.skip("reference meshes not synced (tools/sync_assets.py)")
+    sc = pt.Scene.example("monkeys-making-monkeys")
+    assert (sc.width, sc.height, sc.header.n_instances, sc.header.n_lights) == (1920, 1080, 26, 2)
+    sc = pt.Scene.example("graphics-temple")
+    assert (sc.width, sc.height, sc.header.n_instances, sc.header.n_lights) == (533, 300, 97, 1)
