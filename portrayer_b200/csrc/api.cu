@@ -178,6 +178,7 @@ struct PtScene {
     float4* d_leaf_aabb = nullptr;          // d_aabb gathered into scene-tree leaf order
     float4* d_tri_aabb = nullptr;           // padded FP32 object box per triangle + per run of 32 / 1024 (one allocation)
     uint32_t tri_aabb_l1 = 0, tri_aabb_l2 = 0;  // offsets (in boxes) of the two group levels inside d_tri_aabb
+    uint32_t tri_aabb_leaf = 0;                 // offset (in boxes) of the KDMesh leaf-ordered copy inside d_tri_aabb
     std::vector<uint64_t> resident_keys;    // textures held in the residency cache (refs to drop)
     std::vector<uint8_t*> private_texels;   // unkeyed textures owned by this scene
     uint64_t h2d_bytes = 0;                 // bytes the upload copied to the device
@@ -301,6 +302,7 @@ void fill_view(PtScene* s) {
     v.tri_aabb = s->d_tri_aabb;
     v.tri_aabb_l1 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1 : nullptr;
     v.tri_aabb_l2 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2 : nullptr;
+    v.blas_leaf_aabb = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_leaf : nullptr;
     v.gamma_lut = g_gamma_lut;
     v.ambient[0] = h.ambient[0]; v.ambient[1] = h.ambient[1]; v.ambient[2] = h.ambient[2];
     v.tlas_extent = h.tlas_extent;
@@ -419,7 +421,8 @@ int build_instance_bounds(PtScene* s) {
         const uint32_t n1 = (nt + 31u) / 32u, n2 = (n1 + 31u) / 32u;
         s->tri_aabb_l1 = nt;
         s->tri_aabb_l2 = nt + n1;
-        s->d_tri_aabb = static_cast<float4*>(g_dev.alloc((size_t)(nt + n1 + n2) * 2 * sizeof(float4), &e));
+        s->tri_aabb_leaf = nt + n1 + n2;
+        s->d_tri_aabb = static_cast<float4*>(g_dev.alloc(((size_t)nt + n1 + n2 + s->h.n_blas_items) * 2 * sizeof(float4), &e));
         if (!s->d_tri_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "triangle bounds allocation failed: %s", cudaGetErrorString(e)); }
     }
     s->d_leaf_aabb = static_cast<float4*>(g_dev.alloc(leaf_box_count(s->h.n_tlas_items) * 2 * sizeof(float4), &e));
@@ -429,6 +432,9 @@ int build_instance_bounds(PtScene* s) {
     launch_gather_leaf_boxes(s->d_aabb, s->view.tlas_items, s->h.n_tlas_items, s->d_leaf_aabb, g_stream);
     if (nt) launch_triangle_bounds(s->view.tri_pos, nt, s->d_tri_aabb, s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1,
                                    s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2, g_stream);
+    if (nt && s->h.n_blas_items)
+        launch_gather_blas_leaf_boxes(s->view.meshes, s->h.n_meshes, s->view.blas_items, s->d_tri_aabb,
+                                      s->d_tri_aabb + 2 * (size_t)s->tri_aabb_leaf, s->h.n_blas_items, g_stream);
     g_dev.release(scratch);  // stream-ordered reuse: later users of the block run after this kernel on g_stream
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "instance bounds kernel failed: %s", cudaGetErrorString(e));

@@ -38,6 +38,7 @@ struct DScene {
     const float4* tri_aabb;
     const float4* tri_aabb_l1;
     const float4* tri_aabb_l2;
+    const float4* blas_leaf_aabb;  // [2 * n_blas_items] tri_aabb gathered into KDMesh leaf-item order (BlasLeaf reads it sequentially)
     double ambient[3];
     double tlas_extent;
     uint32_t n_lights;

@@ -737,6 +737,22 @@ __global__ void __launch_bounds__(kBlock) gather_leaf_boxes_kernel(const float4*
     out[2 * (size_t)j + 1] = inst_aabb[2 * (size_t)inst + 1];
 }
 
+// triangle boxes in KDMesh leaf-item order (BlasLeaf reads them sequentially): blockIdx.y walks the meshes, x their items
+__global__ void __launch_bounds__(kBlock) gather_blas_leaf_boxes_kernel(const PtMesh* __restrict__ meshes, uint32_t n_meshes,
+                                                                       const uint32_t* __restrict__ blas_items, const float4* __restrict__ tri_aabb,
+                                                                       float4* __restrict__ out, uint32_t n_blas_items) {
+    for (uint32_t m = blockIdx.y; m < n_meshes; m += gridDim.y) {
+        if (meshes[m].kind != PT_MESH_KD) continue;
+        const uint32_t first = meshes[m].item_first, count = meshes[m].item_count, tri_first = meshes[m].tri_first;
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+            if (first + j >= n_blas_items) break;
+            const size_t tri = (size_t)tri_first + blas_items[first + j];
+            out[2 * (size_t)(first + j)] = tri_aabb[2 * tri];
+            out[2 * (size_t)(first + j) + 1] = tri_aabb[2 * tri + 1];
+        }
+    }
+}
+
 // FP32 box of every triangle (object space), rounded outward and padded by 1e-5 of the triangle's largest
 // coordinate magnitude and extent: the per-triangle cull of Mesh folds (traverse.cuh mesh_fold).
 __global__ void __launch_bounds__(kBlock) triangle_bounds_kernel(const PtTriPos* __restrict__ tri_pos, uint32_t n, float4* __restrict__ out) {
@@ -855,6 +871,13 @@ void launch_gather_leaf_boxes(const float4* inst_aabb, const uint32_t* items, ui
     if (!n_items) return;
     gather_leaf_boxes_kernel<<<blocks_for(n_items), kBlock, 0, st>>>(inst_aabb, items, n_items, out);
     group_bounds_kernel<<<blocks_for((n_items + 7u) / 8u), kBlock, 0, st>>>(out, n_items, 8u, out + 2 * (size_t)n_items);
+}
+
+void launch_gather_blas_leaf_boxes(const PtMesh* meshes, uint32_t n_meshes, const uint32_t* blas_items, const float4* tri_aabb, float4* out,
+                                   uint32_t n_blas_items, cudaStream_t st) {
+    if (!n_meshes || !n_blas_items) return;
+    const dim3 grid(std::min<uint32_t>(blocks_for(n_blas_items), 1024u), std::min<uint32_t>(n_meshes, 1024u));
+    gather_blas_leaf_boxes_kernel<<<grid, kBlock, 0, st>>>(meshes, n_meshes, blas_items, tri_aabb, out, n_blas_items);
 }
 
 // tri_aabb[n], l1[ceil(n / 32)], l2[ceil(n / 1024)]

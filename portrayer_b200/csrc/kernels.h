@@ -18,6 +18,8 @@ void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bo
 // them (out: 2 * (n_items + ceil(n_items / 8)) float4)
 void launch_gather_leaf_boxes(const float4* inst_aabb, const uint32_t* items, uint32_t n_items, float4* out, cudaStream_t st);
 // upload time: padded FP32 object-space boxes of all triangles + of every aligned run of 32 / 1024 of them
+void launch_gather_blas_leaf_boxes(const PtMesh* meshes, uint32_t n_meshes, const uint32_t* blas_items, const float4* tri_aabb, float4* out,
+                                   uint32_t n_blas_items, cudaStream_t st);
 void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, float4* l1, float4* l2, cudaStream_t st);
 
 // stream path: one launch per call; batch / level bookkeeping lives in the device control block

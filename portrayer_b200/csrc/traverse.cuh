@@ -16,6 +16,14 @@
 #pragma once
 #include "device_scene.cuh"
 
+// tuning switches (A/B'd on the box with tools/build_variants.sh + tools/ab_bench.sh)
+#ifndef PT_KD_PREFETCH
+#define PT_KD_PREFETCH 1
+#endif
+#ifndef PT_BLAS_TWO_PHASE
+#define PT_BLAS_TWO_PHASE 1
+#endif
+
 namespace ptd {
 
 struct WorkCounters {
@@ -235,13 +243,6 @@ struct KdStack {
     double e[PT_MAX_KD_STACK];
 };
 
-PT_D void load_kd_node(const PtKdNode* __restrict__ nodes, uint32_t i, double& split, uint32_t& a, uint32_t& b) {
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(nodes) + i);
-    split = __hiloint2double((int)w.y, (int)w.x);
-    a = w.z;
-    b = w.w;
-}
-
 // Iterative form of ray_cast_impl (node.rs:66-203). `leaf(first, count, s, e)`
 // returns true when the leaf's fold produced a hit inside [s, e); the first
 // leaf that does ends the walk.
@@ -249,14 +250,20 @@ template <class LeafFn>
 PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d, double s, double e, KdStack& stack,
                   LeafFn& leaf, uint32_t& err, uint32_t& n_splits) {
     int sp = 0;
-    uint32_t node = 0;
+    const uint4* __restrict__ nodes4 = reinterpret_cast<const uint4*>(nodes);
+    uint4 w = __ldg(nodes4);
     for (;;) {
-        double split;
-        uint32_t a, b;
-        load_kd_node(nodes, node, split, a, b);
+        const double split = __hiloint2double((int)w.y, (int)w.x);
+        const uint32_t a = w.z, b = w.w;
         const uint32_t axis = a & 3u;
         if (axis != 3u) {
             ++n_splits;
+            const uint32_t front = a >> 2, back = b;
+#if PT_KD_PREFETCH
+            // both children are fetched before the side tests: the loads' latency overlaps the f64 dependency chain
+            // below instead of following it (the node fetch was the top long-scoreboard stall of the walk)
+            const uint4 wf = __ldg(nodes4 + front), wb = __ldg(nodes4 + back);
+#endif
             // node.rs:119-127
             double t_max = s + extent;
             if (!in_range(s, e, t_max)) t_max = e - kEps;
@@ -267,9 +274,12 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
             const double p1 = oa + da * t_max;
             const bool f0 = (p0 - split) >= 0.0;  // which_side, infinite_plane.rs:27-35
             const bool f1 = (p1 - split) >= 0.0;
-            const uint32_t front = a >> 2, back = b;
             if (f0 == f1) {  // node.rs:134-137
-                node = f0 ? front : back;
+#if PT_KD_PREFETCH
+                w = f0 ? wf : wb;
+#else
+                w = __ldg(nodes4 + (f0 ? front : back));
+#endif
                 continue;
             }
             const double tp = (split - oa) / da;  // ray_hit_axis_aligned_plane, node.rs:90-110
@@ -279,7 +289,11 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
                 stack.s[sp] = tp;
                 stack.e[sp] = e;
                 ++sp;
-                node = f0 ? front : back;
+#if PT_KD_PREFETCH
+                w = f0 ? wf : wb;
+#else
+                w = __ldg(nodes4 + (f0 ? front : back));
+#endif
                 e = tp;
                 continue;
             }
@@ -289,7 +303,7 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
         }
         if (sp == 0) return false;
         --sp;
-        node = stack.node[sp];
+        w = __ldg(nodes4 + stack.node[sp]);
         s = stack.s[sp];
         e = stack.e[sp];
     }
@@ -339,7 +353,8 @@ template <bool ANY>
 struct BlasLeaf {
     const uint32_t* __restrict__ items;
     const PtTriPos* __restrict__ tris;
-    const float4* __restrict__ boxes;
+    const float4* __restrict__ boxes;       // per triangle of the mesh (index order)
+    const float4* __restrict__ leaf_boxes;  // the same boxes gathered into this tree's leaf-item order (DScene::blas_leaf_aabb)
     V3 o, d;
     RayF rf;
     double t;
@@ -347,6 +362,34 @@ struct BlasLeaf {
     uint32_t n_tests;
     PT_D bool operator()(uint32_t first, uint32_t count, double s, double e) {
         bool found = false;
+#if PT_BLAS_TWO_PHASE
+        // as in TlasLeaf: first slab-test the leaf's boxes (read sequentially, no index indirection) into a survivor
+        // mask, then run the f64 tests of the survivors in list order, each re-culled against the range as it has
+        // shrunk since.  Lanes of a warp then spend their time in the same phase instead of waiting for one lane's
+        // triangle test between two box tests.
+        for (uint32_t base = 0; base < count; base += 32u) {
+            const uint32_t n = min(32u, count - base);
+            const float4* __restrict__ lb = leaf_boxes + 2 * (size_t)(first + base);
+            uint32_t mask = 0u;
+            for (uint32_t j = 0; j < n; ++j)
+                if (aabb_may_hit(lb + 2 * (size_t)j, rf, s, e)) mask |= 1u << j;
+            while (mask) {
+                const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
+                mask &= mask - 1u;
+                if (found && !aabb_may_hit(lb + 2 * (size_t)j, rf, s, e)) continue;
+                const uint32_t idx = __ldg(items + first + base + j);
+                double tt;
+                if (triangle_t(tris + idx, o, d, s, e, tt, nullptr)) {
+                    e = tt;
+                    t = tt;
+                    tri = idx;
+                    found = true;
+                    if (ANY) { n_tests += base + j + 1u; return true; }
+                }
+            }
+        }
+        n_tests += count;
+#else
         for (uint32_t k = 0; k < count; ++k) {
             const uint32_t idx = __ldg(items + first + k);
             ++n_tests;
@@ -359,6 +402,7 @@ struct BlasLeaf {
                 if (ANY) return true;
             }
         }
+#endif
         return found;
     }
 };
@@ -433,8 +477,9 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
         return found;
     }
     // KDMesh: KDTreeNode<Triangle>::ray_hit on a clone of the range (node.rs:33-51)
-    BlasLeaf<ANY> leaf{sc.blas_items + __ldg(&mesh->item_first), sc.tri_pos + tri_first, sc.tri_aabb + 2 * (size_t)tri_first, o, d,
-                       make_rayf(o, d), 0.0, 0, 0};
+    const uint32_t item_first = __ldg(&mesh->item_first);
+    BlasLeaf<ANY> leaf{sc.blas_items + item_first, sc.tri_pos + tri_first, sc.tri_aabb + 2 * (size_t)tri_first,
+                       sc.blas_leaf_aabb + 2 * (size_t)item_first, o, d, make_rayf(o, d), 0.0, 0, 0};
     const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), __ldg(&mesh->extent), o, d, s, e, blas_stack, leaf,
                              err, wc.kd_splits);
     wc.triangle_tests += leaf.n_tests;
