@@ -310,6 +310,15 @@ def run_ours(args, rank, world, local_rank):
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     same_geometry = len({(j.w, j.h) for j in jobs}) == 1
+    # The exchange step at N > 1.  "peer" (default): rank 0's full images are mapped into every rank (CUDA IPC, peer
+    # access over NVLink) and every rank's resolve kernel stores its tiles straight into them — the exchange is fused
+    # into the last kernel of the frame and only a one-element all-reduce (completion signal) is left.  "nccl": compact
+    # tiles + NCCL gather + un-tiling on rank 0 (the library-collective baseline).
+    peer = None
+    if world > 1 and args.exchange == "peer" and same_geometry:
+        peer = ptd.PeerImage(len(jobs), jobs[0].h, jobs[0].w, local_rank, dst=0)
+        for k, j in enumerate(jobs):
+            j.frame.set_image_target(peer.ptr(k))
     n_streams = max(1, min(args.streams, len(jobs)))
     side_streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
     all_streams = [stream] + [s_.cuda_stream for s_ in side_streams]
@@ -333,7 +342,9 @@ def run_ours(args, rank, world, local_rank):
             st = j.frame.finish()
             if collect is not None:
                 collect.append(st)
-        if world > 1:
+        if peer is not None:
+            peer.signal_done()  # the tiles are already in rank 0's images: order them before whatever reads the images
+        elif world > 1:
             # the exchange step: NCCL gather of every rank's RGB8 tiles + device-side un-tiling on rank 0, one call
             # for all frames of the step that share a geometry (the exchange is latency-bound)
             if same_geometry:
@@ -357,6 +368,16 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         flush.zero_()
         step()
+    exchange_verified = None
+    if peer is not None:
+        # the fused exchange against the library collective, once, outside the timed region: same bytes on rank 0
+        ref = ptd.gather_images_device([j.rgb_dev for j in jobs], jobs[0].params, dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            got = peer.images().reshape(len(jobs), -1, 3)
+            exchange_verified = bool(torch.equal(got, ref))
+            if not exchange_verified:
+                raise SystemExit("peer-store exchange differs from the NCCL gather")
 
     # ---- per-kernel launch durations for the roofline: the same frames on the kernel-by-kernel stream path with a
     # CUDA-event pair around every extend / shadow / shade launch (the timed region below replays CUDA graphs, whose
@@ -460,11 +481,18 @@ def run_ours(args, rank, world, local_rank):
                 j.frame.rebind(ds, j.cam)                 # the rank's frame (buffers + graph) is kept, as pt_render does
                 j.frame.set_background(bg_host.numpy())
                 st = j.frame.render(stream=stream)
-                img = ptd.gather_image(j.rgb_dev, p, dst=0)  # NCCL gather, device un-tiling, D2H on rank 0
+                if peer is not None:
+                    peer.signal_done()  # tiles were stored into rank 0's image by the resolve kernels
+                    if rank == 0:
+                        rgb_host.copy_(peer.images()[jobs.index(j)], non_blocking=True)  # D2H on rank 0
+                        torch.cuda.synchronize()
+                        d2h += rgb_host.numel()
+                else:
+                    img = ptd.gather_image(j.rgb_dev, p, dst=0)  # NCCL gather, device un-tiling, D2H on rank 0
+                    if rank == 0:
+                        d2h += int(img.nbytes)
                 rays += st.rays
                 h2d += ds.uploaded_bytes + bg_host.numel() * 8
-                if rank == 0:
-                    d2h += int(img.nbytes)
                 j.frame.rebind(j.dscene)
                 ds.close()
             return rays, h2d, d2h
@@ -485,7 +513,8 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.all_reduce(rr_t, op=torch.distributed.ReduceOp.SUM)
         e2e = {"value": float(rr_t[0]) / float(tt) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(rr_t[1]),
                "d2h_bytes_per_step": int(rr_t[2]), "ms_per_step": float(tt) / n_e2e * 1e3, "steps": n_e2e,
-               "path": "per frame and rank: scene upload + tile render, NCCL gather of RGB8 tiles to rank 0, D2H on rank 0"}
+               "path": "per frame and rank: scene upload + tile render, " + ("tiles stored into rank 0's image by the resolve kernel "
+                       "(peer memory) + completion all-reduce" if peer is not None else "NCCL gather of RGB8 tiles to rank 0") + ", D2H on rank 0"}
 
     if rank != 0:
         return
@@ -579,6 +608,9 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "flushed between timed steps (256 MB write)", "tile": "32x32 interleaved over ranks",
                    "streams": n_streams,
                    "parallelism": f"tiles x{world}", "scene_broadcast_ms": scene_broadcast_ms,
+                   "exchange": None if world == 1 else ("resolve kernel stores tiles into rank 0's image over peer memory (NVLink) + "
+                                                        "1-element all-reduce" if peer is not None else "NCCL gather + un-tiling on rank 0"),
+                   "exchange_verified_against_nccl_gather": exchange_verified,
                    "reference_panics_tolerated": panics},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(r[1].item()), "roofline": roofline, "roofline_fp64": roofline_fp64,
         "cpu_baseline": cpu,
@@ -595,6 +627,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="configs1")
     ap.add_argument("--samples", type=int, default=0, help="samples per pixel at N=1 (default: the workload's)")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the frames of a step are spread over (1 = back to back on one)")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: how the tiles reach rank 0 (peer: stored by the resolve kernel into rank 0's image over NVLink; nccl: gather)")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e and cpu_baseline legs (for runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

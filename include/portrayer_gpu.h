@@ -416,6 +416,23 @@ int pt_frame_pixel_index(const PtFrame* frame, uint32_t* index_out);
 /* copy the compact outputs back and scatter them into full-size host images (any may be NULL) */
 int pt_frame_read(PtFrame* frame, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtStats* stats);
 
+/* ---- multi-GPU: the image exchange fused into the resolve kernel ----
+ * One process per GPU; every rank owns interleaved tiles of the image (PtRenderParams.rank / world).  The rank that
+ * collects the picture allocates a full-image RGB8 buffer with pt_peer_alloc and hands the 64-byte handle to the
+ * other ranks (any transport: bench.py broadcasts it with torch.distributed); they map it with pt_peer_open and
+ * point their frames at it with pt_frame_set_image_target.  The resolve kernel of every rank then stores its owned
+ * pixels at their own place (y * W + x) * 3 of that image — over NVLink for the remote ranks — so no gather and no
+ * un-tiling pass follow the render: the only thing left of the exchange is a completion signal (a barrier).
+ * The compact owned-pixel outputs (pt_frame_rgb_device) are still written.  Replaces nothing in the reference (it is
+ * single-process, src/render.rs:127-150); it is the multi-GPU form of "write RGB8 into the caller's image". */
+typedef struct PtPeerHandle { unsigned char bytes[64]; } PtPeerHandle;
+int pt_peer_alloc(uint64_t bytes, void** d_ptr, PtPeerHandle* handle_out); /* zero-filled device memory other processes can map */
+int pt_peer_free(void* d_ptr);                                               /* pointer from pt_peer_alloc */
+int pt_peer_open(const PtPeerHandle* handle, void** d_ptr);                 /* in ANOTHER process than the allocating one */
+int pt_peer_close(void* d_ptr);                                              /* pointer from pt_peer_open */
+/* d_image_rgb: W * H * 3 bytes, local or peer device memory; NULL detaches.  Takes effect at the next render. */
+int pt_frame_set_image_target(PtFrame* frame, uint8_t* d_image_rgb);
+
 /* ---- k-d tree build on the device (the step right before the render loop) ----
  * Replaces KDLeaf::partitioned (src/kdtree/leaf.rs:89-231) as called by KDTreeScene::from (kdscene.rs:19-44: items =
  * flat instances, bounds = FlatSceneNode::bounds) and KDMesh::new (kdmesh.rs:37-58: items = triangles, bounds =

@@ -166,6 +166,11 @@ GPU_SYMBOLS = {
     "pt_frame_hit_t_device": (C.c_void_p, [C.c_void_p]),
     "pt_frame_pixel_index": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_frame_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PtStats)]),
+    "pt_peer_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "pt_peer_free": (C.c_int, [C.c_void_p]),
+    "pt_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pt_peer_close": (C.c_int, [C.c_void_p]),
+    "pt_frame_set_image_target": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_kd_build": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "pt_kd_build_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "pt_kd_tree_free": (None, [C.c_void_p]),

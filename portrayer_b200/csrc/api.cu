@@ -206,6 +206,7 @@ struct PtFrame {
     uint64_t bg_doubles = 0;
     uint64_t out_pixels = 0;  // entries of the output buffers (owned pixels, or W*H when row-major)
     uint8_t* d_rgb = nullptr;
+    uint8_t* image_target = nullptr;  // pt_frame_set_image_target: full-image RGB8, local or peer memory (not owned)
     uint32_t* d_hit_id = nullptr;
     double* d_hit_t = nullptr;
     // node pool
@@ -517,6 +518,7 @@ FrameState frame_state(const PtFrame* f) {
     st.pool = f->pool;
     st.ctl = f->d_ctl;
     st.rgb = f->d_rgb;
+    st.rgb_image = f->image_target;
     st.hit_id = f->d_hit_id;
     st.hit_t = f->d_hit_t;
     st.row_major = f->row_major ? 1u : 0u;
@@ -1171,6 +1173,59 @@ int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* u
 const uint8_t* pt_frame_rgb_device(const PtFrame* frame) { return frame ? frame->d_rgb : nullptr; }
 const uint32_t* pt_frame_hit_id_device(const PtFrame* frame) { return frame ? frame->d_hit_id : nullptr; }
 const double* pt_frame_hit_t_device(const PtFrame* frame) { return frame ? frame->d_hit_t : nullptr; }
+
+int pt_frame_set_image_target(PtFrame* frame, uint8_t* d_image_rgb) {
+    if (!frame) return fail(PT_ERR_INVALID, "null frame");
+    Lock lock(g_mu);
+    if (frame->pending == PtFrame::IN_FLIGHT) return fail(PT_ERR_INVALID, "a render of this frame is in flight");
+    frame->image_target = d_image_rgb;  // read by frame_state() when the next render uploads the frame's constants
+    return PT_OK;
+}
+
+int pt_peer_alloc(uint64_t bytes, void** d_ptr, PtPeerHandle* handle_out) {
+    if (!d_ptr || !handle_out || bytes == 0) return fail(PT_ERR_INVALID, "null argument or zero size");
+    static_assert(sizeof(PtPeerHandle) == sizeof(cudaIpcMemHandle_t), "PtPeerHandle carries a cudaIpcMemHandle_t");
+    Lock lock(g_mu);
+    if (int rc = ensure_init()) return rc;
+    void* p = nullptr;
+    // plain cudaMalloc, not the caching arena: an IPC handle names a whole allocation
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(PT_ERR_CUDA, "pt_peer_alloc: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out->bytes, &h, sizeof(h));
+    *d_ptr = p;
+    return PT_OK;
+}
+
+int pt_peer_free(void* d_ptr) {
+    if (!d_ptr) return PT_OK;
+    Lock lock(g_mu);
+    CUDA_TRY(cudaFree(d_ptr));
+    return PT_OK;
+}
+
+int pt_peer_open(const PtPeerHandle* handle, void** d_ptr) {
+    if (!handle || !d_ptr) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
+    if (int rc = ensure_init()) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->bytes, sizeof(h));
+    void* p = nullptr;
+    // enables peer access between this device and the owner's when they differ (NVLink / NVSwitch on an HGX board)
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "pt_peer_open: %s", cudaGetErrorString(e));
+    *d_ptr = p;
+    return PT_OK;
+}
+
+int pt_peer_close(void* d_ptr) {
+    if (!d_ptr) return PT_OK;
+    Lock lock(g_mu);
+    CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return PT_OK;
+}
 
 int pt_frame_pixel_index(const PtFrame* frame, uint32_t* index_out) {
     if (!frame || !index_out) return fail(PT_ERR_INVALID, "null argument");

@@ -118,6 +118,7 @@ struct FrameState {
     NodePool pool;
     BatchCtl* ctl;
     uint8_t* rgb;       // resolve outputs: compact owned-pixel order, or full-image row-major
+    uint8_t* rgb_image; // nullable: full-image row-major RGB8 target, possibly another GPU's memory (pt_frame_set_image_target)
     uint32_t* hit_id;   // nullable
     double* hit_t;      // nullable
     uint32_t row_major;

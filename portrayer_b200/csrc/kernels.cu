@@ -608,11 +608,17 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(int slot_id) {
     }
     // compact owned-pixel order (multi-GPU gather), or the pixel's own place in a full row-major image
     const size_t slot = fs.row_major ? (size_t)__ldg(fp.pixel_index + first_slot + k) : (size_t)first_slot + k;
+    // the exchange step of the multi-GPU path, fused: the pixel also goes to its own place in the collecting rank's
+    // full image (peer memory over NVLink for the other ranks); tiles are disjoint, so no two ranks write one byte
+    uint8_t* __restrict__ image = fs.rgb_image;
+    const size_t pixel = image ? (size_t)__ldg(fp.pixel_index + first_slot + k) : 0;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         double c = total[ch] / (double)fp.samples;
         c = pow(c, 1.0 / PT_GAMMA);
-        rgb[slot * 3 + ch] = to_u8(clamp01(c));
+        const uint8_t v = to_u8(clamp01(c));
+        rgb[slot * 3 + ch] = v;
+        if (image) image[pixel * 3 + ch] = v;
     }
     if (hit_id) {
         hit_id[slot * 2] = pool.inst[p0];

@@ -175,6 +175,72 @@ def gather_image(local_rgb: torch.Tensor, params: PtRenderParams, dst: int = 0, 
     return out
 
 
+class PeerImage:
+    """``n_images`` full RGB8 images ([n, H*W, 3] bytes) that live on ``dst``'s GPU and are mapped into every other
+    rank's address space (CUDA IPC -> peer access over NVLink / NVSwitch): frames pointed at ``ptr(i)`` with
+    ``Frame.set_image_target`` have their resolve kernel store the rank's tiles straight into the collecting rank's
+    picture, so the exchange step needs no gather, no padding copy and no un-tiling — only ``signal_done()``, a
+    one-element all-reduce that orders every rank's stores before ``dst`` reads the images.
+
+    ``exchange_handle`` is the only part that touches ``torch.distributed`` (a 64-byte broadcast); it is separate so
+    that the handle plumbing is testable over gloo on CPU with a stand-in allocator."""
+
+    def __init__(self, n_images: int, height: int, width: int, device: int, dst: int = 0):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.dst, self.n, self.h, self.w, self.device = dst, n_images, height, width, device
+        self.image_bytes = height * width * 3
+        self._owned = self.rank == dst
+        self._ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        if self._owned:
+            _ffi.check(_ffi.gpu.pt_peer_alloc(self.image_bytes * n_images, C.byref(self._ptr), handle))
+        payload = exchange_handle(bytes(handle) if self._owned else None, dst,
+                                  torch.device("cuda", device) if dist.is_initialized() and dist.get_backend() == "nccl" else torch.device("cpu"))
+        if not self._owned:
+            buf = (C.c_ubyte * 64).from_buffer_copy(payload)
+            _ffi.check(_ffi.gpu.pt_peer_open(buf, C.byref(self._ptr)))
+        self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", device))
+
+    def ptr(self, image: int = 0) -> int:
+        return self._ptr.value + image * self.image_bytes
+
+    def signal_done(self) -> None:
+        """stream-ordered completion signal: when it has passed on ``dst``, every rank's resolve kernels that were
+        enqueued before it have finished and their peer stores are visible"""
+        if self.world > 1:
+            dist.all_reduce(self._flag)
+
+    def images(self) -> torch.Tensor | None:
+        """[n, H, W, 3] uint8 view of the images on ``dst`` (None elsewhere)"""
+        if not self._owned:
+            return None
+        return device_tensor(self._ptr.value, (self.n, self.h, self.w, 3), "|u1", self.device)
+
+    def close(self) -> None:
+        if self._ptr.value:
+            if self._owned:
+                if self.world > 1:
+                    dist.barrier()  # nobody may still be storing into memory that is about to be freed
+                _ffi.gpu.pt_peer_free(self._ptr)
+            else:
+                _ffi.gpu.pt_peer_close(self._ptr)
+                if self.world > 1:
+                    dist.barrier()
+            self._ptr = C.c_void_p()
+
+
+def exchange_handle(handle: bytes | None, src: int, device: torch.device) -> bytes:
+    """broadcast a 64-byte peer-memory handle from ``src`` to every rank"""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return handle
+    t = torch.zeros(64, dtype=torch.uint8, device=device)
+    if dist.get_rank() == src:
+        t.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+    dist.broadcast(t, src)
+    return bytes(t.cpu().numpy().tobytes())
+
+
 def _with_rank(params: PtRenderParams, rank: int, world: int) -> PtRenderParams:
     p = PtRenderParams.from_buffer_copy(bytes(params))
     p.rank, p.world = rank, world

@@ -143,6 +143,11 @@ class Frame:
     def set_background_device(self, device_ptr: int) -> None:
         check(gpu.pt_frame_set_background_device(self._h, C.c_void_p(device_ptr)))
 
+    def set_image_target(self, device_ptr: int | None) -> None:
+        """the resolve kernel also stores this rank's pixels into a full-image RGB8 buffer (W*H*3 bytes, local or peer
+        device memory, distributed.PeerImage): the multi-GPU exchange without a gather.  None detaches."""
+        check(gpu.pt_frame_set_image_target(self._h, C.c_void_p(device_ptr) if device_ptr else None))
+
     def render(self, stream: int | None = None, progress=None) -> PtStats:
         stats = PtStats()
         cb = _ffi.PROGRESS_FN(lambda _user, n: progress(n)) if progress else None

@@ -60,6 +60,31 @@ def test_two_rank_tiles_gather_to_rank0(tmp_path):
     assert np.array_equal(multi0, full) and np.array_equal(multi1, full), "the batched multi-frame exchange must agree"
 
 
+def _handle_worker(rank, world, port, out_path):
+    sys.path.insert(0, REPO)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch
+
+    from portrayer_b200 import distributed as ptd
+
+    ptd.init_process_group("gloo")
+    handle = bytes(range(100, 164)) if rank == 1 else None  # the collecting rank need not be rank 0
+    got = ptd.exchange_handle(handle, 1, torch.device("cpu"))
+    assert len(got) == 64
+    if rank == 0:
+        np.save(out_path, np.frombuffer(got, np.uint8))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_peer_handle_reaches_every_rank(tmp_path):
+    """the 64-byte peer-memory handle of distributed.PeerImage (pt_peer_alloc -> pt_peer_open) crosses ranks intact"""
+    out = str(tmp_path / "handle.npy")
+    mp.spawn(_handle_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert np.array_equal(np.load(out), np.arange(100, 164, dtype=np.uint8))
+
+
 def test_tile_partition_is_a_partition():
     sys.path.insert(0, REPO)
     from portrayer_b200 import distributed as ptd

@@ -220,6 +220,59 @@ def test_tile_ownership_matches_single_rank(gpu_ready):
     assert np.array_equal(img.buffer, full.buffer)
 
 
+def test_resolve_kernel_stores_tiles_into_a_shared_image(gpu_ready):
+    """The fused exchange of the multi-GPU path (pt_frame_set_image_target): frames of world=3 ranks all point at ONE
+    full-image buffer allocated with pt_peer_alloc; every resolve kernel stores its own tiles at their place, and the
+    result is the single-rank image — no gather, no un-tiling.  (Across processes the other ranks map the same buffer
+    with pt_peer_open; bench.py --gpus N checks that path against the NCCL gather on every run.)"""
+    import ctypes as C
+
+    import torch
+
+    from portrayer_b200 import _ffi
+    from portrayer_b200 import distributed as ptd
+    from portrayer_b200.render import _background_arg, make_params
+
+    scene = pt.Scene.example("primitives")
+    w, h = 200, 120
+    full, _ = parity.render_gpu(scene, samples=2, rng="hash", size=(w, h))
+    ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    _ffi.check(_ffi.gpu.pt_peer_alloc(w * h * 3, C.byref(ptr), handle))
+    assert any(handle), "the handle another process would open must be filled in"
+    try:
+        ds = pt.DeviceScene(scene.blob)
+        bg, bg_mode = _background_arg(scene, w, h)
+        compact = []
+        for rank in range(3):
+            params = make_params(w, h, 2, "hash", 1, bg_mode=bg_mode, rank=rank, world=3, tile=16)
+            fr = pt.Frame(ds, scene.camera(w, h), params)
+            fr.set_background(bg)
+            fr.set_image_target(ptr.value)
+            fr.render()
+            # the compact owned-pixel output is still written, and agrees
+            own = ptd.device_tensor(fr.rgb_device_ptr, (fr.owned_pixels, 3)).cpu().numpy()
+            compact.append((fr.pixel_index(), own))
+            fr.close()
+        image = ptd.device_tensor(ptr.value, (h, w, 3)).cpu().numpy()
+        assert np.array_equal(image, full.buffer)
+        for index, own in compact:
+            assert np.array_equal(image.reshape(-1, 3)[index.astype(np.int64)], own)
+        # detaching: a later render leaves the image alone
+        torch.cuda.synchronize()
+        ptd.device_tensor(ptr.value, (h, w, 3)).zero_()
+        params = make_params(w, h, 2, "hash", 1, bg_mode=bg_mode)
+        fr = pt.Frame(ds, scene.camera(w, h), params)
+        fr.set_background(bg)
+        fr.set_image_target(ptr.value)
+        fr.set_image_target(None)
+        fr.render()
+        fr.close()
+        assert not ptd.device_tensor(ptr.value, (h, w, 3)).any()
+        ds.close()
+    finally:
+        _ffi.check(_ffi.gpu.pt_peer_free(ptr))
+
+
 def test_reference_panic_is_reported(gpu_ready):
     """A textured material on a cylinder panics in the reference (material.rs:141); the C ABI returns that text."""
     import ctypes as C
