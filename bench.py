@@ -316,9 +316,21 @@ def run_ours(args, rank, world, local_rank):
     # tiles + NCCL gather + un-tiling on rank 0 (the library-collective baseline).
     peer = None
     if world > 1 and args.exchange == "peer" and same_geometry:
-        peer = ptd.PeerImage(len(jobs), jobs[0].h, jobs[0].w, local_rank, dst=0)
-        for k, j in enumerate(jobs):
-            j.frame.set_image_target(peer.ptr(k))
+        try:
+            peer = ptd.PeerImage(len(jobs), jobs[0].h, jobs[0].w, local_rank, dst=0)
+            ok = 1
+        except Exception as exc:  # no peer access between some pair of GPUs on this box: every rank falls back together
+            print(f"[rank {rank}] peer image unavailable ({exc}); using the NCCL gather", file=sys.stderr)
+            ok = 0
+        agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(agree, op=torch.distributed.ReduceOp.MIN)
+        if int(agree.item()) == 0:
+            if peer is not None:
+                peer.close_local()
+            peer = None
+        else:
+            for k, j in enumerate(jobs):
+                j.frame.set_image_target(peer.ptr(k))
     n_streams = max(1, min(args.streams, len(jobs)))
     side_streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
     all_streams = [stream] + [s_.cuda_stream for s_ in side_streams]

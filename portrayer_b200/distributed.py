@@ -193,10 +193,17 @@ class PeerImage:
         self._owned = self.rank == dst
         self._ptr = C.c_void_p()
         handle = (C.c_ubyte * 64)()
+        alloc_error = None
         if self._owned:
-            _ffi.check(_ffi.gpu.pt_peer_alloc(self.image_bytes * n_images, C.byref(self._ptr), handle))
+            try:
+                _ffi.check(_ffi.gpu.pt_peer_alloc(self.image_bytes * n_images, C.byref(self._ptr), handle))
+            except _ffi.PortrayerError as exc:  # still take part in the broadcast: an all-zero handle tells every rank
+                alloc_error = exc
+                handle = (C.c_ubyte * 64)()
         payload = exchange_handle(bytes(handle) if self._owned else None, dst,
                                   torch.device("cuda", device) if dist.is_initialized() and dist.get_backend() == "nccl" else torch.device("cpu"))
+        if not any(payload):
+            raise RuntimeError(f"the collecting rank could not allocate the shared image: {alloc_error or 'see rank ' + str(dst)}")
         if not self._owned:
             buf = (C.c_ubyte * 64).from_buffer_copy(payload)
             _ffi.check(_ffi.gpu.pt_peer_open(buf, C.byref(self._ptr)))
@@ -216,6 +223,12 @@ class PeerImage:
         if not self._owned:
             return None
         return device_tensor(self._ptr.value, (self.n, self.h, self.w, 3), "|u1", self.device)
+
+    def close_local(self) -> None:
+        """release this rank's mapping / allocation without any collective (error paths)"""
+        if self._ptr.value:
+            (_ffi.gpu.pt_peer_free if self._owned else _ffi.gpu.pt_peer_close)(self._ptr)
+            self._ptr = C.c_void_p()
 
     def close(self) -> None:
         if self._ptr.value:
