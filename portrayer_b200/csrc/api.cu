@@ -177,8 +177,13 @@ struct PtScene {
     float4* d_aabb = nullptr;               // padded FP32 world box per instance (conservative cull, traverse.cuh)
     float4* d_leaf_aabb = nullptr;          // d_aabb gathered into scene-tree leaf order
     float4* d_tri_aabb = nullptr;           // padded FP32 object box per triangle + per run of 32 / 1024 (one allocation)
-    uint32_t tri_aabb_l1 = 0, tri_aabb_l2 = 0;  // offsets (in boxes) of the two group levels inside d_tri_aabb
     uint32_t tri_aabb_leaf = 0;                 // offset (in boxes) of the KDMesh leaf-ordered copy inside d_tri_aabb
+    // Mesh fold structure (traverse.cuh mesh_fold): Morton order of every linear mesh's triangles, boxes in that order
+    // and 4-ary group levels, all inside d_tri_aabb / d_fold_order
+    uint32_t* d_fold_order = nullptr;
+    uint32_t fold_off[ptd::kFoldLevels + 1] = {};  // offsets (in boxes) of the fold levels inside d_tri_aabb
+    uint32_t fold_levels = 0;
+    bool fold_sort = false;  // some linear mesh is big enough to be worth sorting, and the meshes' triangle ranges do not overlap partially
     std::vector<uint64_t> resident_keys;    // textures held in the residency cache (refs to drop)
     std::vector<uint8_t*> private_texels;   // unkeyed textures owned by this scene
     uint64_t h2d_bytes = 0;                 // bytes the upload copied to the device
@@ -301,8 +306,10 @@ void fill_view(PtScene* s) {
     v.leaf_aabb = s->d_leaf_aabb;
     v.leaf_grp_aabb = s->d_leaf_aabb ? s->d_leaf_aabb + 2 * (size_t)s->h.n_tlas_items : nullptr;
     v.tri_aabb = s->d_tri_aabb;
-    v.tri_aabb_l1 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1 : nullptr;
-    v.tri_aabb_l2 = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2 : nullptr;
+    v.fold_order = s->d_fold_order;
+    for (int l = 0; l <= ptd::kFoldLevels; ++l)
+        v.fold_aabb[l] = s->d_tri_aabb && l <= (int)s->fold_levels ? s->d_tri_aabb + 2 * (size_t)s->fold_off[l] : nullptr;
+    v.fold_levels = s->fold_levels;
     v.blas_leaf_aabb = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_leaf : nullptr;
     v.gamma_lut = g_gamma_lut;
     v.ambient[0] = h.ambient[0]; v.ambient[1] = h.ambient[1]; v.ambient[2] = h.ambient[2];
@@ -323,6 +330,7 @@ void free_scene(PtScene* s) {
     g_dev.release(s->d_textures);
     g_dev.release(s->d_aabb);
     g_dev.release(s->d_tri_aabb);
+    g_dev.release(s->d_fold_order);
     g_dev.release(s->d_leaf_aabb);
     g_dev.release(s->d_own_tlas_nodes);
     g_dev.release(s->d_own_tlas_items);
@@ -345,6 +353,21 @@ int adopt_header(PtScene* s, const void* host_blob, uint64_t bytes, bool* texels
     s->has_reflective = false;
     for (uint32_t i = 0; i < d.n_materials; ++i)
         if (d.materials[i].reflectivity > 0.0) s->has_reflective = true;
+    // Mesh fold order: sort when a linear mesh is big enough to gain from it; the sort keys assume that two meshes'
+    // triangle ranges are either the same range or disjoint (what the packer emits) — anything else keeps index order
+    s->fold_sort = false;
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> ranges;
+        for (uint32_t i = 0; i < d.n_meshes; ++i) {
+            if (d.meshes[i].kind == PT_MESH_LINEAR && d.meshes[i].tri_count >= 256) s->fold_sort = true;  // below that the sort costs more upload time than the fold gains
+            ranges.emplace_back(d.meshes[i].tri_first, d.meshes[i].tri_count);
+        }
+        std::sort(ranges.begin(), ranges.end());
+        for (size_t i = 1; i < ranges.size() && s->fold_sort; ++i) {
+            const auto &a = ranges[i - 1], &b = ranges[i];
+            if (a != b && (uint64_t)a.first + a.second > b.first) s->fold_sort = false;
+        }
+    }
     s->h = h;
     if (h.tlas_depth > PT_MAX_KD_STACK || h.blas_max_depth > PT_MAX_KD_STACK)
         return fail(PT_ERR_KD_TOO_DEEP, "kd-tree depth %u / %u exceeds PT_MAX_KD_STACK = %d", h.tlas_depth, h.blas_max_depth,
@@ -416,26 +439,51 @@ int build_instance_bounds(PtScene* s) {
     if (!s->d_aabb) return fail(PT_ERR_CUDA, "instance bounds allocation failed: %s", cudaGetErrorString(e));
     double* scratch = static_cast<double*>(g_dev.alloc(std::max<size_t>(s->h.n_meshes, 1) * 6 * sizeof(double), &e));
     if (!scratch) return fail(PT_ERR_CUDA, "mesh bounds allocation failed: %s", cudaGetErrorString(e));
-    // triangle boxes for the Mesh-fold cull
+    // triangle boxes: index order, KDMesh leaf-item order, and the Mesh fold structure (Morton order + 4-ary group levels)
     const uint32_t nt = s->h.n_triangles;
+    void* fold_scratch = nullptr;
+    size_t fold_temp = 0;
     if (nt) {
-        const uint32_t n1 = (nt + 31u) / 32u, n2 = (n1 + 31u) / 32u;
-        s->tri_aabb_l1 = nt;
-        s->tri_aabb_l2 = nt + n1;
-        s->tri_aabb_leaf = nt + n1 + n2;
-        s->d_tri_aabb = static_cast<float4*>(g_dev.alloc(((size_t)nt + n1 + n2 + s->h.n_blas_items) * 2 * sizeof(float4), &e));
+        s->tri_aabb_leaf = nt;
+        uint32_t off = nt + s->h.n_blas_items, n_level = nt;
+        s->fold_levels = 0;
+        for (int l = 0; l <= ptd::kFoldLevels; ++l) {
+            s->fold_off[l] = off;
+            off += n_level;
+            if (l >= 1) s->fold_levels = (uint32_t)l;
+            if (n_level <= 1) break;  // a level with one box: nothing coarser to build
+            n_level = (n_level + 3u) / 4u;
+        }
+        s->d_tri_aabb = static_cast<float4*>(g_dev.alloc((size_t)off * 2 * sizeof(float4), &e));
         if (!s->d_tri_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "triangle bounds allocation failed: %s", cudaGetErrorString(e)); }
+        s->d_fold_order = static_cast<uint32_t*>(g_dev.alloc((size_t)nt * sizeof(uint32_t), &e));
+        fold_temp = s->fold_sort ? fold_sort_temp_bytes(nt) : 0;
+        if (s->d_fold_order) fold_scratch = g_dev.alloc(fold_scratch_bytes(nt, fold_temp), &e);
+        if (!fold_scratch) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "fold order allocation failed: %s", cudaGetErrorString(e)); }
     }
     s->d_leaf_aabb = static_cast<float4*>(g_dev.alloc(leaf_box_count(s->h.n_tlas_items) * 2 * sizeof(float4), &e));
     if (!s->d_leaf_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e)); }
     fill_view(s);
     launch_instance_bounds(s->view, s->h.n_meshes, scratch, s->d_aabb, g_stream);
     launch_gather_leaf_boxes(s->d_aabb, s->view.tlas_items, s->h.n_tlas_items, s->d_leaf_aabb, g_stream);
-    if (nt) launch_triangle_bounds(s->view.tri_pos, nt, s->d_tri_aabb, s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l1,
-                                   s->d_tri_aabb + 2 * (size_t)s->tri_aabb_l2, g_stream);
-    if (nt && s->h.n_blas_items)
-        launch_gather_blas_leaf_boxes(s->view.meshes, s->h.n_meshes, s->view.blas_items, s->d_tri_aabb,
-                                      s->d_tri_aabb + 2 * (size_t)s->tri_aabb_leaf, s->h.n_blas_items, g_stream);
+    if (nt) {
+        launch_triangle_bounds(s->view.tri_pos, nt, s->d_tri_aabb, g_stream);
+        if (s->h.n_blas_items)
+            launch_gather_blas_leaf_boxes(s->view.meshes, s->h.n_meshes, s->view.blas_items, s->d_tri_aabb,
+                                          s->d_tri_aabb + 2 * (size_t)s->tri_aabb_leaf, s->h.n_blas_items, g_stream);
+        int end_bit = 33;
+        while (end_bit < 64 && (nt >> (end_bit - 32)) != 0) ++end_bit;
+        const cudaError_t se = launch_fold_order(s->view.meshes, s->h.n_meshes, s->view.tri_pos, scratch, nt, s->fold_sort, s->d_fold_order,
+                                                 fold_scratch, fold_temp, end_bit, g_stream);
+        if (se != cudaSuccess) { g_dev.release(scratch); g_dev.release(fold_scratch); return fail(PT_ERR_CUDA, "fold order sort failed: %s", cudaGetErrorString(se)); }
+        launch_gather_fold_boxes(s->d_tri_aabb, s->d_fold_order, nt, s->d_tri_aabb + 2 * (size_t)s->fold_off[0], g_stream);
+        uint32_t n_level = nt;
+        for (uint32_t l = 1; l <= s->fold_levels; ++l) {
+            launch_group_bounds(s->d_tri_aabb + 2 * (size_t)s->fold_off[l - 1], n_level, 4u, s->d_tri_aabb + 2 * (size_t)s->fold_off[l], g_stream);
+            n_level = (n_level + 3u) / 4u;
+        }
+        g_dev.release(fold_scratch);
+    }
     g_dev.release(scratch);  // stream-ordered reuse: later users of the block run after this kernel on g_stream
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "instance bounds kernel failed: %s", cudaGetErrorString(e));
@@ -1639,7 +1687,9 @@ int pt_scene_set_instances(PtScene* scene, const PtFlatScene* flat, const PtKdTr
     g_dev.release(scene->d_aabb);
     g_dev.release(scene->d_leaf_aabb);
     g_dev.release(scene->d_tri_aabb);
+    g_dev.release(scene->d_fold_order);
     scene->d_aabb = scene->d_leaf_aabb = scene->d_tri_aabb = nullptr;
+    scene->d_fold_order = nullptr;
     int rc = build_instance_bounds(scene);
     if (rc != PT_OK) return rc;
     return pt_scene_set_tlas(scene, tree);

@@ -7,6 +7,8 @@
 
 namespace ptd {
 
+constexpr int kFoldLevels = 6;  // group levels of the Mesh fold structure: runs of 4, 16, 64, 256, 1024, 4096 positions
+
 // One texture as the kernels see it: the texels live either inside the uploaded blob or in the
 // library's texture residency cache (PtTexture.key), so the record carries a device pointer.
 struct TextureDev {
@@ -34,10 +36,14 @@ struct DScene {
     const float4* inst_aabb;  // [2 * n_instances] padded world-space box of every instance (lo, hi), FP32, rounded outward
     const float4* leaf_aabb;  // [2 * n_tlas_items] inst_aabb gathered into scene-tree leaf order: leaf_aabb[j] = inst_aabb[tlas_items[j]]
     const float4* leaf_grp_aabb;  // [2 * ceil(n_tlas_items / 8)] union of leaf_aabb over every aligned run of 8 leaf positions
-    // padded object-space FP32 box of every triangle, of every aligned run of 32 and of 1024 triangles (Mesh fold cull)
+    // padded object-space FP32 box of every triangle (index order)
     const float4* tri_aabb;
-    const float4* tri_aabb_l1;
-    const float4* tri_aabb_l2;
+    // Mesh fold cull (traverse.cuh mesh_fold): the triangles of every linear Mesh in Morton order of their centroids
+    // (fold_order: position -> triangle index, positions of a mesh stay inside its own [tri_first, tri_first + tri_count)),
+    // their boxes in that order (fold_aabb[0]) and the union boxes of every aligned run of 4^l positions (fold_aabb[l])
+    const uint32_t* fold_order;
+    const float4* fold_aabb[kFoldLevels + 1];
+    uint32_t fold_levels;  // group levels actually built (<= kFoldLevels)
     const float4* blas_leaf_aabb;  // [2 * n_blas_items] tri_aabb gathered into KDMesh leaf-item order (BlasLeaf reads it sequentially)
     double ambient[3];
     double tlas_extent;

@@ -886,13 +886,15 @@ void launch_gather_blas_leaf_boxes(const PtMesh* meshes, uint32_t n_meshes, cons
     gather_blas_leaf_boxes_kernel<<<grid, kBlock, 0, st>>>(meshes, n_meshes, blas_items, tri_aabb, out, n_blas_items);
 }
 
-// tri_aabb[n], l1[ceil(n / 32)], l2[ceil(n / 1024)]
-void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, float4* l1, float4* l2, cudaStream_t st) {
+void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, cudaStream_t st) {
     if (!n) return;
-    const uint32_t n1 = (n + 31u) / 32u, n2 = (n1 + 31u) / 32u;
     triangle_bounds_kernel<<<blocks_for(n), kBlock, 0, st>>>(tri_pos, n, tri_aabb);
-    group_bounds_kernel<<<blocks_for(n1), kBlock, 0, st>>>(tri_aabb, n, 32u, l1);
-    group_bounds_kernel<<<blocks_for(n2), kBlock, 0, st>>>(l1, n1, 32u, l2);
+}
+
+// out[ceil(n / run)] = union of every aligned run of `run` boxes of in[n]
+void launch_group_bounds(const float4* in, uint32_t n, uint32_t run, float4* out, cudaStream_t st) {
+    if (!n) return;
+    group_bounds_kernel<<<blocks_for((n + run - 1u) / run), kBlock, 0, st>>>(in, n, run, out);
 }
 
 cudaError_t upload_state(int slot, const FrameState& state, cudaStream_t st) {

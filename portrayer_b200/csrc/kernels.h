@@ -20,7 +20,14 @@ void launch_gather_leaf_boxes(const float4* inst_aabb, const uint32_t* items, ui
 // upload time: padded FP32 object-space boxes of all triangles + of every aligned run of 32 / 1024 of them
 void launch_gather_blas_leaf_boxes(const PtMesh* meshes, uint32_t n_meshes, const uint32_t* blas_items, const float4* tri_aabb, float4* out,
                                    uint32_t n_blas_items, cudaStream_t st);
-void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, float4* l1, float4* l2, cudaStream_t st);
+void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, cudaStream_t st);
+// fold structure of linear meshes (fold_order.cu, traverse.cuh mesh_fold)
+size_t fold_sort_temp_bytes(uint32_t n);
+size_t fold_scratch_bytes(uint32_t n, size_t temp_bytes);
+cudaError_t launch_fold_order(const PtMesh* meshes, uint32_t n_meshes, const PtTriPos* tri_pos, const double* mesh_bounds, uint32_t n, bool sort,
+                              uint32_t* order, void* scratch, size_t temp_bytes, int end_bit, cudaStream_t st);
+void launch_gather_fold_boxes(const float4* tri_aabb, const uint32_t* order, uint32_t n, float4* out, cudaStream_t st);
+void launch_group_bounds(const float4* in, uint32_t n, uint32_t run, float4* out, cudaStream_t st);
 
 // stream path: one launch per call; batch / level bookkeeping lives in the device control block
 void launch_camera(int slot, uint32_t first_slot, uint32_t n_slots, uint32_t samples, cudaStream_t st);

@@ -194,7 +194,8 @@ PT_D bool cone_t(V3 o, V3 d, double s, double e, double& t_out, uint32_t& part) 
 struct TriBary {
     double beta, gamma;
 };
-PT_D bool triangle_t(const PtTriPos* __restrict__ tp, V3 o, V3 dir, double s, double e_, double& t_out, TriBary* bary) {
+// `tie`: also accept t == e_ (only mesh_fold asks: it visits the triangles out of index order and settles exact ties itself)
+PT_D bool triangle_t(const PtTriPos* __restrict__ tp, V3 o, V3 dir, double s, double e_, double& t_out, TriBary* bary, bool tie = false) {
     const double* v = reinterpret_cast<const double*>(tp);
     const V3 A = v3(__ldg(v + 0), __ldg(v + 1), __ldg(v + 2));
     const V3 B = v3(__ldg(v + 3), __ldg(v + 4), __ldg(v + 5));
@@ -215,7 +216,7 @@ PT_D bool triangle_t(const PtTriPos* __restrict__ tp, V3 o, V3 dir, double s, do
     const double bl_ck = b * l - c * k;
 
     const double t = -(f * ak_jb + e * jc_al + d * bl_ck) / m;
-    if (!in_range(s, e_, t)) return false;
+    if (!in_range(s, e_, t) && !(tie && t == e_ && s <= t)) return false;
     const double gamma = (i * ak_jb + h * jc_al + g * bl_ck) / m;
     if (gamma < 0.0 || gamma > 1.0) return false;
     const double beta = (j * ei_hf + k * gf_di + l * dh_eg) / m;
@@ -408,48 +409,55 @@ struct BlasLeaf {
 };
 
 // Mesh::ray_hit's fold over EVERY triangle of the mesh in index order with a shrinking range (mesh.rs:157-167,
-// ray.rs:50-63), minus the triangles that certainly miss: every triangle has an FP32 box (DScene::tri_aabb), every
-// aligned run of 32 and of 1024 triangles the union of theirs (tri_aabb_l1 / _l2), all rounded outward and padded
-// like the instance boxes, built at upload by triangle_bounds_kernel.  A run (or a triangle) whose box the ray
-// certainly misses inside [s, e) is skipped; the survivors get the exact f64 test, still in index order, so the
-// accepted hits, the shrinking of e, ANY mode's "first accepted triangle" and the count of triangle tests the
-// reference makes (skipped ones included: they are tests the reference pays for) are those of the plain fold.
-// For OBJ meshes (index order is spatially coherent) a 5 804-triangle fold costs ~200 FP32 box tests and a few
-// dozen f64 triangle tests instead of 5 804 f64 tests.
+// ray.rs:50-63).  A triangle is accepted when its own test passes with t inside [s, e_now) and then e_now = t, so what
+// the fold returns is the triangle with the smallest t, and among exactly equal t the one with the smallest index: the
+// lexicographic minimum of (t, index) over the triangles whose test passes inside [s, e) — a quantity that does not
+// depend on the order of evaluation.  It is evaluated here in MORTON order of the triangle centroids (DScene::fold_order,
+// fold_order.cu), where consecutive positions are neighbours in space and the union boxes of aligned runs of 4, 16,
+// 64 ... 4096 positions (DScene::fold_aabb[1..]) form an implicit 4-ary hierarchy: a run whose padded FP32 box the ray
+// certainly misses inside [s, e_now] is skipped whole (coarsest aligned level first), a surviving triangle gets the exact
+// f64 test, ties on t are settled by index.  All boxes are rounded outward and padded like the instance boxes, and
+// the cull range is closed at e_now so that an exact tie is never culled.  ANY mode returns at the first accepted
+// triangle ("is there a hit" does not depend on the order either).  The count of triangle tests is the reference's:
+// all of them for a closest-hit fold.
+// A 5 804-triangle fold costs a few dozen FP32 box tests and a handful of f64 triangle tests instead of 5 804 f64 tests.
 template <bool ANY>
 PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3 o, V3 d, double s, double e, double& t_out,
                     uint32_t& sub, uint32_t& n_tests) {
     const RayF rf = make_rayf(o, d);
-    const float4* __restrict__ bb0 = sc.tri_aabb;
-    const float4* __restrict__ bb1 = sc.tri_aabb_l1;
-    const float4* __restrict__ bb2 = sc.tri_aabb_l2;
+    const uint32_t* __restrict__ order = sc.fold_order;
+    const float4* __restrict__ bb0 = sc.fold_aabb[0];
     const uint32_t end = tri_first + tri_count;
+    const int levels = (int)sc.fold_levels;
     bool found = false;
+    uint32_t best = 0xFFFFFFFFu;
     uint32_t k = tri_first;
     while (k < end) {
-        if ((k & 1023u) == 0u && !aabb_may_hit(bb2 + 2 * (size_t)(k >> 10), rf, s, e)) {
-            const uint32_t step = min(1024u, end - k);
-            n_tests += step;
-            k += step;
-            continue;
+        // the coarsest level this position starts a run of, then finer ones: one box test per visited node
+        int l = k ? min(levels, (__ffs((int)k) - 1) >> 1) : levels;
+        bool skipped = false;
+        for (; l >= 1; --l) {
+            if (!aabb_may_hit(sc.fold_aabb[l] + 2 * (size_t)(k >> (2 * l)), rf, s, e)) {
+                k = min(k + (1u << (2 * l)), end);
+                skipped = true;
+                break;
+            }
         }
-        if ((k & 31u) == 0u && !aabb_may_hit(bb1 + 2 * (size_t)(k >> 5), rf, s, e)) {
-            const uint32_t step = min(32u, end - k);
-            n_tests += step;
-            k += step;
-            continue;
-        }
-        ++n_tests;
+        if (skipped) continue;
         double tt;
-        if (aabb_may_hit(bb0 + 2 * (size_t)k, rf, s, e) && triangle_t(sc.tri_pos + k, o, d, s, e, tt, nullptr)) {
-            e = tt;
-            t_out = tt;
-            sub = k - tri_first;
-            found = true;
-            if (ANY) return true;
+        if (aabb_may_hit(bb0 + 2 * (size_t)k, rf, s, e)) {
+            const uint32_t idx = __ldg(order + k);
+            if (triangle_t(sc.tri_pos + idx, o, d, s, e, tt, nullptr, found) && (tt < e || idx < best)) {
+                if (ANY) { n_tests += 1u; t_out = tt; sub = idx - tri_first; return true; }
+                e = tt;
+                best = idx;
+                found = true;
+            }
         }
         ++k;
     }
+    n_tests += tri_count;
+    if (found) { t_out = e; sub = best - tri_first; }
     return found;
 }
 

@@ -20,7 +20,7 @@ for name in names:
     sc = pt.Scene.example(name)
     w, h = sc.width, sc.height
     bg, bg_mode = _background_arg(sc, w, h)
-    p = make_params(w, h, 1, "hash", 1, bg_mode=bg_mode)
+    p = make_params(w, h, int(os.environ.get("SAMPLES", "1")), "hash", 1, bg_mode=bg_mode)
     blob = torch.from_numpy(sc.blob.copy()).pin_memory().numpy()
     bgp = torch.from_numpy(np.ascontiguousarray(bg)).pin_memory().numpy()
     rgb = torch.zeros((h, w, 3), dtype=torch.uint8).pin_memory().numpy()
