@@ -111,8 +111,49 @@ ExampleScene edge_scene(int which) {
     return ex;
 }
 
+// Exact ties inside one linear Mesh: coplanar, overlapping triangles with small-integer coordinates in the plane
+// z = -4, listed so that INDEX order and spatial (Morton) order disagree, plus 400 filler triangles behind them.  For an
+// axis-aligned ray (0, 0, -1) from z = 0 every product in Triangle::ray_hit is exact, so all triangles covering a point
+// return t == 4.0 bit for bit and the fold's rule decides: the FIRST listed wins (ray.rs:50-63: later candidates need
+// t < e_now).  tests/: the oracle against the brute-force answer, the device fold (which visits triangles in Morton
+// order) against the oracle.
+ExampleScene mesh_ties() {
+    std::vector<Vec3> pos;
+    std::vector<std::array<size_t, 3>> tris;
+    auto tri = [&](Vec3 a, Vec3 b, Vec3 c) {
+        const size_t base = pos.size();
+        pos.push_back(a); pos.push_back(b); pos.push_back(c);
+        tris.push_back({base, base + 1, base + 2});
+    };
+    const double z = -4.0;
+    tri({8.0, 8.0, z}, {12.0, 8.0, z}, {8.0, 12.0, z});      // 0: small, far corner (high Morton)
+    tri({0.0, 0.0, z}, {16.0, 0.0, z}, {0.0, 16.0, z});      // 1: big, covers 0, 2, 3, 5
+    tri({0.0, 0.0, z}, {4.0, 0.0, z}, {0.0, 4.0, z});        // 2: small, near corner (low Morton), listed AFTER the big one
+    tri({2.0, 2.0, z}, {6.0, 2.0, z}, {2.0, 6.0, z});        // 3: small, overlaps 2 and 1
+    tri({0.0, 0.0, z}, {16.0, 0.0, z}, {0.0, 16.0, z});      // 4: the big one again
+    tri({1.0, 1.0, z}, {3.0, 1.0, z}, {1.0, 3.0, z});        // 5: inside 2
+    tri({20.0, 0.0, z}, {24.0, 0.0, z}, {20.0, 4.0, z});     // 6: alone
+    tri({20.0, 0.0, z}, {24.0, 0.0, z}, {20.0, 4.0, z});     // 7: its twin: loses to 6 everywhere
+    for (int j = 0; j < 20; ++j)                              // fillers behind (z = -8), some under the tie region
+        for (int i = 0; i < 20; ++i)
+            tri({(double)i, (double)j, -8.0}, {(double)i + 1.0, (double)j, -8.0}, {(double)i, (double)j + 1.0, -8.0});
+    auto data = std::make_shared<const MeshData>(std::move(pos), std::move(tris), std::vector<Vec3>{}, std::vector<Uv>{});
+    auto mat = Arc(Material{.diffuse = {0.2, 0.6, 0.9}});
+    ExampleScene ex;
+    ex.name = "edge-mesh-ties";
+    ex.scene = HierScene{.root = SceneNode::from(Geometry(Mesh(data, Shading::Flat), mat)).into(),
+                         .lights = {Light{.position = {8.0, 8.0, 20.0}, .color = {0.9, 0.9, 0.9}}},
+                         .ambient = {0.3, 0.3, 0.3}};
+    ex.cam = CameraSettings{.eye = {10.0, 8.0, 30.0}, .center = {10.0, 8.0, -4.0}, .up = Vec3::up(), .fovy = Radians::from_degrees(45.0)};
+    ex.width = 160;
+    ex.height = 120;
+    ex.background = sky_gradient;
+    return ex;
+}
+
 }  // namespace
 
+PORTRAYER_EXAMPLE(edge_mesh_ties, "edge-mesh-ties") { return mesh_ties(); }
 PORTRAYER_EXAMPLE(edge_empty, "edge-empty") { return edge_scene(0); }
 PORTRAYER_EXAMPLE(edge_no_lights, "edge-no-lights") { return edge_scene(1); }
 PORTRAYER_EXAMPLE(edge_degenerate, "edge-degenerate") { return edge_scene(2); }

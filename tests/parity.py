@@ -53,3 +53,30 @@ def compare(gpu_img: pt.Image, ref: "oracle.OracleResult", label: str = "") -> d
 def assert_parity(report: dict):
     assert report["rgb_within_1lsb"] >= RGB_MIN_FRACTION, report
     assert report["hit_id_mismatches"] == report["hit_id_grazing"], report
+
+
+def mesh_tie_rays():
+    """Axis-aligned rays over the edge-mesh-ties scene (host/examples/kats.cpp) and, by brute force, the triangle the
+    reference's index-order fold must return for each: the FIRST listed triangle of the z = -4 layer containing the
+    point (all of them return t == 4.0 exactly), else the filler cell behind it (t == 8.0), else a miss."""
+    layer = [((8, 8), (12, 8), (8, 12)), ((0, 0), (16, 0), (0, 16)), ((0, 0), (4, 0), (0, 4)), ((2, 2), (6, 2), (2, 6)),
+             ((0, 0), (16, 0), (0, 16)), ((1, 1), (3, 1), (1, 3)), ((20, 0), (24, 0), (20, 4)), ((20, 0), (24, 0), (20, 4))]
+    xs = np.arange(0.25, 26.0, 0.5)
+    ys = np.arange(0.25, 22.0, 0.5)
+    gx, gy = np.meshgrid(xs, ys)
+    px, py = gx.ravel(), gy.ravel()
+    origins = np.stack([px, py, np.zeros_like(px)], axis=1)
+    dirs = np.tile(np.array([0.0, 0.0, -1.0]), (len(px), 1))
+    expect_sub = np.full(len(px), -1, np.int64)
+    expect_t = np.full(len(px), np.inf)
+    for i, (x, y) in enumerate(zip(px, py)):
+        for k, ((ax, ay), (bx, by), (cx, cy)) in enumerate(layer):  # right triangles with legs along +x / +y from a
+            leg = bx - ax
+            if x >= ax and y >= ay and (x - ax) + (y - ay) <= leg:
+                expect_sub[i], expect_t[i] = k, 4.0
+                break
+        else:
+            cx_, cy_ = int(np.floor(x)), int(np.floor(y))
+            if 0 <= cx_ < 20 and 0 <= cy_ < 20 and (x - cx_) + (y - cy_) <= 1.0:
+                expect_sub[i], expect_t[i] = 8 + cy_ * 20 + cx_, 8.0
+    return origins, dirs, expect_sub, expect_t

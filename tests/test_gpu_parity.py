@@ -166,6 +166,21 @@ def test_ray_cast_edge_case_device(gpu_ready, name, origin, direction):
     assert hit_id[0, 0] == 0 and tuple(color[0]) == (1.0, 0.0, 0.0)
 
 
+# exact ties inside a linear Mesh: the device folds in Morton order (fold_order.cu) and must still return the FIRST
+# listed triangle among those with bit-identical t
+def test_mesh_fold_ties_device(gpu_ready):
+    scene = pt.Scene.example("edge-mesh-ties")
+    origins, dirs, expect_sub, expect_t = parity.mesh_tie_rays()
+    _c, hit_id, hit_t, _ = pt.DeviceScene(scene.blob).trace_rays(origins, dirs)
+    rc, _co, io, to, _ = oracle.trace_rays(scene.blob, origins, dirs)
+    assert rc == 0
+    assert np.array_equal(hit_id, io) and np.array_equal(hit_t, to)
+    hit = expect_sub >= 0
+    assert np.array_equal(hit_id[hit, 1].astype(np.int64), expect_sub[hit]) and np.array_equal(hit_t[hit], expect_t[hit])
+    # and through the camera path (shadow rays: any-hit folds) like every other scene
+    parity.assert_parity(_report("edge-mesh-ties", samples=2, rng="hash"))
+
+
 # src/kdtree/kdmesh.rs:99-166 on the device: Mesh == KDMesh bit-exact, and both == the oracle
 def test_mesh_equivalence_device(gpu_ready):
     mesh = pt.Scene.example("kat-mesh-equivalence-mesh")

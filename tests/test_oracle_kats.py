@@ -95,3 +95,21 @@ def test_castle_kd_plane_panic_is_reproduced(native_libraries):
         p = make_params(w, h, 64, "hash", 1, slice_=(px[0], px[1], px[0], px[1]), bg_mode=bg_mode)
         res = oracle.render(scene.blob, scene.camera(w, h), p, bg, threads=1)
         assert res.rc == expect
+
+
+def test_mesh_fold_ties_first_listed_wins():
+    """ray.rs:50-63 / mesh.rs:157-167: among triangles that return exactly the same t the first listed wins.  Pins the
+    oracle's fold against a brute-force answer on a mesh built to tie (the device's Morton-order fold is then held to
+    the oracle in test_gpu_parity.py)."""
+    import parity
+
+    scene = pt.Scene.example("edge-mesh-ties")
+    origins, dirs, expect_sub, expect_t = parity.mesh_tie_rays()
+    rc, _color, hit_id, hit_t, _ = oracle.trace_rays(scene.blob, origins, dirs)
+    assert rc == 0
+    hit = expect_sub >= 0
+    assert hit.sum() > 1000 and (expect_t == 4.0).sum() > 300
+    assert np.array_equal(hit_id[hit, 0], np.zeros(hit.sum(), np.uint32))
+    assert np.array_equal(hit_id[hit, 1].astype(np.int64), expect_sub[hit])
+    assert np.array_equal(hit_t[hit], expect_t[hit])
+    assert np.all(hit_id[~hit, 0] == 0xFFFFFFFF)
