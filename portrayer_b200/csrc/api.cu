@@ -462,7 +462,7 @@ int build_instance_bounds(PtScene* s) {
         if (!fold_scratch) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "fold order allocation failed: %s", cudaGetErrorString(e)); }
     }
     s->d_leaf_aabb = static_cast<float4*>(g_dev.alloc(leaf_box_count(s->h.n_tlas_items) * 2 * sizeof(float4), &e));
-    if (!s->d_leaf_aabb) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e)); }
+    if (!s->d_leaf_aabb) { g_dev.release(scratch); g_dev.release(fold_scratch); return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e)); }
     fill_view(s);
     launch_instance_bounds(s->view, s->h.n_meshes, scratch, s->d_aabb, g_stream);
     launch_gather_leaf_boxes(s->d_aabb, s->view.tlas_items, s->h.n_tlas_items, s->d_leaf_aabb, g_stream);
