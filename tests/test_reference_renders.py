@@ -64,3 +64,39 @@ def test_oracle_matches_published_render(name, samples, max_mae, min_psnr):
     psnr = 10.0 * np.log10(255.0 ** 2 / max(mse, 1e-12))
     print(f"{name}: MAE {mae:.3f} LSB, PSNR {psnr:.2f} dB, p99 {np.percentile(err, 99):.1f}")
     assert mae <= max_mae and psnr >= min_psnr, (name, mae, psnr)
+
+
+# The CUDA path against the reference's published renders, at the reference's own sample count (SAMPLES defaults to
+# 100, render.rs:107-113): the same statistical comparison as above, but with the sampling noise of OUR side gone too,
+# so the bounds are tighter than the oracle's low-sample ones.  -m gpu.
+GPU_CASES = [
+    ("primitives", 0.45, 47.0), ("primitives-simple", 0.45, 47.0), ("smooth-shading", 0.5, 46.0), ("glossy-reflection", 0.5, 47.0),
+    ("soft-shadows", 0.5, 47.0), ("normal-mapping", 0.7, 45.0), ("normal-mapping-left", 0.7, 45.0), ("normal-mapping-right", 0.7, 45.0),
+    ("water-glass", 1.2, 33.0),  # coplanar cap / table patch, see above
+    ("big-scene", 0.5, 46.0), ("entering-the-mirror-dimension", 0.5, 46.0), ("transmission-refraction", 0.6, 46.0),
+    ("robot-alarm-clock", 0.8, 44.0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,max_mae,min_psnr", GPU_CASES)
+def test_device_matches_published_render_at_100_samples(gpu_ready, name, max_mae, min_psnr):
+    if name in TEXTURED and not has_reference_assets():
+        pytest.skip("reference textures not synced (tools/sync_assets.py)")
+    golden = np.asarray(Image.open(os.path.join(GOLDEN, f"{name}.png")).convert("RGB")).astype(np.float64)
+    scene = pt.Scene.example(name)
+    img = pt.Image(scene.width, scene.height)
+    # Over the 1.4e9 rays of transmission-refraction at 100 samples ONE ray trips the reference's own
+    # "bug: ray should definitely hit infinite plane" expect (kdtree/node.rs:147,178; the README calls the kd-tree
+    # "occasionally buggy"); whether upstream's run met such a ray depends on its OS-seeded jitter.  The frame is
+    # finished (that ray treats the split as a miss) and the event stays in the stats.
+    from portrayer_b200 import _ffi
+    st = img.render(scene, samples=100, rng="hash", seed=11, flags=_ffi.PT_RENDER_TOLERATE_KD_PLANE)
+    assert st.device_error_bits == 0 or name == "transmission-refraction", hex(st.device_error_bits)
+    ours = _box_down(img.buffer, FACTOR)
+    assert ours.shape == golden.shape, (ours.shape, golden.shape)
+    err = np.abs(ours - golden)
+    mae = float(err.mean())
+    psnr = 10.0 * np.log10(255.0 ** 2 / max(float(((ours - golden) ** 2).mean()), 1e-12))
+    print(f"{name}: MAE {mae:.3f} LSB, PSNR {psnr:.2f} dB, p99 {np.percentile(err, 99):.1f}")
+    assert mae <= max_mae and psnr >= min_psnr, (name, mae, psnr)
