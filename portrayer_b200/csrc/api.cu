@@ -219,7 +219,10 @@ struct PtFrame {
     NodePool pool{};
     uint32_t n_lights_cap = 0;
     bool reflective_cap = false;
-    uint32_t batch_slots = 0;  // owned pixels per batch
+    uint32_t batch_slots = 0;  // owned pixels per batch the frame (graph, node pool) was sized for
+    // owned pixels per batch actually used (<= batch_slots): halved, for good, whenever a render of this frame ran out
+    // of node pool, so that a scene with deep ray trees pays for the discovery once and not on every render
+    uint32_t batch_slots_now = 0;
     BatchCtl* d_ctl = nullptr;
     BatchCtl* h_ctl = nullptr;  // pinned ring, one per batch
     uint32_t h_ctl_count = 0;
@@ -734,6 +737,7 @@ int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* p
     if (slots * p.samples > 0x7FFFFFFFull) slots = 0x7FFFFFFFull / p.samples;
     if (slots == 0) { free_frame(f); return fail(PT_ERR_INVALID, "samples too large"); }
     f->batch_slots = (uint32_t)slots;
+    f->batch_slots_now = f->batch_slots;
     const uint64_t batch_paths = slots * p.samples;
     uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * 4 : batch_paths);
     capacity = std::max<uint64_t>(capacity, batch_paths);
@@ -787,7 +791,7 @@ int render_stream_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void*
     KernelTimer timer;
     if (f->params.flags & PT_RENDER_KERNEL_TIMES) timer.events = &f->kernel_events;
     uint32_t first_slot = 0;
-    uint32_t batch_slots = f->batch_slots;
+    uint32_t batch_slots = std::max<uint32_t>(1, std::min(f->batch_slots_now, f->batch_slots));
     while (first_slot < owned) {
         const uint32_t n_slots = std::min(batch_slots, owned - first_slot);
         const uint32_t n_paths = n_slots * S;
@@ -825,12 +829,22 @@ int enqueue_graph_path(PtFrame* f, cudaStream_t st) {
     if (rc != PT_OK) return rc;
     const uint32_t owned = (uint32_t)f->pixel_index.size();
     const uint32_t S = f->params.samples;
-    const uint32_t n_batches = (owned + f->batch_slots - 1) / f->batch_slots;
-    if (n_batches > f->h_ctl_count) return fail(PT_ERR_INVALID, "frame has more batches than control-block slots");
+    const uint32_t per_batch = std::max<uint32_t>(1, std::min(f->batch_slots_now, f->batch_slots));
+    const uint32_t n_batches = (owned + per_batch - 1) / per_batch;
+    if (n_batches > f->h_ctl_count) {  // the batch size has been halved since the frame was created: a longer control-block ring
+        if (n_batches > (1u << 16)) return fail(PT_ERR_INVALID, "frame has more batches than control-block slots");
+        cudaError_t e = cudaSuccess;
+        BatchCtl* ring = static_cast<BatchCtl*>(g_pin.alloc(sizeof(BatchCtl) * n_batches, &e));
+        if (!ring) return fail(PT_ERR_CUDA, "control-block ring allocation failed: %s", cudaGetErrorString(e));
+        CUDA_TRY(cudaStreamSynchronize(st));  // nothing may still be copying into the old ring
+        g_pin.release(f->h_ctl);
+        f->h_ctl = ring;
+        f->h_ctl_count = n_batches;
+    }
     f->pending_batches.clear();
     uint32_t first_slot = 0;
     for (uint32_t b = 0; b < n_batches; ++b) {
-        const uint32_t n_slots = std::min(f->batch_slots, owned - first_slot);
+        const uint32_t n_slots = std::min(per_batch, owned - first_slot);
         CUDA_TRY(set_graph_batch(f->exec[k], f->camera_node[k], f->slot, first_slot, n_slots, f->batch_slots, S));
         CUDA_TRY(cudaGraphLaunch(f->exec[k], st));
         CUDA_TRY(cudaMemcpyAsync(&f->h_ctl[b], f->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
@@ -1180,12 +1194,31 @@ int pt_frame_finish(PtFrame* frame, PtStats* stats) {
         uint32_t launches = 0, batches = 0, error_bits = 0;
         bool overflow = false;
         collect_graph_path(f, f->progress, f->progress_user, &local, &launches, &batches, &error_bits, &overflow);
-        if (overflow) {
-            // node pool overflow: redo the frame with per-batch checks (results do not depend on batching)
+        // Node pool overflow: the ray trees of some batch did not fit.  Results do not depend on batching, so the frame
+        // is redone with batches half the size — on the same graph path, and the frame keeps the smaller batch for its
+        // later renders — a few times before the careful path (host check after every level, per-batch halving) takes over.
+        uint32_t graph_retries = 0;
+        while (overflow && graph_retries < 4 && f->batch_slots_now > 1) {
+            f->batch_slots_now = std::max<uint32_t>(1, f->batch_slots_now / 2);
+            ++graph_retries;
+            local = PtStats{};
+            launches = batches = error_bits = 0;
+            CUDA_TRY(cudaEventRecord(f->ev_start, f->pending_stream));
+            rc = enqueue_graph_path(f, f->pending_stream);
+            if (rc != PT_OK) break;
+            CUDA_TRY(cudaEventRecord(f->ev_stop, f->pending_stream));
+            CUDA_TRY(cudaEventSynchronize(f->ev_stop));
+            CUDA_TRY(cudaGetLastError());
+            collect_graph_path(f, f->progress, f->progress_user, &local, &launches, &batches, &error_bits, &overflow);
+        }
+        if (rc != PT_OK) {
+            // enqueue failed above: reported below
+        } else if (overflow) {
             local = PtStats{};
             CUDA_TRY(cudaEventRecord(f->ev_start, f->pending_stream));
-            rc = render_blocking_stream(f, f->pending_stream, f->progress, f->progress_user, &local, 1);
+            rc = render_blocking_stream(f, f->pending_stream, f->progress, f->progress_user, &local, 1 + graph_retries);
         } else {
+            local.retries = graph_retries;
             float ms = 0.f;
             CUDA_TRY(cudaEventElapsedTime(&ms, f->ev_start, f->ev_stop));
             local.device_ms = ms;
