@@ -49,6 +49,9 @@ WORKLOADS = {
                    label="configs[4]: examples/graphics-castle @ 3840x2160, SAMPLES=64, KD_DEPTH=10"),
     "castle-hd": dict(frames=["graphics-castle"], samples=4, size=(1920, 1080), scaling="strong", tolerate_kd_plane=True,
                       label="examples/graphics-castle @ native 1920x1080, SAMPLES=4, KD_DEPTH=10"),
+    # the two heaviest of the other example programs (linear meshes, area lights, dielectric / glossy materials)
+    "monkeys": dict(frames=["monkeys-making-monkeys"], samples=4, label="examples/monkeys-making-monkeys @ 1920x1080, SAMPLES=4"),
+    "robot": dict(frames=["robot-alarm-clock"], samples=4, label="examples/robot-alarm-clock @ 1920x1080, SAMPLES=4"),
     # configs[2], synthetic half: kd trees as deep as ceil(log2(N / 3))
     "synthetic-instances-1e5": dict(frames=["synthetic-instances:100000"], samples=1,
                                     label="configs[2]: synthetic 1e5 random instances @ 1980x1020, KD_DEPTH=16"),

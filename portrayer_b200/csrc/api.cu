@@ -240,7 +240,7 @@ struct PtFrame {
     // a render that has been enqueued but not finished (pt_frame_enqueue / pt_frame_finish)
     enum { IDLE, IN_FLIGHT, FINISHED } pending = IDLE;
     cudaStream_t pending_stream = nullptr;
-    std::vector<std::pair<uint32_t, uint32_t>> pending_batches;  // (n_slots, n_paths)
+    std::vector<std::pair<uint32_t, uint32_t>> pending_batches;  // (first_slot, n_slots) of the batches in flight, in ring order
     int pending_rc = PT_OK;
     std::string pending_error;
     PtProgressFn progress = nullptr;  // of the pt_frame_render call in progress
@@ -251,6 +251,10 @@ struct PtFrame {
 namespace {
 
 std::vector<PtFrame*> g_frame_cache;  // frames pt_render keeps between calls (LRU, small)
+// Ray-tree nodes the pool holds per path of a batch when a material reflects (129 B + 1 B / light each: 4.3 GB for the
+// default 4 Mi-path batch — HBM is 180 GB).  The reference's scenes average 2-5 nodes per path, but a batch that looks at
+// a dielectric needs far more, and every overflow costs that batch a second pass (pt_frame_finish).
+constexpr uint64_t kPoolNodesPerPath = 8;
 uint64_t g_frame_tick = 0;
 constexpr size_t kFrameCacheMax = 6;
 
@@ -739,7 +743,7 @@ int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* p
     f->batch_slots = (uint32_t)slots;
     f->batch_slots_now = f->batch_slots;
     const uint64_t batch_paths = slots * p.samples;
-    uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * 4 : batch_paths);
+    uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * kPoolNodesPerPath : batch_paths);
     capacity = std::max<uint64_t>(capacity, batch_paths);
     capacity = std::min<uint64_t>(capacity, 0xFFF00000ull);  // head room for the work cursors (every warp overshoots by <= 2 chunks)
     // the shadow kernel's 32-bit work cursor counts (hit, light) pairs
@@ -822,16 +826,14 @@ int render_stream_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void*
 
 // graph path, part 1: every batch is one replay of the frame graph; control blocks come back through a pinned ring.
 // Nothing here waits for the device.
-int enqueue_graph_path(PtFrame* f, cudaStream_t st) {
+int enqueue_ranges(PtFrame* f, cudaStream_t st, const std::vector<std::pair<uint32_t, uint32_t>>& ranges) {
     const bool count = (f->params.flags & PT_RENDER_COUNTERS) != 0;
     const int k = count ? 1 : 0;
     int rc = ensure_graph(f, count);
     if (rc != PT_OK) return rc;
-    const uint32_t owned = (uint32_t)f->pixel_index.size();
     const uint32_t S = f->params.samples;
-    const uint32_t per_batch = std::max<uint32_t>(1, std::min(f->batch_slots_now, f->batch_slots));
-    const uint32_t n_batches = (owned + per_batch - 1) / per_batch;
-    if (n_batches > f->h_ctl_count) {  // the batch size has been halved since the frame was created: a longer control-block ring
+    const size_t n_batches = ranges.size();
+    if (n_batches > f->h_ctl_count) {  // smaller batches than the frame was created with: a longer control-block ring
         if (n_batches > (1u << 16)) return fail(PT_ERR_INVALID, "frame has more batches than control-block slots");
         cudaError_t e = cudaSuccess;
         BatchCtl* ring = static_cast<BatchCtl*>(g_pin.alloc(sizeof(BatchCtl) * n_batches, &e));
@@ -839,36 +841,68 @@ int enqueue_graph_path(PtFrame* f, cudaStream_t st) {
         CUDA_TRY(cudaStreamSynchronize(st));  // nothing may still be copying into the old ring
         g_pin.release(f->h_ctl);
         f->h_ctl = ring;
-        f->h_ctl_count = n_batches;
+        f->h_ctl_count = (uint32_t)n_batches;
     }
-    f->pending_batches.clear();
-    uint32_t first_slot = 0;
-    for (uint32_t b = 0; b < n_batches; ++b) {
-        const uint32_t n_slots = std::min(per_batch, owned - first_slot);
-        CUDA_TRY(set_graph_batch(f->exec[k], f->camera_node[k], f->slot, first_slot, n_slots, f->batch_slots, S));
+    f->pending_batches = ranges;
+    for (size_t b = 0; b < n_batches; ++b) {
+        CUDA_TRY(set_graph_batch(f->exec[k], f->camera_node[k], f->slot, ranges[b].first, ranges[b].second, f->batch_slots, S));
         CUDA_TRY(cudaGraphLaunch(f->exec[k], st));
         CUDA_TRY(cudaMemcpyAsync(&f->h_ctl[b], f->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
-        f->pending_batches.emplace_back(n_slots, n_slots * S);
-        first_slot += n_slots;
     }
     return PT_OK;
 }
 
-// graph path, part 2 (after the stream / event has been waited for): read the control blocks.  *overflow = a batch
-// ran out of node pool; the caller then redoes the frame on the careful path.
+// [first, first + n) cut into batches of the frame's current batch size
+void split_range(const PtFrame* f, uint32_t first, uint32_t n, std::vector<std::pair<uint32_t, uint32_t>>* out) {
+    const uint32_t per_batch = std::max<uint32_t>(1, std::min(f->batch_slots_now, f->batch_slots));
+    for (uint32_t done = 0; done < n; done += per_batch) out->emplace_back(first + done, std::min(per_batch, n - done));
+}
+
+// A batch ran out of node pool.  pool_count keeps counting the allocations that were refused, so pool_count / capacity
+// is a LOWER bound of the shortfall (the refused children's own children never asked): the batch is cut by twice that,
+// rounded up to a power of two, and at least halved (a tighter 1.25 x was measured: more retry rounds, slower overall).
+uint32_t overflow_divisor(const PtFrame* f, const BatchCtl& c) {
+    const double want = 2.0 * (double)c.pool_count / (double)std::max<uint32_t>(f->pool.capacity, 1);
+    uint32_t div = 2;
+    while ((double)div < want && div < (1u << 16)) div *= 2;
+    return div;
+}
+// ... and the frame keeps the smaller batch for its later renders: a scene with deep ray trees pays for finding that
+// out once, not on every render
+void shrink_frame_batch(PtFrame* f, uint32_t div) {
+    f->batch_slots_now = std::max<uint32_t>(1, std::min(f->batch_slots_now, f->batch_slots) / std::max<uint32_t>(div, 1));
+}
+
+int enqueue_graph_path(PtFrame* f, cudaStream_t st) {
+    std::vector<std::pair<uint32_t, uint32_t>> ranges;
+    split_range(f, 0, (uint32_t)f->pixel_index.size(), &ranges);
+    return enqueue_ranges(f, st, ranges);
+}
+
+// graph path, part 2 (after the stream / event has been waited for): read the control blocks of the batches in flight.
+// Batches that ran out of node pool are returned in `failed` (their pixels are not final, nothing of them is counted),
+// after the frame's batch size has been shrunk by what they asked for.
+struct FailedBatch { uint32_t first, n, div; };
 void collect_graph_path(PtFrame* f, PtProgressFn progress, void* user, PtStats* stats, uint32_t* launches_out,
-                        uint32_t* batches_out, uint32_t* error_bits_out, bool* overflow) {
-    *overflow = false;
-    for (size_t b = 0; b < f->pending_batches.size(); ++b)
-        if (f->h_ctl[b].error_bits & PT_DEVERR_OVERFLOW) { *overflow = true; return; }
+                        uint32_t* batches_out, uint32_t* error_bits_out, std::vector<FailedBatch>* failed, bool whole_frame) {
+    failed->clear();
+    const uint32_t S = f->params.samples;
+    uint32_t max_div = 0;
     for (size_t b = 0; b < f->pending_batches.size(); ++b) {
         const BatchCtl& c = f->h_ctl[b];
-        *error_bits_out |= c.error_bits;
-        accumulate_stats(stats, c, f->pending_batches[b].second);
         *launches_out += 3 + c.levels_run * 3;
+        if (c.error_bits & PT_DEVERR_OVERFLOW) {
+            const uint32_t div = overflow_divisor(f, c);
+            failed->push_back({f->pending_batches[b].first, f->pending_batches[b].second, div});
+            max_div = std::max(max_div, div);
+            continue;
+        }
+        *error_bits_out |= c.error_bits;
+        accumulate_stats(stats, c, f->pending_batches[b].second * S);
         ++*batches_out;
-        if (progress) progress(user, f->pending_batches[b].first);
+        if (progress) progress(user, f->pending_batches[b].second);
     }
+    if (whole_frame && max_div) shrink_frame_batch(f, max_div);
 }
 
 }  // namespace
@@ -1191,34 +1225,39 @@ int pt_frame_finish(PtFrame* frame, PtStats* stats) {
         CUDA_TRY(cudaEventSynchronize(f->ev_stop));
         CUDA_TRY(cudaGetLastError());
         PtStats local{};
-        uint32_t launches = 0, batches = 0, error_bits = 0;
-        bool overflow = false;
-        collect_graph_path(f, f->progress, f->progress_user, &local, &launches, &batches, &error_bits, &overflow);
-        // Node pool overflow: the ray trees of some batch did not fit.  Results do not depend on batching, so the frame
-        // is redone with batches half the size — on the same graph path, and the frame keeps the smaller batch for its
-        // later renders — a few times before the careful path (host check after every level, per-batch halving) takes over.
-        uint32_t graph_retries = 0;
-        while (overflow && graph_retries < 4 && f->batch_slots_now > 1) {
-            f->batch_slots_now = std::max<uint32_t>(1, f->batch_slots_now / 2);
-            ++graph_retries;
-            local = PtStats{};
-            launches = batches = error_bits = 0;
-            CUDA_TRY(cudaEventRecord(f->ev_start, f->pending_stream));
-            rc = enqueue_graph_path(f, f->pending_stream);
+        uint32_t launches = 0, batches = 0, error_bits = 0, retries = 0;
+        std::vector<FailedBatch> failed;
+        std::vector<std::pair<uint32_t, uint32_t>> again;
+        collect_graph_path(f, f->progress, f->progress_user, &local, &launches, &batches, &error_bits, &failed, true);
+        // Node pool overflow: the ray trees of some batches did not fit.  Results do not depend on batching and batches
+        // are independent, so ONLY those batches are redone, each cut by what it asked for (overflow_divisor); when most
+        // of the frame overflowed, the frame also keeps a smaller batch for its later renders (collect_graph_path).  The
+        // careful path (host check after every level) remains as the last resort.
+        while (rc == PT_OK && !failed.empty() && retries < 8) {
+            ++retries;
+            again.clear();
+            bool stuck = false;
+            for (const FailedBatch& r : failed) {
+                if (r.n <= 1) { stuck = true; break; }  // a single pixel whose ray trees do not fit
+                const uint32_t piece = std::max<uint32_t>(1, r.n / r.div);
+                for (uint32_t done = 0; done < r.n; done += piece) again.emplace_back(r.first + done, std::min(piece, r.n - done));
+            }
+            if (stuck) break;
+            rc = enqueue_ranges(f, f->pending_stream, again);
             if (rc != PT_OK) break;
             CUDA_TRY(cudaEventRecord(f->ev_stop, f->pending_stream));
             CUDA_TRY(cudaEventSynchronize(f->ev_stop));
             CUDA_TRY(cudaGetLastError());
-            collect_graph_path(f, f->progress, f->progress_user, &local, &launches, &batches, &error_bits, &overflow);
+            collect_graph_path(f, f->progress, f->progress_user, &local, &launches, &batches, &error_bits, &failed, false);
         }
         if (rc != PT_OK) {
             // enqueue failed above: reported below
-        } else if (overflow) {
+        } else if (!failed.empty()) {
             local = PtStats{};
             CUDA_TRY(cudaEventRecord(f->ev_start, f->pending_stream));
-            rc = render_blocking_stream(f, f->pending_stream, f->progress, f->progress_user, &local, 1 + graph_retries);
+            rc = render_blocking_stream(f, f->pending_stream, f->progress, f->progress_user, &local, 1 + retries);
         } else {
-            local.retries = graph_retries;
+            local.retries = retries;
             float ms = 0.f;
             CUDA_TRY(cudaEventElapsedTime(&ms, f->ev_start, f->ev_stop));
             local.device_ms = ms;
