@@ -116,3 +116,19 @@ def test_product_code_never_touches_the_oracle():
                     if pattern.search(open(os.path.join(dirpath, f), errors="ignore").read()):
                         offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/portrayer_gpu.h is what a cgo / bindgen / ctypes consumer compiles: it must be valid C99 on its own
+    (no C++ types, no torch, no CUDA headers) and valid C++ for the host mirror."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "portrayer_gpu.h"\nint main(void) { PtPeerHandle h; PtStats s; (void)h; (void)s; return 0; }\n')
+    inc = os.path.join(REPO, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    if shutil.which("g++"):
+        subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
