@@ -427,6 +427,8 @@ def run_ours(args, rank, world, local_rank):
     local_ms = sum(step_ms)
     rays_per_step_local = sum(st.rays for st in step_stats[0])
     launches_local = sum(st.kernel_launches for sts in step_stats for st in sts)
+    # batches that ran out of node pool inside the timed steps and were redone (their first attempt is in the timed region too)
+    overflow_retries = sum(st.retries for sts in step_stats for st in sts)
     t = torch.tensor([local_ms], dtype=torch.float64, device=dev)
     r = torch.tensor([float(rays_per_step_local), float(launches_local)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -626,6 +628,7 @@ def run_ours(args, rank, world, local_rank):
                    "exchange": None if world == 1 else ("resolve kernel stores tiles into rank 0's image over peer memory (NVLink) + "
                                                         "1-element all-reduce" if peer is not None else "NCCL gather + un-tiling on rank 0"),
                    "exchange_verified_against_nccl_gather": exchange_verified,
+                   "node_pool_retry_rounds_in_timed_steps": int(overflow_retries),
                    "reference_panics_tolerated": panics},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(r[1].item()), "roofline": roofline, "roofline_fp64": roofline_fp64,
         "cpu_baseline": cpu,
