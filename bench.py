@@ -338,6 +338,18 @@ def run_ours(args, rank, world, local_rank):
     side_streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
     all_streams = [stream] + [s_.cuda_stream for s_ in side_streams]
 
+    # which stream a frame goes to: round-robin until the frames' costs are known (the counting pass below measures
+    # them), then longest-processing-time-first onto the least loaded stream, so that no stream is left finishing a
+    # long chain of frames alone while the others idle
+    stream_of = [k % len(all_streams) for k in range(len(jobs))]
+
+    def balance_streams(costs):
+        load = [0.0] * len(all_streams)
+        for k in sorted(range(len(jobs)), key=lambda i: -costs[i]):
+            t = min(range(len(load)), key=lambda i: load[i])
+            stream_of[k] = t
+            load[t] += costs[k]
+
     def step(collect=None):
         """one pass over the workload, device-resident; returns device ms (torch events on the launch stream)"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -348,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
         for side in side_streams:
             side.wait_event(e0)
         for k, j in enumerate(jobs):
-            j.frame.enqueue(stream=all_streams[k % len(all_streams)])
+            j.frame.enqueue(stream=all_streams[stream_of[k]])
         for side in side_streams:
             ev = torch.cuda.Event()
             ev.record(side)
@@ -380,6 +392,8 @@ def run_ours(args, rank, world, local_rank):
         counted.append(fr.render(stream=stream))
         fr.close()
 
+    if args.balance and len(all_streams) > 1:
+        balance_streams([max(float(st.device_ms), 1e-6) for st in counted])  # device time of each frame's counting pass
     for _ in range(args.warmup):
         flush.zero_()
         step()
@@ -623,7 +637,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": wl["label"], "frames_per_step": len(jobs), "samples": samples, "rng": "hash", "seed": SEED,
                    "rays_per_step": rays_per_step, "ms_per_frame": total_ms / args.steps / len(jobs),
                    "l2": "flushed between timed steps (256 MB write)", "tile": "32x32 interleaved over ranks",
-                   "streams": n_streams,
+                   "streams": n_streams, "stream_of_frame": list(stream_of),
                    "parallelism": f"tiles x{world}", "scene_broadcast_ms": scene_broadcast_ms,
                    "exchange": None if world == 1 else ("resolve kernel stores tiles into rank 0's image over peer memory (NVLink) + "
                                                         "1-element all-reduce" if peer is not None else "NCCL gather + un-tiling on rank 0"),
@@ -645,6 +659,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="configs1")
     ap.add_argument("--samples", type=int, default=0, help="samples per pixel at N=1 (default: the workload's)")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the frames of a step are spread over (1 = back to back on one)")
+    ap.add_argument("--no-balance", dest="balance", action="store_false",
+                    help="keep the frames round-robin over the streams instead of balancing the streams by the frames' measured device times")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
                     help="N > 1: how the tiles reach rank 0 (peer: stored by the resolve kernel into rank 0's image over NVLink; nccl: gather)")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e and cpu_baseline legs (for runs under ncu)")
