@@ -61,3 +61,25 @@ def test_last_two_examples_build_with_the_expected_instance_counts(native_librar
     assert (sc.width, sc.height, sc.header.n_instances, sc.header.n_lights) == (1920, 1080, 26, 2)
     sc = pt.Scene.example("graphics-temple")
     assert (sc.width, sc.height, sc.header.n_instances, sc.header.n_lights) == (533, 300, 97, 1)
+
+
+def test_scene_programs_agree_with_the_reference_sources(native_libraries):
+    """Where the reference checkout is present (this container; not the GPU box): every scene program's image size and
+    light count against what its examples/*.rs says (`Image::new(.., W, H)`, `Light {` literals, comments skipped)."""
+    import re
+
+    import pytest
+
+    import portrayer_b200 as pt
+    from conftest import has_reference_assets
+
+    examples = "/root/reference/examples"
+    if not os.path.isdir(examples) or not has_reference_assets():
+        pytest.skip("reference checkout not present")
+    for name in REFERENCE_EXAMPLES:
+        code = "\n".join(l for l in open(os.path.join(examples, name + ".rs")).read().splitlines() if not l.strip().startswith("//"))
+        sizes = re.findall(r"Image::new\([^;]*?,\s*(\d+)\s*,\s*(\d+)\s*\)", code)
+        assert sizes, name
+        scene = pt.Scene.example(name)
+        assert (int(sizes[-1][0]), int(sizes[-1][1])) == (scene.width, scene.height), (name, sizes, scene.width, scene.height)
+        assert len(re.findall(r"\bLight\s*\{", code)) == scene.header.n_lights, name
