@@ -30,6 +30,17 @@
 
 #include "oracle.h"
 
+/* analysis hooks: no-ops unless a tool that #includes this file defines them (tools/leafstats) */
+#ifndef ORACLE_HOOK_SCENE_CAST
+#define ORACLE_HOOK_SCENE_CAST(kind, depth) ((void)0)
+#endif
+#ifndef ORACLE_HOOK_TLAS_LEAF
+#define ORACLE_HOOK_TLAS_LEAF(cx, first, count, ray, range) ((void)0)
+#endif
+#ifndef ORACLE_HOOK_BLAS_LEAF
+#define ORACLE_HOOK_BLAS_LEAF(cx, tr, first, count, ray, range) ((void)0)
+#endif
+
 #define EPSILON PT_EPSILON /* src/math.rs:15 */
 #define GAMMA PT_GAMMA     /* src/math.rs:20 */
 #define PI 3.14159265358979323846264338327950288
@@ -517,6 +528,7 @@ static int leaf_cast(Ctx* cx, const Tree* tr, uint32_t first, uint32_t count, co
                      uint32_t* out_inst) {
     int found = 0;
     if (tr->is_blas) {
+        ORACLE_HOOK_BLAS_LEAF(cx, tr, first, count, ray, range);
         Range r = *range; /* [T]::ray_hit clones the range, ray.rs:52 */
         for (uint32_t k = 0; k < count; ++k) {
             Isect hit;
@@ -528,6 +540,7 @@ static int leaf_cast(Ctx* cx, const Tree* tr, uint32_t first, uint32_t count, co
         }
         if (found) range->end = out->ray_parameter; /* node.rs:40-46 */
     } else {
+        ORACLE_HOOK_TLAS_LEAF(cx, first, count, ray, range);
         for (uint32_t k = 0; k < count; ++k) {
             Isect hit;
             uint32_t inst = tr->items[first + k];
@@ -759,6 +772,7 @@ static void hit_color(Ctx* cx, const PtMaterial* mat, const double* background, 
         uint32_t sh_inst;
         cx->st.rays_shadow++;
         const OracleStats before = cx->st;
+        ORACLE_HOOK_SCENE_CAST(3, depth);
         const int shadowed = scene_ray_cast(cx, &shadow_ray, &shadow_range, &sh, &sh_inst); /* material.rs:174-179 */
         cx->st.shadow_kd_splits += cx->st.kd_splits - before.kd_splits;
         cx->st.shadow_instance_tests += cx->st.instance_tests - before.instance_tests;
@@ -867,6 +881,7 @@ static void ray_color(Ctx* cx, const Ray* ray, const double* background, uint32_
     Range t_range = {EPSILON, INFINITY};
     Isect hit;
     uint32_t inst = 0xFFFFFFFFu;
+    ORACLE_HOOK_SCENE_CAST(ray_kind, depth);
     if (scene_ray_cast(cx, ray, &t_range, &hit, &inst)) {
         if (hit_id) { hit_id[0] = inst; hit_id[1] = hit.sub; }
         if (hit_t) *hit_t = hit.ray_parameter;

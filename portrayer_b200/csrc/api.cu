@@ -59,6 +59,22 @@ double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// PT_DEBUG_SYNC=1: synchronise the library stream after every upload-time stage and say which one just finished
+// (stderr) — for locating a hanging or faulting kernel on a box without a debugger
+void debug_sync(const char* stage) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PT_DEBUG_SYNC");
+        on = (e && *e && *e != '0') ? 1 : 0;
+    }
+    if (!on) return;
+    fprintf(stderr, "[pt] %s ...", stage);
+    fflush(stderr);
+    const cudaError_t e = cudaStreamSynchronize(g_stream);
+    fprintf(stderr, " %s\n", cudaGetErrorString(e));
+    fflush(stderr);
+}
+
 int ensure_init() {
     if (g_initialised) return PT_OK;
     return pt_init(-1);
@@ -175,9 +191,11 @@ struct PtScene {
     bool has_reflective = false;
     TextureDev* d_textures = nullptr;
     float4* d_aabb = nullptr;               // padded FP32 world box per instance (conservative cull, traverse.cuh)
-    float4* d_leaf_aabb = nullptr;          // d_aabb gathered into scene-tree leaf order
-    float4* d_tri_aabb = nullptr;           // padded FP32 object box per triangle + per run of 32 / 1024 (one allocation)
-    uint32_t tri_aabb_leaf = 0;                 // offset (in boxes) of the KDMesh leaf-ordered copy inside d_tri_aabb
+    float4* d_tl_cull = nullptr;            // leaf cull structure of the scene tree (leaf_cull.cu): two box sets + the root box (last 2 float4)
+    float4* d_bl_cull = nullptr;            // ... of the KDMesh trees
+    ptd::LeafCull tl_cull{}, bl_cull{};
+    std::vector<ptd::LcTree> blas_trees;    // where each KDMesh tree lies in blas_nodes / blas_items / tri_pos
+    float4* d_tri_aabb = nullptr;           // padded FP32 object box per triangle + the Mesh fold levels (one allocation)
     // Mesh fold structure (traverse.cuh mesh_fold): Morton order of every linear mesh's triangles, boxes in that order
     // and 4-ary group levels, all inside d_tri_aabb / d_fold_order
     uint32_t* d_fold_order = nullptr;
@@ -310,14 +328,14 @@ void fill_view(PtScene* s) {
     v.lights = reinterpret_cast<const PtLight*>(b + h.off_lights);
     v.textures = s->d_textures;
     v.inst_aabb = s->d_aabb;
-    v.leaf_aabb = s->d_leaf_aabb;
-    v.leaf_grp_aabb = s->d_leaf_aabb ? s->d_leaf_aabb + 2 * (size_t)s->h.n_tlas_items : nullptr;
+    v.tl_cull = s->tl_cull;
+    v.bl_cull = s->bl_cull;
+    v.tl_root = s->d_tl_cull ? s->d_tl_cull + 2 * ptd::leaf_cull_sizes(s->h.n_tlas_nodes, s->h.n_tlas_items).set_float4 : nullptr;
     v.tri_aabb = s->d_tri_aabb;
     v.fold_order = s->d_fold_order;
     for (int l = 0; l <= ptd::kFoldLevels; ++l)
         v.fold_aabb[l] = s->d_tri_aabb && l <= (int)s->fold_levels ? s->d_tri_aabb + 2 * (size_t)s->fold_off[l] : nullptr;
     v.fold_levels = s->fold_levels;
-    v.blas_leaf_aabb = s->d_tri_aabb ? s->d_tri_aabb + 2 * (size_t)s->tri_aabb_leaf : nullptr;
     v.gamma_lut = g_gamma_lut;
     v.ambient[0] = h.ambient[0]; v.ambient[1] = h.ambient[1]; v.ambient[2] = h.ambient[2];
     v.tlas_extent = h.tlas_extent;
@@ -338,7 +356,8 @@ void free_scene(PtScene* s) {
     g_dev.release(s->d_aabb);
     g_dev.release(s->d_tri_aabb);
     g_dev.release(s->d_fold_order);
-    g_dev.release(s->d_leaf_aabb);
+    g_dev.release(s->d_tl_cull);
+    g_dev.release(s->d_bl_cull);
     g_dev.release(s->d_own_tlas_nodes);
     g_dev.release(s->d_own_tlas_items);
     g_dev.release(s->d_own_instances);
@@ -363,6 +382,14 @@ int adopt_header(PtScene* s, const void* host_blob, uint64_t bytes, bool* texels
     // Mesh fold order: sort when a linear mesh is big enough to gain from it; the sort keys assume that two meshes'
     // triangle ranges are either the same range or disjoint (what the packer emits) — anything else keeps index order
     s->fold_sort = false;
+    s->blas_trees.clear();
+    for (uint32_t i = 0; i < d.n_meshes; ++i) {
+        const PtMesh& m = d.meshes[i];
+        if (m.kind != PT_MESH_KD || m.node_count == 0) continue;
+        bool seen = false;  // several meshes may share one tree (instanced KDMesh): build its boxes once
+        for (const ptd::LcTree& t : s->blas_trees) seen = seen || (t.node_first == m.node_first && t.item_first == m.item_first);
+        if (!seen) s->blas_trees.push_back(ptd::LcTree{m.node_first, m.node_count, m.item_first, m.tri_first});
+    }
     {
         std::vector<std::pair<uint32_t, uint32_t>> ranges;
         for (uint32_t i = 0; i < d.n_meshes; ++i) {
@@ -435,24 +462,65 @@ int bind_textures(PtScene* s, const PtTexture* tex, const unsigned char* texel_s
     return PT_OK;
 }
 
-// boxes behind DScene::leaf_aabb + leaf_grp_aabb: one per leaf position, one per aligned run of 8 positions
-size_t leaf_box_count(uint32_t n_items) { return std::max<size_t>((size_t)n_items + ((size_t)n_items + 7) / 8, 1); }
+ptd::KdAllocator arena_allocator() {
+    ptd::KdAllocator al;
+    al.alloc = [](size_t bytes, cudaError_t* err) { return g_dev.alloc(bytes, err); };
+    al.release = [](void* p) { g_dev.release(p); };
+    return al;
+}
+
+// leaf cull structure (leaf_cull.cu) of one forest; `extra` float4 are appended to the storage (the scene tree keeps its root box there)
+int build_leaf_cull(PtKdNode* d_nodes, uint32_t n_nodes, const uint32_t* d_items, uint32_t n_items, const std::vector<ptd::LcTree>& trees,
+                    const float4* d_item_boxes, size_t extra, float4** d_storage, ptd::LeafCull* out) {
+    const ptd::LeafCullSizes sz = ptd::leaf_cull_sizes(n_nodes, n_items);
+    cudaError_t e;
+    g_dev.release(*d_storage);
+    *d_storage = static_cast<float4*>(g_dev.alloc((2 * sz.set_float4 + extra) * sizeof(float4), &e));
+    if (!*d_storage) return fail(PT_ERR_CUDA, "leaf cull allocation failed: %s", cudaGetErrorString(e));
+    void* scratch = g_dev.alloc(sz.scratch_bytes + std::max<size_t>(trees.size(), 1) * sizeof(ptd::LcTree), &e);
+    if (!scratch) return fail(PT_ERR_CUDA, "leaf cull scratch allocation failed: %s", cudaGetErrorString(e));
+    ptd::LcTree* d_trees = reinterpret_cast<ptd::LcTree*>(static_cast<unsigned char*>(scratch) + sz.scratch_bytes);
+    if (!trees.empty()) {
+        // pageable source: staged before the call returns
+        e = cudaMemcpyAsync(d_trees, trees.data(), trees.size() * sizeof(ptd::LcTree), cudaMemcpyHostToDevice, g_stream);
+        if (e != cudaSuccess) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "leaf cull upload failed: %s", cudaGetErrorString(e)); }
+    }
+    debug_sync("leaf cull: before launch");
+    e = ptd::launch_leaf_cull(d_nodes, n_nodes, d_items, n_items, d_trees, (uint32_t)trees.size(), d_item_boxes, *d_storage, scratch,
+                              arena_allocator(), out, g_stream);
+    debug_sync("leaf cull: built");
+    g_dev.release(scratch);  // stream-ordered reuse
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "leaf cull build failed: %s", cudaGetErrorString(e));
+    return PT_OK;
+}
+
+// the scene tree's cull structure + root box; needs d_aabb and the current tree in the view
+int build_tlas_cull(PtScene* s) {
+    fill_view(s);
+    const std::vector<ptd::LcTree> one{ptd::LcTree{0u, s->h.n_tlas_nodes, 0u, 0u}};
+    int rc = build_leaf_cull(const_cast<PtKdNode*>(s->view.tlas_nodes), s->h.n_tlas_nodes, s->view.tlas_items, s->h.n_tlas_items, one, s->d_aabb,
+                             2, &s->d_tl_cull, &s->tl_cull);
+    if (rc != PT_OK) return rc;
+    ptd::launch_root_box(s->d_aabb, s->h.n_instances, s->d_tl_cull + 2 * ptd::leaf_cull_sizes(s->h.n_tlas_nodes, s->h.n_tlas_items).set_float4, g_stream);
+    debug_sync("root box");
+    fill_view(s);
+    return PT_OK;
+}
 
 // instance boxes for the FP32 cull, computed on the device from the uploaded records
-int build_instance_bounds(PtScene* s) {
+int build_instance_bounds(PtScene* s, bool with_tlas = true) {
     const uint32_t n = s->h.n_instances;
     cudaError_t e;
     s->d_aabb = static_cast<float4*>(g_dev.alloc(std::max<size_t>(n, 1) * 2 * sizeof(float4), &e));
     if (!s->d_aabb) return fail(PT_ERR_CUDA, "instance bounds allocation failed: %s", cudaGetErrorString(e));
     double* scratch = static_cast<double*>(g_dev.alloc(std::max<size_t>(s->h.n_meshes, 1) * 6 * sizeof(double), &e));
     if (!scratch) return fail(PT_ERR_CUDA, "mesh bounds allocation failed: %s", cudaGetErrorString(e));
-    // triangle boxes: index order, KDMesh leaf-item order, and the Mesh fold structure (Morton order + 4-ary group levels)
+    // triangle boxes: index order and the Mesh fold structure (Morton order + 4-ary group levels)
     const uint32_t nt = s->h.n_triangles;
     void* fold_scratch = nullptr;
     size_t fold_temp = 0;
     if (nt) {
-        s->tri_aabb_leaf = nt;
-        uint32_t off = nt + s->h.n_blas_items, n_level = nt;
+        uint32_t off = nt, n_level = nt;
         s->fold_levels = 0;
         for (int l = 0; l <= ptd::kFoldLevels; ++l) {
             s->fold_off[l] = off;
@@ -468,16 +536,12 @@ int build_instance_bounds(PtScene* s) {
         if (s->d_fold_order) fold_scratch = g_dev.alloc(fold_scratch_bytes(nt, fold_temp), &e);
         if (!fold_scratch) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "fold order allocation failed: %s", cudaGetErrorString(e)); }
     }
-    s->d_leaf_aabb = static_cast<float4*>(g_dev.alloc(leaf_box_count(s->h.n_tlas_items) * 2 * sizeof(float4), &e));
-    if (!s->d_leaf_aabb) { g_dev.release(scratch); g_dev.release(fold_scratch); return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e)); }
     fill_view(s);
+    debug_sync("records + textures uploaded");
     launch_instance_bounds(s->view, s->h.n_meshes, scratch, s->d_aabb, g_stream);
-    launch_gather_leaf_boxes(s->d_aabb, s->view.tlas_items, s->h.n_tlas_items, s->d_leaf_aabb, g_stream);
+    debug_sync("instance bounds");
     if (nt) {
         launch_triangle_bounds(s->view.tri_pos, nt, s->d_tri_aabb, g_stream);
-        if (s->h.n_blas_items)
-            launch_gather_blas_leaf_boxes(s->view.meshes, s->h.n_meshes, s->view.blas_items, s->d_tri_aabb,
-                                          s->d_tri_aabb + 2 * (size_t)s->tri_aabb_leaf, s->h.n_blas_items, g_stream);
         int end_bit = 33;
         while (end_bit < 64 && (nt >> (end_bit - 32)) != 0) ++end_bit;
         const cudaError_t se = launch_fold_order(s->view.meshes, s->h.n_meshes, s->view.tri_pos, scratch, nt, s->fold_sort, s->d_fold_order,
@@ -490,11 +554,18 @@ int build_instance_bounds(PtScene* s) {
             n_level = (n_level + 3u) / 4u;
         }
         g_dev.release(fold_scratch);
+        debug_sync("triangle bounds + fold structure");
     }
     g_dev.release(scratch);  // stream-ordered reuse: later users of the block run after this kernel on g_stream
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "instance bounds kernel failed: %s", cudaGetErrorString(e));
-    return PT_OK;
+    // leaf cull structures: KDMesh trees (the blob's node records, patched in place), then the scene tree
+    int rc = build_leaf_cull(const_cast<PtKdNode*>(s->view.blas_nodes), s->h.n_blas_nodes, s->view.blas_items, s->h.n_blas_items, s->blas_trees,
+                             s->d_tri_aabb, 0, &s->d_bl_cull, &s->bl_cull);
+    if (rc != PT_OK) return rc;
+    if (with_tlas) rc = build_tlas_cull(s);
+    else fill_view(s);
+    return rc;
 }
 
 void destroy_graphs(PtFrame* f) {
@@ -1565,9 +1636,7 @@ int pt_kd_build_device(const double* d_bounds, uint32_t n, const PtKdBuildConfig
     rc = ensure_init();
     if (rc != PT_OK) return rc;
     ptd::KdTreeDev* dev = nullptr;
-    ptd::KdAllocator al;
-    al.alloc = [](size_t bytes, cudaError_t* err) { return g_dev.alloc(bytes, err); };
-    al.release = [](void* p) { g_dev.release(p); };
+    ptd::KdAllocator al = arena_allocator();
     const cudaError_t e = ptd::kd_build_device(d_bounds, n, *config, al, stream ? (cudaStream_t)stream : g_stream, &dev);
     if (e == cudaErrorInvalidValue) return fail(PT_ERR_INVALID, "k-d tree does not fit 30-bit node / item indices");
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "k-d tree build failed: %s", cudaGetErrorString(e));
@@ -1658,11 +1727,8 @@ int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree) {
     scene->h.tlas_depth = ptd::kd_tree_depth(tree->dev);
     scene->h.n_tlas_nodes = nn;
     scene->h.n_tlas_items = ni;
-    float4* d_leaf = static_cast<float4*>(g_dev.alloc(leaf_box_count(ni) * 2 * sizeof(float4), &e));
-    if (!d_leaf) return fail(PT_ERR_CUDA, "leaf bounds allocation failed: %s", cudaGetErrorString(e));
-    g_dev.release(scene->d_leaf_aabb);
-    scene->d_leaf_aabb = d_leaf;
-    launch_gather_leaf_boxes(scene->d_aabb, d_items, ni, d_leaf, g_stream);
+    int rc = build_tlas_cull(scene);
+    if (rc != PT_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     fill_view(scene);
     return PT_OK;
@@ -1697,9 +1763,7 @@ int pt_flatten(const PtHierNode* nodes, uint32_t n_nodes, const uint32_t* childr
     if (e == cudaSuccess && n_geometries)
         e = cudaMemcpyAsync(d_geoms, geometries, (size_t)n_geometries * sizeof(PtGeometryRec), cudaMemcpyHostToDevice, g_stream);
     if (e != cudaSuccess) { cleanup(); return fail(PT_ERR_CUDA, "hierarchy upload failed: %s", cudaGetErrorString(e)); }
-    ptd::KdAllocator al;
-    al.alloc = [](size_t bytes, cudaError_t* err) { return g_dev.alloc(bytes, err); };
-    al.release = [](void* p) { g_dev.release(p); };
+    ptd::KdAllocator al = arena_allocator();
     ptd::FlatSceneDev* dev = nullptr;
     e = ptd::flatten_device(d_nodes, n_nodes, d_children, n_children, root, d_geoms, /*max_levels=*/n_nodes, al, g_stream, &dev);
     cleanup();
@@ -1757,12 +1821,11 @@ int pt_scene_set_instances(PtScene* scene, const PtFlatScene* flat, const PtKdTr
     scene->h.n_instances = n;
     // the FP32 instance boxes depend on the instances: rebuild them, then splice the tree in (which re-gathers the leaf boxes)
     g_dev.release(scene->d_aabb);
-    g_dev.release(scene->d_leaf_aabb);
     g_dev.release(scene->d_tri_aabb);
     g_dev.release(scene->d_fold_order);
-    scene->d_aabb = scene->d_leaf_aabb = scene->d_tri_aabb = nullptr;
+    scene->d_aabb = scene->d_tri_aabb = nullptr;
     scene->d_fold_order = nullptr;
-    int rc = build_instance_bounds(scene);
+    int rc = build_instance_bounds(scene, /*with_tlas=*/false);  // the old tree's items index the old instances
     if (rc != PT_OK) return rc;
     return pt_scene_set_tlas(scene, tree);
 }

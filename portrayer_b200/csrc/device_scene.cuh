@@ -16,6 +16,17 @@ struct TextureDev {
     const uint8_t* texels;
 };
 
+// Leaf cull structure of one forest of k-d trees (leaf_cull.cu): per leaf an "occupied" box, per run of 8 list positions
+// a union box, per position the candidate's box clipped to the leaf's cell; the same arrays with unclipped boxes lie
+// `set_stride` float4 further on.  A leaf node's `split` field in the device copy of the tree carries rank | gbase << 32.
+struct LeafCull {
+    float4* occ;          // [2 * leaves]       occ[2 * rank], occ[2 * rank + 1] = lo, hi
+    float4* grp;          // [2 * runs]         grp[2 * (gbase + g)]
+    float4* item;         // [2 * 8 * runs]     item[2 * ((gbase + g) * 8 + j)]
+    uint32_t set_stride;  // in float4
+    uint32_t pad_;
+};
+
 // Pointers into the scene records as they lie in HBM (the record sections of the blob are
 // uploaded verbatim, so an NCCL-broadcast copy is usable as is).
 struct DScene {
@@ -34,8 +45,9 @@ struct DScene {
     const TextureDev* textures;
     const double* gamma_lut;  // [256] pow(i / 255, 2.2) computed once on the device (ImageTexture::at, texture.rs:162-168)
     const float4* inst_aabb;  // [2 * n_instances] padded world-space box of every instance (lo, hi), FP32, rounded outward
-    const float4* leaf_aabb;  // [2 * n_tlas_items] inst_aabb gathered into scene-tree leaf order: leaf_aabb[j] = inst_aabb[tlas_items[j]]
-    const float4* leaf_grp_aabb;  // [2 * ceil(n_tlas_items / 8)] union of leaf_aabb over every aligned run of 8 leaf positions
+    LeafCull tl_cull;         // scene tree: boxes of the leaves' candidates (inst_aabb clipped to the leaf cells)
+    LeafCull bl_cull;         // KDMesh trees: boxes of the leaves' triangles (tri_aabb clipped to the leaf cells)
+    const float4* tl_root;    // [2] union of all instance boxes (the probe-segment check of traverse.cuh scene_cast)
     // padded object-space FP32 box of every triangle (index order)
     const float4* tri_aabb;
     // Mesh fold cull (traverse.cuh mesh_fold): the triangles of every linear Mesh in Morton order of their centroids
@@ -44,7 +56,6 @@ struct DScene {
     const uint32_t* fold_order;
     const float4* fold_aabb[kFoldLevels + 1];
     uint32_t fold_levels;  // group levels actually built (<= kFoldLevels)
-    const float4* blas_leaf_aabb;  // [2 * n_blas_items] tri_aabb gathered into KDMesh leaf-item order (BlasLeaf reads it sequentially)
     double ambient[3];
     double tlas_extent;
     uint32_t n_lights;

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
         const V3 d = v3(pool.dx[i], pool.dy[i], pool.dz[i]);
         Hit hit{(double)INFINITY, kNone, 0};
         const uint32_t err_before = err;
-        const bool found = scene_cast<false>(sc, o, d, hit, tlas_stack, blas_stack, err, wc);
+        const bool found = scene_cast<false, COUNT>(sc, o, d, hit, tlas_stack, blas_stack, err, wc);
         if (err != err_before) record_error(fs.fp, pool, ctl, err & ~err_before, i, 0u | level << 8);
         pool.t[i] = found ? hit.t : (double)INFINITY;
         pool.inst[i] = found ? hit.inst : kNone;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
         const V3 light_dir = hit_to_light / light_dist;
         Hit hit{(double)INFINITY, kNone, 0};
         const uint32_t err_before = err;
-        const bool occluded = scene_cast<true>(sc, hit_point, light_dir, hit, tlas_stack, blas_stack, err, wc);
+        const bool occluded = scene_cast<true, COUNT>(sc, hit_point, light_dir, hit, tlas_stack, blas_stack, err, wc);
         if (err != err_before) record_error(fp, pool, ctl, err & ~err_before, i, 1u | level << 8 | l << 16);
         pool.occl[(size_t)l * pool.capacity + i] = occluded ? 1 : 0;
         ++cast;
@@ -733,32 +733,6 @@ __global__ void __launch_bounds__(kBlock) instance_bounds_kernel(const PtInstanc
     out[2 * (size_t)i + 1] = make_float4(fhi[0], fhi[1], fhi[2], 0.f);
 }
 
-// instance boxes in scene-tree leaf order (TlasLeaf reads them sequentially)
-__global__ void __launch_bounds__(kBlock) gather_leaf_boxes_kernel(const float4* __restrict__ inst_aabb, const uint32_t* __restrict__ items,
-                                                                  uint32_t n_items, float4* __restrict__ out) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_items) return;
-    const uint32_t inst = items[j];
-    out[2 * (size_t)j] = inst_aabb[2 * (size_t)inst];
-    out[2 * (size_t)j + 1] = inst_aabb[2 * (size_t)inst + 1];
-}
-
-// triangle boxes in KDMesh leaf-item order (BlasLeaf reads them sequentially): blockIdx.y walks the meshes, x their items
-__global__ void __launch_bounds__(kBlock) gather_blas_leaf_boxes_kernel(const PtMesh* __restrict__ meshes, uint32_t n_meshes,
-                                                                       const uint32_t* __restrict__ blas_items, const float4* __restrict__ tri_aabb,
-                                                                       float4* __restrict__ out, uint32_t n_blas_items) {
-    for (uint32_t m = blockIdx.y; m < n_meshes; m += gridDim.y) {
-        if (meshes[m].kind != PT_MESH_KD) continue;
-        const uint32_t first = meshes[m].item_first, count = meshes[m].item_count, tri_first = meshes[m].tri_first;
-        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-            if (first + j >= n_blas_items) break;
-            const size_t tri = (size_t)tri_first + blas_items[first + j];
-            out[2 * (size_t)(first + j)] = tri_aabb[2 * tri];
-            out[2 * (size_t)(first + j) + 1] = tri_aabb[2 * tri + 1];
-        }
-    }
-}
-
 // FP32 box of every triangle (object space), rounded outward and padded by 1e-5 of the triangle's largest
 // coordinate magnitude and extent: the per-triangle cull of Mesh folds (traverse.cuh mesh_fold).
 __global__ void __launch_bounds__(kBlock) triangle_bounds_kernel(const PtTriPos* __restrict__ tri_pos, uint32_t n, float4* __restrict__ out) {
@@ -870,20 +844,6 @@ void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bo
     if (sc.n_instances)
         instance_bounds_kernel<<<blocks_for(sc.n_instances), kBlock, 0, st>>>(sc.instances, sc.instance_trans, sc.n_instances,
                                                                             mesh_bounds_scratch, out);
-}
-
-// out: n_items leaf-ordered boxes followed by ceil(n_items / 8) run boxes
-void launch_gather_leaf_boxes(const float4* inst_aabb, const uint32_t* items, uint32_t n_items, float4* out, cudaStream_t st) {
-    if (!n_items) return;
-    gather_leaf_boxes_kernel<<<blocks_for(n_items), kBlock, 0, st>>>(inst_aabb, items, n_items, out);
-    group_bounds_kernel<<<blocks_for((n_items + 7u) / 8u), kBlock, 0, st>>>(out, n_items, 8u, out + 2 * (size_t)n_items);
-}
-
-void launch_gather_blas_leaf_boxes(const PtMesh* meshes, uint32_t n_meshes, const uint32_t* blas_items, const float4* tri_aabb, float4* out,
-                                   uint32_t n_blas_items, cudaStream_t st) {
-    if (!n_meshes || !n_blas_items) return;
-    const dim3 grid(std::min<uint32_t>(blocks_for(n_blas_items), 1024u), std::min<uint32_t>(n_meshes, 1024u));
-    gather_blas_leaf_boxes_kernel<<<grid, kBlock, 0, st>>>(meshes, n_meshes, blas_items, tri_aabb, out, n_blas_items);
 }
 
 void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, cudaStream_t st) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "device_scene.cuh"
+#include "kd_build.h"
 
 namespace ptd {
 void kernels_init();
@@ -14,12 +15,23 @@ void launch_gamma_lut(double* lut256, cudaStream_t st);
 // upload time: padded FP32 world boxes of all instances (mesh_bounds_scratch: n_meshes * 6 doubles)
 void launch_instance_bounds(const DScene& sc, uint32_t n_meshes, double* mesh_bounds_scratch, float4* out, cudaStream_t st);
 
-// upload time: the instance boxes gathered into scene-tree leaf order + the union box of every aligned run of 8 of
-// them (out: 2 * (n_items + ceil(n_items / 8)) float4)
-void launch_gather_leaf_boxes(const float4* inst_aabb, const uint32_t* items, uint32_t n_items, float4* out, cudaStream_t st);
-// upload time: padded FP32 object-space boxes of all triangles + of every aligned run of 32 / 1024 of them
-void launch_gather_blas_leaf_boxes(const PtMesh* meshes, uint32_t n_meshes, const uint32_t* blas_items, const float4* tri_aabb, float4* out,
-                                   uint32_t n_blas_items, cudaStream_t st);
+// upload time: the leaf cull structure of a forest of k-d trees (leaf_cull.cu).  One LcTree per tree: where its nodes
+// and items lie in the forest's arrays (child / item indices inside the records are relative to these) and what to add
+// to an item value to index `item_boxes` (0 for the scene tree, tri_first for a KDMesh tree).
+struct LcTree {
+    uint32_t node_first, node_count, item_first, box_first;
+};
+struct LeafCullSizes {
+    uint32_t n_leaf_cap, n_grp_cap;
+    size_t set_float4;     // float4 per box set; the storage holds two sets
+    size_t scratch_bytes;
+};
+LeafCullSizes leaf_cull_sizes(uint32_t n_nodes, uint32_t n_items);
+// nodes: the forest's node array in device memory — the leaves' `split` fields are overwritten with rank | gbase << 32
+cudaError_t launch_leaf_cull(PtKdNode* nodes, uint32_t n_nodes, const uint32_t* items, uint32_t n_items, const LcTree* d_trees, uint32_t n_trees,
+                             const float4* item_boxes, float4* storage, void* scratch, const KdAllocator& al, LeafCull* out, cudaStream_t st);
+void launch_root_box(const float4* boxes, uint32_t n, float4* out2, cudaStream_t st);
+// upload time: padded FP32 object-space boxes of all triangles
 void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, cudaStream_t st);
 // fold structure of linear meshes (fold_order.cu, traverse.cuh mesh_fold)
 size_t fold_sort_temp_bytes(uint32_t n);

@@ -244,8 +244,8 @@ struct KdStack {
     double e[PT_MAX_KD_STACK];
 };
 
-// Iterative form of ray_cast_impl (node.rs:66-203). `leaf(first, count, s, e)`
-// returns true when the leaf's fold produced a hit inside [s, e); the first
+// Iterative form of ray_cast_impl (node.rs:66-203). `leaf(rank, gbase, first, count, s, e)` returns true when the
+// leaf's fold produced a hit inside [s, e) — (rank, gbase) locate the leaf's cull boxes, leaf_cull.cu —; the first
 // leaf that does ends the walk.
 template <class LeafFn>
 PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d, double s, double e, KdStack& stack,
@@ -254,10 +254,10 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
     const uint4* __restrict__ nodes4 = reinterpret_cast<const uint4*>(nodes);
     uint4 w = __ldg(nodes4);
     for (;;) {
-        const double split = __hiloint2double((int)w.y, (int)w.x);
         const uint32_t a = w.z, b = w.w;
         const uint32_t axis = a & 3u;
         if (axis != 3u) {
+            const double split = __hiloint2double((int)w.y, (int)w.x);
             ++n_splits;
             const uint32_t front = a >> 2, back = b;
 #if PT_KD_PREFETCH
@@ -299,7 +299,7 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
                 continue;
             }
             err |= PT_DEVERR_KD_PLANE;  // .expect("bug: ray should definitely hit infinite plane")
-        } else if (leaf(a >> 2, b, s, e)) {
+        } else if (b != 0u && leaf(w.x, w.y, a >> 2, b, s, e)) {
             return true;
         }
         if (sp == 0) return false;
@@ -311,99 +311,143 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
 }
 
 // ------------------------------------------------------------------ conservative FP32 cull
-// Before an instance is tested exactly (f64, object space) its padded world-space bounding box
-// (DScene::inst_aabb, built at upload by instance_bounds_kernel) is slab-tested in FP32.  The test
-// may only answer "certainly no hit inside [s, e)": every rounding source is covered by padding
-// that is orders of magnitude larger than the FP32 error (the box is padded at build time, the ray
-// origin by 4e-6 * |o|, the slab parameters by 2e-5 relative), so a candidate the f64 test would
-// accept is never dropped and the result stays bit-identical to the un-culled walk.  The cull runs
-// on the FP32 pipe; the f64 pipe — the binding resource of this kernel — only sees the survivors.
+// Before a candidate is tested exactly (f64, object space) a padded FP32 box that contains every hit it could return
+// is slab-tested against the ray.  The test may only answer "certainly no hit inside [s, e)": every rounding source
+// is covered by padding that is orders of magnitude larger than the FP32 error (the boxes are rounded outward and
+// padded at build time, the ray origin by 4e-6 * |o|, the slab parameters by 2e-5 relative), so a candidate the f64
+// test would accept is never dropped and the result stays bit-identical to the un-culled walk.  The cull runs on the
+// FP32 pipe (explicit FMAs: the library is built -fmad=false for the f64 path, and nothing here needs to round like the
+// reference); the f64 pipe only sees the survivors.
+//
+// kClipPadT: boxes CLIPPED to a k-d leaf's cell (leaf_cull.cu) rest on "a hit the leaf accepts lies inside the leaf's
+// cell".  The walk above decides sides from two probe points, ray.at(s + EPSILON) and ray.at(t_max) (node.rs:119-131):
+// between them the ray is on the side it was sent to, but a hit in the first or last EPSILON of an ancestor's range —
+// or, when a range is shorter than 2 EPSILON, up to 2 EPSILON from the plane's crossing — can lie on the other side,
+// by at most 2 EPSILON of ray PARAMETER whatever the direction's length.  So the slab parameters of a clipped box get
+// an ABSOLUTE pad as well (each box side 2 EPSILON: 4e-5 between them).  Beyond t_max = s + extent the ray is outside
+// the tree's bounds for every ray that passes `probe_covers` below; the others use the unclipped box set.
+constexpr float kClipPadT = 4e-5f;
+
 struct RayF {
-    float ox_lo, oy_lo, oz_lo;  // origin + pad  (subtracted from box minima)
-    float ox_hi, oy_hi, oz_hi;  // origin - pad  (subtracted from box maxima)
     float ix, iy, iz;           // 1 / direction (inf when a component is 0)
+    float cx_lo, cy_lo, cz_lo;  // -(origin + pad) / direction: box minima * i + c_lo = slab parameter
+    float cx_hi, cy_hi, cz_hi;  // -(origin - pad) / direction: box maxima
 };
 PT_D RayF make_rayf(V3 o, V3 d) {
     RayF r;
     const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
     const float pad = 4e-6f * fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz)));
-    r.ox_lo = ox + pad; r.oy_lo = oy + pad; r.oz_lo = oz + pad;
-    r.ox_hi = ox - pad; r.oy_hi = oy - pad; r.oz_hi = oz - pad;
     r.ix = 1.0f / (float)d.x; r.iy = 1.0f / (float)d.y; r.iz = 1.0f / (float)d.z;
+    r.cx_lo = -((ox + pad) * r.ix); r.cy_lo = -((oy + pad) * r.iy); r.cz_lo = -((oz + pad) * r.iz);
+    r.cx_hi = -((ox - pad) * r.ix); r.cy_hi = -((oy - pad) * r.iy); r.cz_hi = -((oz - pad) * r.iz);
     return r;
 }
-// false = the ray certainly misses the instance inside [s, e)
-PT_D bool aabb_may_hit(const float4* __restrict__ bb, const RayF& r, double s, double e) {
+// the ray's range as the slab tests see it: [s, e) widened by 1e-4 relative, the far end also by kClipPadT
+struct RangeF {
+    float s, e;
+};
+PT_D RangeF make_rangef(double s, double e) { return RangeF{(float)s * 0.9999f, (float)e * 1.0001f + kClipPadT}; }  // s, e > 0
+
+// padded slab parameters of the ray inside the box; fminf / fmaxf drop a NaN operand (0 * inf on a slab boundary):
+// the slab then does not constrain
+PT_D void box_interval(const float4* __restrict__ bb, const RayF& r, float& tn, float& tf) {
     const float4 lo = __ldg(bb), hi = __ldg(bb + 1);
-    const float ax = (lo.x - r.ox_lo) * r.ix, bx = (hi.x - r.ox_hi) * r.ix;
-    const float ay = (lo.y - r.oy_lo) * r.iy, by = (hi.y - r.oy_hi) * r.iy;
-    const float az = (lo.z - r.oz_lo) * r.iz, bz = (hi.z - r.oz_hi) * r.iz;
-    // fminf / fmaxf drop a NaN operand (0 * inf on a slab boundary): the slab then does not constrain
-    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-    tn -= 2e-5f * fabsf(tn);
-    tf += 2e-5f * fabsf(tf);
-    const float sf = (float)s * 0.9999f, ef = (float)e * 1.0001f;  // s, e > 0
-    return !(tn > tf) && !(tf < sf) && !(tn > ef);
+    const float ax = __fmaf_rn(lo.x, r.ix, r.cx_lo), bx = __fmaf_rn(hi.x, r.ix, r.cx_hi);
+    const float ay = __fmaf_rn(lo.y, r.iy, r.cy_lo), by = __fmaf_rn(hi.y, r.iy, r.cy_hi);
+    const float az = __fmaf_rn(lo.z, r.iz, r.cz_lo), bz = __fmaf_rn(hi.z, r.iz, r.cz_hi);
+    tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    tn = __fmaf_rn(-2e-5f, fabsf(tn), tn);
+    tf = __fmaf_rn(2e-5f, fabsf(tf), tf) + kClipPadT;
+}
+// false = the ray certainly has no hit inside the box within the range
+PT_D bool box_may_hit(const float4* __restrict__ bb, const RayF& r, const RangeF& rg) {
+    float tn, tf;
+    box_interval(bb, r, tn, tf);
+    return !(tn > tf) && !(tf < rg.s) && !(tn > rg.e);
+}
+// The probe segment of the walk ends at s + extent (node.rs:119): does the ray leave `box` — a box around everything
+// the tree holds — before that?  Then no hit lies beyond the probe and the clipped boxes are valid for the whole walk.
+// A ray that misses the box altogether cannot hit anything: any box set will do.
+PT_D bool probe_covers(const float4* __restrict__ box, const RayF& r, double s, double extent) {
+    float tn, tf;
+    box_interval(box, r, tn, tf);
+    return (tn > tf) || (tf < (float)((s + extent) * 0.999));  // NaN / inf anywhere: false
 }
 
-// leaf of a KDMesh tree: RayHit for [Triangle] with a shrinking clone of the range (ray.rs:50-63).  A triangle whose
-// padded FP32 box (DScene::tri_aabb) the ray certainly misses inside [s, e) is rejected on the FP32 pipe; the others
-// get the exact f64 test — same accepted hits, same order.
+// One leaf of a k-d tree: the fold over its candidate list with a shrinking range (ray.rs:50-63 / :87-99), restricted
+// to the candidates whose boxes the ray may hit inside the range.  Three levels of boxes (leaf_cull.cu): the leaf's
+// occupied box, the union box of every run of 8 list positions, the candidates' own boxes.  Per 32 positions the lanes
+// first slab-test boxes into a survivor mask — a tight, branch-light loop — and then run the exact tests of the
+// survivors in list order, each culled again against the range as it has shrunk since: a one-phase loop (test a box,
+// then maybe the primitive) makes the whole warp wait whenever ANY lane has a survivor.
+//   exact(k, s, e): the reference's test of list position k over [s, e); on a hit it records it, sets e = t and returns true.
+template <bool ANY, class Exact>
+PT_D bool leaf_fold(const LeafCull& lc, uint32_t set, uint32_t rank, uint32_t gbase, uint32_t count, const RayF& rf, double s, double& e,
+                    Exact& exact) {
+    RangeF rg = make_rangef(s, e);
+    if (!box_may_hit(lc.occ + set + 2 * (size_t)rank, rf, rg)) return false;
+    const float4* __restrict__ grp = lc.grp + set + 2 * (size_t)gbase;
+    const float4* __restrict__ item = lc.item + set + 16 * (size_t)gbase;
+    const uint32_t n_groups = (count + 7u) >> 3;
+    bool found = false;
+    for (uint32_t gc = 0; gc < n_groups; gc += 4u) {  // 4 runs of 8 = one 32-bit survivor mask
+        uint32_t mask = 0u;
+        const uint32_t g_stop = min(gc + 4u, n_groups);
+        for (uint32_t g = gc; g < g_stop; ++g) {
+            if (n_groups > 1u && !box_may_hit(grp + 2 * (size_t)g, rf, rg)) continue;  // a single run's box is the occupied box
+            const float4* __restrict__ ib = item + 16 * (size_t)g;
+            uint32_t m8 = 0u;
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; ++j)
+                if (box_may_hit(ib + 2 * j, rf, rg)) m8 |= 1u << j;
+            mask |= m8 << ((g - gc) << 3);
+        }
+        const uint32_t left = count - (gc << 3);
+        if (left < 32u) mask &= (1u << left) - 1u;  // the padding slots of the last run
+        while (mask) {
+            const uint32_t k = (gc << 3) + (uint32_t)__ffs((int)mask) - 1u;
+            mask &= mask - 1u;
+            if (found && !box_may_hit(item + 2 * (size_t)k, rf, rg)) continue;  // the range has shrunk since phase 1
+            if (exact(k, s, e)) {
+                if (ANY) return true;
+                found = true;
+                rg = make_rangef(s, e);
+            }
+        }
+    }
+    return found;
+}
+
+// leaf of a KDMesh tree: RayHit for [Triangle] with a shrinking clone of the range (ray.rs:50-63)
 template <bool ANY>
 struct BlasLeaf {
+    const LeafCull& lc;
+    uint32_t set;
     const uint32_t* __restrict__ items;
     const PtTriPos* __restrict__ tris;
-    const float4* __restrict__ boxes;       // per triangle of the mesh (index order)
-    const float4* __restrict__ leaf_boxes;  // the same boxes gathered into this tree's leaf-item order (DScene::blas_leaf_aabb)
     V3 o, d;
     RayF rf;
     double t;
     uint32_t tri;
     uint32_t n_tests;
-    PT_D bool operator()(uint32_t first, uint32_t count, double s, double e) {
-        bool found = false;
-#if PT_BLAS_TWO_PHASE
-        // as in TlasLeaf: first slab-test the leaf's boxes (read sequentially, no index indirection) into a survivor
-        // mask, then run the f64 tests of the survivors in list order, each re-culled against the range as it has
-        // shrunk since.  Lanes of a warp then spend their time in the same phase instead of waiting for one lane's
-        // triangle test between two box tests.
-        for (uint32_t base = 0; base < count; base += 32u) {
-            const uint32_t n = min(32u, count - base);
-            const float4* __restrict__ lb = leaf_boxes + 2 * (size_t)(first + base);
-            uint32_t mask = 0u;
-            for (uint32_t j = 0; j < n; ++j)
-                if (aabb_may_hit(lb + 2 * (size_t)j, rf, s, e)) mask |= 1u << j;
-            while (mask) {
-                const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
-                mask &= mask - 1u;
-                if (found && !aabb_may_hit(lb + 2 * (size_t)j, rf, s, e)) continue;
-                const uint32_t idx = __ldg(items + first + base + j);
-                double tt;
-                if (triangle_t(tris + idx, o, d, s, e, tt, nullptr)) {
-                    e = tt;
-                    t = tt;
-                    tri = idx;
-                    found = true;
-                    if (ANY) { n_tests += base + j + 1u; return true; }
-                }
-            }
-        }
-        n_tests += count;
-#else
-        for (uint32_t k = 0; k < count; ++k) {
-            const uint32_t idx = __ldg(items + first + k);
-            ++n_tests;
-            double tt;
-            if (aabb_may_hit(boxes + 2 * (size_t)idx, rf, s, e) && triangle_t(tris + idx, o, d, s, e, tt, nullptr)) {
-                e = tt;
-                t = tt;
-                tri = idx;
-                found = true;
-                if (ANY) return true;
-            }
-        }
-#endif
+    uint32_t first;
+    PT_D bool operator()(uint32_t k, double s, double& e) {
+        const uint32_t idx = __ldg(items + first + k);
+        double tt;
+        if (!triangle_t(tris + idx, o, d, s, e, tt, nullptr)) return false;
+        e = tt;
+        t = tt;
+        tri = idx;
+        if (ANY) n_tests += k + 1u;
+        return true;
+    }
+    PT_D bool operator()(uint32_t rank, uint32_t gbase, uint32_t first_, uint32_t count, double s, double e) {
+        first = first_;
+        if (!ANY) n_tests += count;
+        const uint32_t before = n_tests;
+        const bool found = leaf_fold<ANY>(lc, set, rank, gbase, count, rf, s, e, *this);
+        if (ANY && !found) n_tests = before + count;
         return found;
     }
 };
@@ -425,6 +469,7 @@ template <bool ANY>
 PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3 o, V3 d, double s, double e, double& t_out,
                     uint32_t& sub, uint32_t& n_tests) {
     const RayF rf = make_rayf(o, d);
+    RangeF rg = make_rangef(s, e);
     const uint32_t* __restrict__ order = sc.fold_order;
     const float4* __restrict__ bb0 = sc.fold_aabb[0];
     const uint32_t end = tri_first + tri_count;
@@ -437,7 +482,7 @@ PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3
         int l = k ? min(levels, (__ffs((int)k) - 1) >> 1) : levels;
         bool skipped = false;
         for (; l >= 1; --l) {
-            if (!aabb_may_hit(sc.fold_aabb[l] + 2 * (size_t)(k >> (2 * l)), rf, s, e)) {
+            if (!box_may_hit(sc.fold_aabb[l] + 2 * (size_t)(k >> (2 * l)), rf, rg)) {
                 k = min(k + (1u << (2 * l)), end);
                 skipped = true;
                 break;
@@ -445,11 +490,12 @@ PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3
         }
         if (skipped) continue;
         double tt;
-        if (aabb_may_hit(bb0 + 2 * (size_t)k, rf, s, e)) {
+        if (box_may_hit(bb0 + 2 * (size_t)k, rf, rg)) {
             const uint32_t idx = __ldg(order + k);
             if (triangle_t(sc.tri_pos + idx, o, d, s, e, tt, nullptr, found) && (tt < e || idx < best)) {
                 if (ANY) { n_tests += 1u; t_out = tt; sub = idx - tri_first; return true; }
                 e = tt;
+                rg = make_rangef(s, e);
                 best = idx;
                 found = true;
             }
@@ -461,10 +507,12 @@ PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3
     return found;
 }
 
-// Primitive::ray_hit in object space (primitive.rs:55-61), t + sub id only
+// Primitive::ray_hit in object space (primitive.rs:55-61), t + sub id only.
+// `world_exit`: upper bound of the ray parameter at which the ray leaves the instance's box (KDMesh only: decides
+// whether the KDMesh walk may use the clipped triangle boxes, see probe_covers).
 template <bool ANY>
 PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V3 d, double s, double e, double& t,
-                      uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc) {
+                      uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc, float world_exit) {
     sub = 0;
     switch (prim) {
         case PT_PRIM_SPHERE: return sphere_t(o, d, s, e, t);
@@ -486,94 +534,74 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     }
     // KDMesh: KDTreeNode<Triangle>::ray_hit on a clone of the range (node.rs:33-51)
     const uint32_t item_first = __ldg(&mesh->item_first);
-    BlasLeaf<ANY> leaf{sc.blas_items + item_first, sc.tri_pos + tri_first, sc.tri_aabb + 2 * (size_t)tri_first,
-                       sc.blas_leaf_aabb + 2 * (size_t)item_first, o, d, make_rayf(o, d), 0.0, 0, 0};
-    const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), __ldg(&mesh->extent), o, d, s, e, blas_stack, leaf,
-                             err, wc.kd_splits);
+    const double extent = __ldg(&mesh->extent);
+    // the walk's first probe ends at s + extent (object-space extent on the world-ray parameter): the
+    // clipped triangle boxes hold only if the ray has left the mesh by then
+    const uint32_t set = world_exit < (float)((s + extent) * 0.999) ? 0u : sc.bl_cull.set_stride;
+    BlasLeaf<ANY> leaf{sc.bl_cull, set, sc.blas_items + item_first, sc.tri_pos + tri_first, o, d, make_rayf(o, d), 0.0, 0, 0, 0};
+    const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), extent, o, d, s, e, blas_stack, leaf, err, wc.kd_splits);
     wc.triangle_tests += leaf.n_tests;
     if (hit) { t = leaf.t; sub = leaf.tri; }
     return hit;
 }
 
-// leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99).
-//
-// Two phases per 32 candidates, so that the lanes of a warp do the same thing at the same time:
-//   1. every lane slab-tests padded boxes in FP32 and keeps the survivors as a bit mask: first the union box of each
-//      aligned run of 8 leaf positions (DScene::leaf_grp_aabb), then, for the runs it may hit, the 8 instance boxes
-//      (DScene::leaf_aabb: the instance boxes copied into leaf order, read sequentially).  Leaf order is flat-instance
-//      order, so runs are spatially coherent: on graphics-castle 51 box tests per leaf visit become 15;
-//   2. the survivors are tested exactly (f64, object space) in list order.
-// A one-phase loop (test a box, then maybe the primitive) makes the whole warp wait whenever ANY lane has a survivor:
-// with ~10 % survivors per lane that is almost every iteration, and ncu showed 8 of 32 lanes active on
-// graphics-castle (62 candidates per leaf).  The mask is built with the range as it was at the start of the run — a
-// superset of what the shrinking range would let through — and each survivor is culled again against the current
-// range before its f64 test, so the accepted hits and their order are unchanged.
-template <bool ANY>
+// leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99)
+template <bool ANY, bool COUNT>
 struct TlasLeaf {
     const DScene& sc;
+    uint32_t set;
     V3 o, d;
     RayF rf;
     KdStack& blas_stack;
     Hit& hit;
     uint32_t& err;
     WorkCounters& wc;
-    PT_D bool operator()(uint32_t first, uint32_t count, double s, double e) {
-        bool found = false;
-        if (count == 0u) return false;
-        const float4* __restrict__ boxes = sc.leaf_aabb;      // indexed by position in tlas_items
-        const float4* __restrict__ groups = sc.leaf_grp_aabb;  // union box of every aligned run of 8 positions
-        const uint32_t* __restrict__ items = sc.tlas_items;
-        const uint32_t end = first + count;
-        for (uint32_t k = first; k < end; ++k) {
-            // counting kernels only (dead code otherwise): the reference's work for every candidate, culled or not
-            const uint32_t prim = __ldg(&sc.instances[__ldg(items + k)].prim);
-            ++wc.instance_tests;
-            wc.prim_flops += prim_flop_count(prim);
-            wc.bbox_gates += (prim == PT_PRIM_MESH || prim == PT_PRIM_KDMESH) ? 1u : 0u;  // mesh.rs:153, kdmesh.rs:67
-            wc.triangle_tests += prim == PT_PRIM_TRIANGLE ? 1u : 0u;
+    uint32_t first;
+    // FlatSceneNode::ray_cast of list position k: the ray in object space, direction NOT renormalised (flat_scene.rs:75, ray.rs:130-135)
+    PT_D bool operator()(uint32_t k, double s, double& e) {
+        const uint32_t inst = __ldg(sc.tlas_items + first + k);
+        const PtInstance* rec = sc.instances + inst;
+        double m[12];
+        load_doubles12(rec->invtrans, m);
+        const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&rec->prim));
+        const V3 lo = xf_point(m, o), ld = xf_dir(m, d);
+        float world_exit = INFINITY;
+        if (pm.x == PT_PRIM_KDMESH) {
+            float tn;
+            box_interval(sc.inst_aabb + 2 * (size_t)inst, rf, tn, world_exit);
         }
-        const uint32_t g_last = (end - 1u) >> 3;
-        for (uint32_t gc = first >> 3; gc <= g_last; gc += 4u) {  // 4 runs of 8 = one 32-bit survivor mask
-            uint32_t mask = 0u;
-            const uint32_t g_stop = min(gc + 4u, g_last + 1u);
-            for (uint32_t g = gc; g < g_stop; ++g) {
-                const uint32_t k0 = max(first, g << 3), k1 = min(end, (g << 3) + 8u);
-                if (k1 - k0 > 2u && !aabb_may_hit(groups + 2 * (size_t)g, rf, s, e)) continue;  // a run of 1-2 is tested directly
-                for (uint32_t k = k0; k < k1; ++k)
-                    if (aabb_may_hit(boxes + 2 * (size_t)k, rf, s, e)) mask |= 1u << (k - (gc << 3));
-            }
-            while (mask) {
-                const uint32_t k = (gc << 3) + (uint32_t)__ffs((int)mask) - 1u;
-                mask &= mask - 1u;
-                if (found && !aabb_may_hit(boxes + 2 * (size_t)k, rf, s, e)) continue;  // the range has shrunk since phase 1
-                const uint32_t inst = __ldg(items + k);
-                // FlatSceneNode::ray_cast: the ray in object space, direction NOT renormalised (flat_scene.rs:75, ray.rs:130-135)
-                const PtInstance* rec = sc.instances + inst;
-                double m[12];
-                load_doubles12(rec->invtrans, m);
-                const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&rec->prim));
-                const V3 lo = xf_point(m, o), ld = xf_dir(m, d);
-                double t;
-                uint32_t sub;
-                if (primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc)) {
-                    e = t;  // flat_scene.rs:92
-                    hit.t = t;
-                    hit.inst = inst;
-                    hit.sub = sub;
-                    found = true;
-                    if (ANY) return true;
-                }
+        double t;
+        uint32_t sub;
+        if (!primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc, world_exit)) return false;
+        e = t;  // flat_scene.rs:92
+        hit.t = t;
+        hit.inst = inst;
+        hit.sub = sub;
+        return true;
+    }
+    PT_D bool operator()(uint32_t rank, uint32_t gbase, uint32_t first_, uint32_t count, double s, double e) {
+        first = first_;
+        if (COUNT) {
+            // the reference's work for every candidate, culled or not
+            for (uint32_t k = first; k < first + count; ++k) {
+                const uint32_t prim = __ldg(&sc.instances[__ldg(sc.tlas_items + k)].prim);
+                ++wc.instance_tests;
+                wc.prim_flops += prim_flop_count(prim);
+                wc.bbox_gates += (prim == PT_PRIM_MESH || prim == PT_PRIM_KDMESH) ? 1u : 0u;  // mesh.rs:153, kdmesh.rs:67
+                wc.triangle_tests += prim == PT_PRIM_TRIANGLE ? 1u : 0u;
             }
         }
-        return found;
+        return leaf_fold<ANY>(sc.tl_cull, set, rank, gbase, count, rf, s, e, *this);
     }
 };
 
 // scene.root.ray_cast(ray, [EPSILON, inf)) — ray.rs:140-141, material.rs:174-179
-template <bool ANY>
+template <bool ANY, bool COUNT>
 PT_D bool scene_cast(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& tlas_stack, KdStack& blas_stack, uint32_t& err,
                      WorkCounters& wc) {
-    TlasLeaf<ANY> leaf{sc, o, d, make_rayf(o, d), blas_stack, hit, err, wc};
+    const RayF rf = make_rayf(o, d);
+    const uint32_t set = probe_covers(sc.tl_root, rf, kEps, sc.tlas_extent) ? 0u : sc.tl_cull.set_stride;
+    TlasLeaf<ANY, COUNT> leaf{sc, set, o, d, rf, blas_stack, hit, err, wc, 0};
     return kd_walk(sc.tlas_nodes, sc.tlas_extent, o, d, kEps, (double)INFINITY, tlas_stack, leaf, err, wc.kd_splits);
 }
 
