@@ -591,6 +591,8 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_bytes_per_launch": bytes_step * kernel_passes / max(k_n, 1),
                 "avg_launch_ms": k_ms / max(k_n, 1), "launches_timed": k_n,
                 "kernel_ms_per_step": {"extend": ms_ext / kernel_passes, "shadow": ms_shd / kernel_passes, "shade": ms_sha / kernel_passes},
+                "kernel_ms_per_level": {"extend": [round(sum(st.ms_extend_level[l] for st in timed_stats) / kernel_passes, 4) for l in range(12)],
+                                        "shadow": [round(sum(st.ms_shadow_level[l] for st in timed_stats) / kernel_passes, 4) for l in range(12)]},
                 "timing": "CUDA events around every launch of the kernel on the stream path (same frames, same kernels; the "
                           "timed region replays them inside CUDA graphs)",
                 "note": "bytes TOUCHED per SURVEY 8d (16/kd split, 108/instance test, 72/triangle, 96/bbox gate + ray records); "

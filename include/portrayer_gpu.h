@@ -38,6 +38,7 @@ extern "C" {
 #define PT_EPSILON 0.00001            /* src/math.rs:15 */
 #define PT_GAMMA 2.2                  /* src/math.rs:20 */
 #define PT_MAX_RECURSION_DEPTH 10u    /* src/material.rs:12 */
+#define PT_MAX_DEPTH_SUPPORTED 13u    /* largest PtRenderParams.max_depth the library accepts (ray trees of 14 levels) */
 #define PT_DEFAULT_SAMPLES 100u       /* src/render.rs:113 */
 
 #define PT_MAX_KD_STACK 48            /* deepest kd-tree (KD_DEPTH / KD_MESH_DEPTH) the device walks */
@@ -320,6 +321,8 @@ typedef struct PtStats {
      * pixel index y*W+x, sample, path id (1 = primary; child = parent << 1 | refracted), and
      * kernel (0 extend, 1 shadow, 2 shade) | recursion level << 8 | light << 16 */
     uint32_t err_bit, err_pixel, err_sample, err_pathid, err_where, reserved3;
+    /* only with PT_RENDER_KERNEL_TIMES: the extend / shadow time split by recursion level (level 0 = primary rays) */
+    double ms_extend_level[16], ms_shadow_level[16];
 } PtStats;
 
 typedef struct PtScene PtScene; /* opaque, library-owned */

@@ -90,6 +90,7 @@ class PtStats(C.Structure):
         ("k_prim_flops", C.c_uint64 * 2),
         ("err_bit", C.c_uint32), ("err_pixel", C.c_uint32), ("err_sample", C.c_uint32), ("err_pathid", C.c_uint32),
         ("err_where", C.c_uint32), ("reserved3", C.c_uint32),
+        ("ms_extend_level", C.c_double * 16), ("ms_shadow_level", C.c_double * 16),
     ]
 
     def as_dict(self) -> dict:

@@ -375,7 +375,7 @@ int adopt_header(PtScene* s, const void* host_blob, uint64_t bytes, bool* texels
     *texels_present = bytes >= h.total_bytes;
     PtSceneDesc d;
     int rc = *texels_present ? pt_scene_unpack(host_blob, bytes, &d) : pt_scene_unpack_records(host_blob, bytes, &d);
-    if (rc != PT_OK) return fail(rc, "malformed scene blob");
+    if (rc != PT_OK) return fail(rc, "%s", rc == PT_ERR_KD_TOO_DEEP ? panic_text(rc) : "malformed scene blob");
     s->has_reflective = false;
     for (uint32_t i = 0; i < d.n_materials; ++i)
         if (d.materials[i].reflectivity > 0.0) s->has_reflective = true;
@@ -656,8 +656,9 @@ FrameState frame_state(const PtFrame* f) {
 struct KernelTimer {
     std::vector<cudaEvent_t>* events = nullptr;  // null: timing off
     size_t used = 0;
-    struct Span { int kind; size_t begin; };
+    struct Span { int kind; size_t begin; int level; };
     std::vector<Span> spans;
+    int level = 0;  // recursion level of the spans begun from now on
     void begin(int kind, cudaStream_t st) {
         if (!events) return;
         while (events->size() < used + 2) {
@@ -665,7 +666,7 @@ struct KernelTimer {
             cudaEventCreate(&e);
             events->push_back(e);
         }
-        spans.push_back({kind, used});
+        spans.push_back({kind, used, level});
         cudaEventRecord((*events)[used], st);
     }
     void end(cudaStream_t st) {
@@ -679,8 +680,9 @@ struct KernelTimer {
         for (const Span& s : spans) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, (*events)[s.begin], (*events)[s.begin + 1]);
-            if (s.kind == 0) { stats->ms_extend += ms; ++stats->n_extend; }
-            else if (s.kind == 1) { stats->ms_shadow += ms; ++stats->n_shadow; }
+            const int lv = std::min(std::max(s.level, 0), 15);
+            if (s.kind == 0) { stats->ms_extend += ms; ++stats->n_extend; stats->ms_extend_level[lv] += ms; }
+            else if (s.kind == 1) { stats->ms_shadow += ms; ++stats->n_shadow; stats->ms_shadow_level[lv] += ms; }
             else { stats->ms_shade += ms; ++stats->n_shade; }
         }
         spans.clear();
@@ -696,6 +698,7 @@ int run_levels_stream(int slot, uint32_t n_lights, uint64_t capacity, BatchCtl* 
         // level d holds at most n_paths * 2^d rays, and never more than the pool
         const uint64_t bound = (uint64_t)n_paths << std::min(level, 31);
         const uint64_t max_items = std::min<uint64_t>(bound, capacity);
+        timer->level = level;
         timer->begin(0, st);
         launch_extend(slot, max_items, count, st);
         timer->end(st);
@@ -781,7 +784,7 @@ int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* p
     if ((uint64_t)p.width * p.height > 0xFFFFFFF0ull) return fail(PT_ERR_INVALID, "image too large");
     if (p.world > 1 && p.rank >= p.world) return fail(PT_ERR_INVALID, "rank %u out of range for world %u", p.rank, p.world);
     if (p.bg_mode > PT_BG_CONSTANT || p.rng_mode > PT_RNG_HASH) return fail(PT_ERR_INVALID, "bad bg_mode / rng_mode");
-    if (effective_max_depth(p) > 13) return fail(PT_ERR_INVALID, "max_depth > 13 is not supported");
+    if (effective_max_depth(p) > PT_MAX_DEPTH_SUPPORTED) return fail(PT_ERR_INVALID, "max_depth > %u is not supported", PT_MAX_DEPTH_SUPPORTED);
     if ((p.flags & PT_RENDER_ROW_MAJOR) && p.world > 1)
         return fail(PT_ERR_INVALID, "PT_RENDER_ROW_MAJOR needs world <= 1 (ranks own interleaved tiles)");
 
@@ -816,7 +819,10 @@ int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* p
     const uint64_t batch_paths = slots * p.samples;
     uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * kPoolNodesPerPath : batch_paths);
     capacity = std::max<uint64_t>(capacity, batch_paths);
-    capacity = std::min<uint64_t>(capacity, 0xFFF00000ull);  // head room for the work cursors (every warp overshoots by <= 2 chunks)
+    // the shade kernel keeps counting refused allocations after the pool is full (pool_count is how the retry sizes its
+    // batches), and the graph path runs one more level after the pool has filled: up to 5 x capacity in all, which must
+    // not wrap the 32-bit counter
+    capacity = std::min<uint64_t>(capacity, 0x30000000ull);
     // the shadow kernel's 32-bit work cursor counts (hit, light) pairs
     capacity = std::min<uint64_t>(capacity, 0xFFF00000ull / std::max<uint32_t>(scene->h.n_lights, 1));
     if (capacity < batch_paths) { free_frame(f); return fail(PT_ERR_INVALID, "batch too large for %u lights: lower max_batch_paths", scene->h.n_lights); }
@@ -1534,7 +1540,7 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
     if (n > 0x7FFFFFFFull) return fail(PT_ERR_INVALID, "too many rays");
     Lock lock(g_mu);
     const uint32_t depth = max_depth ? max_depth : PT_MAX_RECURSION_DEPTH;
-    if (depth > 13) return fail(PT_ERR_INVALID, "max_depth > 13 is not supported");
+    if (depth > PT_MAX_DEPTH_SUPPORTED) return fail(PT_ERR_INVALID, "max_depth > %u is not supported", PT_MAX_DEPTH_SUPPORTED);
     const int n_levels = scene->has_reflective ? (int)depth + 1 : 1;
     const bool count = (flags & PT_RENDER_COUNTERS) != 0;
     const uint32_t batch = (uint32_t)std::min<uint64_t>(n, 1u << 20);

@@ -236,17 +236,34 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
 }
 
 // ------------------------------------------------------------------ shade
-// Allocate one node per lane that wants one: one atomicAdd per warp
-// (__ballot_sync/__popc), lanes get consecutive slots.
-PT_D uint32_t warp_alloc(BatchCtl* ctl, bool want) {
-    const unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
-    if (mask == 0) return kNone;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(&ctl->pool_count, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    return want ? base + (uint32_t)__popc(mask & ((1u << lane) - 1u)) : kNone;
+// Node slots for the children of one block-wide round of the shade kernel: ONE atomicAdd per block, the reflected
+// children of the block's 128 parents first (in parent order), then the refracted ones.  Allocating per warp
+// (32 parents -> up to 32 + 32 slots) made every 32-ray chunk of the next level a mixture of reflected and refracted
+// rays, and the mixture compounds level by level: on graphics-castle ncu counted 12 of 32 lanes active in the extend
+// launches of levels >= 1.  Grouped per block, a chunk of the next level holds children of ONE kind from neighbouring
+// parents.  (Sorting every level by (direction octant, origin cell) was measured too and lost: DESIGN.md section 10.)
+// Every thread of the block must call it (two barriers).
+PT_D void block_alloc(BatchCtl* ctl, bool want0, bool want1, uint32_t& n0, uint32_t& n1) {
+    __shared__ uint32_t s_cnt[2][kBlock / 32];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, want0), m1 = __ballot_sync(0xFFFFFFFFu, want1);
+    if (lane == 0) { s_cnt[0][warp] = (uint32_t)__popc(m0); s_cnt[1][warp] = (uint32_t)__popc(m1); }
+    __syncthreads();
+    uint32_t before0 = 0, before1 = 0, total0 = 0, total1 = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) {
+        const uint32_t c0 = s_cnt[0][w], c1 = s_cnt[1][w];
+        if (w < warp) { before0 += c0; before1 += c1; }
+        total0 += c0;
+        total1 += c1;
+    }
+    if (threadIdx.x == 0) s_base = (total0 + total1) ? atomicAdd(&ctl->pool_count, total0 + total1) : 0u;
+    __syncthreads();
+    const uint32_t base = s_base;
+    const unsigned lt = (1u << lane) - 1u;
+    n0 = want0 ? base + before0 + (uint32_t)__popc(m0 & lt) : kNone;
+    n1 = want1 ? base + total0 + before1 + (uint32_t)__popc(m1 & lt) : kNone;
 }
 
 // `loop`: the conditional handle of the frame graph's WHILE node (0 on the stream path); the last block to
@@ -262,7 +279,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int 
     const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
     const uint32_t n = end - begin;
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounds = (n + stride - 1) / stride;  // every lane runs the same number of rounds (warp_alloc is collective)
+    const uint32_t rounds = (n + stride - 1) / stride;  // every thread runs the same number of rounds (block_alloc is collective)
     uint32_t err = 0, err_seen = 0;
     unsigned long long n_shaded = 0, n_reflect = 0, n_refract = 0, n_cut = 0, n_texel = 0;
 
@@ -432,8 +449,8 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int 
         }
 
         // children: reflected ray first, then refracted (material.rs:243 before :303)
-        const uint32_t n0 = warp_alloc(ctl, want0);
-        const uint32_t n1 = warp_alloc(ctl, want1);
+        uint32_t n0, n1;
+        block_alloc(ctl, want0, want1, n0, n1);
         if (want0) {
             if (n0 < pool.capacity) {
                 pool.ox[n0] = hit_point.x; pool.oy[n0] = hit_point.y; pool.oz[n0] = hit_point.z;
@@ -512,7 +529,7 @@ __global__ void __launch_bounds__(kBlock) tree_eval_kernel(int slot_id) {
     double bg[3];
     background_of(fp, pixel, bg);
 
-    constexpr int kMaxFrames = PT_MAX_RECURSION_DEPTH + 2;
+    constexpr int kMaxFrames = PT_MAX_DEPTH_SUPPORTED + 2;  // a path's tree has max_depth + 1 levels; one spare
     uint32_t f_node[kMaxFrames];
     uint8_t f_stage[kMaxFrames];
     double f_refl[kMaxFrames][3];  // reflected_color once child0 is done

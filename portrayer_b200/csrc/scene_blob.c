@@ -3,6 +3,7 @@
  * is uploaded / NCCL-broadcast, and view a blob as a desc again.
  * Pure host C: no CUDA, works on a machine without a GPU.
  */
+#include <stdlib.h>
 #include <string.h>
 
 #include "portrayer_gpu.h"
@@ -101,22 +102,34 @@ static int section_ok(uint64_t off, uint64_t len, uint64_t total) {
     return (off % PT_ALIGN) == 0 && off <= total && len <= total - off;
 }
 
-static int kd_tree_ok(const PtKdNode* nodes, uint32_t n_nodes, uint32_t n_items_avail, const uint32_t* items,
-                      uint32_t item_base, uint32_t item_limit) {
-    (void)n_items_avail;
-    for (uint32_t i = 0; i < n_nodes; ++i) {
+/* Structure check of one tree: indices in range, children after their parent (no cycles), every node the child of at
+ * most ONE split (the leaf cull structure derives a leaf's cell from its chain of parents, leaf_cull.cu), and the TRUE
+ * depth of the deepest node — the device walk's explicit stack holds PT_MAX_KD_STACK entries and is not bounds-checked,
+ * so the depth a blob declares in its header is not trusted.  Returns 1 / 0; -1 when the tree is too deep. */
+static int kd_tree_ok(const PtKdNode* nodes, uint32_t n_nodes, uint32_t item_limit, uint32_t* depth_out) {
+    uint8_t* depth = (uint8_t*)calloc(n_nodes ? n_nodes : 1, 2); /* depth, then reference count (saturating) */
+    if (!depth) return 0;
+    uint8_t* refs = depth + n_nodes;
+    int ok = 1;
+    uint32_t deepest = 0;
+    for (uint32_t i = 0; i < n_nodes && ok == 1; ++i) {
         uint32_t axis = nodes[i].a & 3u, hi = nodes[i].a >> 2;
         if (axis == 3u) {
-            if ((uint64_t)hi + nodes[i].b > item_limit) return 0;
-            if (items) {
-                (void)item_base;
-            }
+            if ((uint64_t)hi + nodes[i].b > item_limit) ok = 0;
         } else {
-            if (hi >= n_nodes || nodes[i].b >= n_nodes) return 0;
-            if (hi <= i || nodes[i].b <= i) return 0; /* children come after their parent: no cycles */
+            const uint32_t child[2] = {hi, nodes[i].b};
+            for (int c = 0; c < 2 && ok == 1; ++c) {
+                if (child[c] >= n_nodes || child[c] <= i) { ok = 0; break; } /* children come after their parent: no cycles */
+                if (refs[child[c]]++) { ok = 0; break; }                      /* a second parent: not a tree */
+                if (depth[i] + 1u > PT_MAX_KD_STACK) { ok = -1; break; }
+                depth[child[c]] = (uint8_t)(depth[i] + 1u);
+                if (depth[child[c]] > deepest) deepest = depth[child[c]];
+            }
         }
     }
-    return 1;
+    free(depth);
+    if (depth_out) *depth_out = deepest;
+    return ok;
 }
 
 static int unpack_impl(const void* blob, uint64_t bytes, PtSceneDesc* d, int records_only) {
@@ -169,8 +182,12 @@ static int unpack_impl(const void* blob, uint64_t bytes, PtSceneDesc* d, int rec
 
     /* semantic validation: every index the kernels will follow must be in range */
     if (d->n_tlas_nodes == 0 || d->n_lights > PT_MAX_LIGHTS) return PT_ERR_INVALID;
-    if (!kd_tree_ok(d->tlas_nodes, d->n_tlas_nodes, d->n_tlas_items, d->tlas_items, 0, d->n_tlas_items))
-        return PT_ERR_INVALID;
+    {
+        uint32_t depth = 0;
+        const int ok = kd_tree_ok(d->tlas_nodes, d->n_tlas_nodes, d->n_tlas_items, &depth);
+        if (ok < 0 || depth > PT_MAX_KD_STACK) return PT_ERR_KD_TOO_DEEP;
+        if (!ok) return PT_ERR_INVALID;
+    }
     for (uint32_t i = 0; i < d->n_tlas_items; ++i)
         if (d->tlas_items[i] >= d->n_instances) return PT_ERR_INVALID;
     for (uint32_t i = 0; i < d->n_instances; ++i) {
@@ -195,8 +212,10 @@ static int unpack_impl(const void* blob, uint64_t bytes, PtSceneDesc* d, int rec
         if (m->kind == PT_MESH_KD) {
             if (m->node_count == 0 || (uint64_t)m->node_first + m->node_count > d->n_blas_nodes) return PT_ERR_INVALID;
             if ((uint64_t)m->item_first + m->item_count > d->n_blas_items) return PT_ERR_INVALID;
-            if (!kd_tree_ok(d->blas_nodes + m->node_first, m->node_count, m->item_count, 0, 0, m->item_count))
-                return PT_ERR_INVALID;
+            uint32_t depth = 0;
+            const int ok = kd_tree_ok(d->blas_nodes + m->node_first, m->node_count, m->item_count, &depth);
+            if (ok < 0 || depth > PT_MAX_KD_STACK) return PT_ERR_KD_TOO_DEEP;
+            if (!ok) return PT_ERR_INVALID;
             for (uint32_t k = 0; k < m->item_count; ++k)
                 if (d->blas_items[m->item_first + k] >= m->tri_count) return PT_ERR_INVALID;
         } else if (m->kind == PT_MESH_TRIANGLE) {

@@ -11,7 +11,7 @@ for w in "$@"; do
 import json
 try:
     d=json.load(open("gpurun_out/${TAG}_$n.json"))
-    print("$w", round(d["value"],1), "Mrays/s", round(d["ms_per_step"],3), "ms", d["roofline"]["kernel_ms_per_step"], d["gpu_launches"])
+    print("$w", round(d["value"],1), "Mrays/s", round(d["ms_per_step"],3), "ms", d["roofline"]["kernel_ms_per_step"], d["gpu_launches"]); print("   levels", d["roofline"]["kernel_ms_per_level"])
 except Exception as e: print("$w", "FAILED", e); print(open("gpurun_out/${TAG}_$n.err").read()[-1500:])
 PY
 done
