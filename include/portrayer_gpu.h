@@ -323,6 +323,11 @@ typedef struct PtStats {
     uint32_t err_bit, err_pixel, err_sample, err_pathid, err_where, reserved3;
     /* only with PT_RENDER_KERNEL_TIMES: the extend / shadow time split by recursion level (level 0 = primary rays) */
     double ms_extend_level[16], ms_shadow_level[16];
+    /* only with PT_RENDER_COUNTERS: what the device EXECUTED, per traversal kernel ([0] extend, [1] shadow) — FP32 slab
+     * tests of the conservative cull, and the exact f64 instance tests / triangle tests / bbox gates that survived it
+     * (x_prim_flops: the primitives' own f64 op counts of those instance tests); kd splits are walked exactly as the
+     * reference walks them (k_kd_splits).  The k_* counters above are the REFERENCE's work for the same rays. */
+    uint64_t x_box_tests[2], x_instance_tests[2], x_triangle_tests[2], x_bbox_gates[2], x_prim_flops[2];
 } PtStats;
 
 typedef struct PtScene PtScene; /* opaque, library-owned */

@@ -34,6 +34,9 @@ class OracleStats(C.Structure):
 lib.oracle_render.restype = C.c_int
 lib.oracle_render.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OracleStats)]
+lib.oracle_render_rows.restype = C.c_int
+lib.oracle_render_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(OracleStats)]
 lib.oracle_trace_rays.restype = C.c_int
 lib.oracle_trace_rays.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                   C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -54,8 +57,9 @@ class OracleResult:
 
 
 def render(blob: np.ndarray, camera, params, background: np.ndarray, rgb_init: np.ndarray | None = None,
-           threads: int | None = None) -> OracleResult:
-    """The pixel loop of src/render.rs:127-150 on the CPU. `camera`/`params` are the ctypes structs of the boundary."""
+           threads: int | None = None, row_stride: int = 1, row_offset: int = 0) -> OracleResult:
+    """The pixel loop of src/render.rs:127-150 on the CPU. `camera`/`params` are the ctypes structs of the boundary.
+    row_stride > 1: only every row_stride-th row of the slice (a benchmark sample of a big frame)."""
     h, w = params.height, params.width
     rgb = np.zeros((h, w, 3), np.uint8) if rgb_init is None else np.ascontiguousarray(rgb_init).copy()
     hit_id = np.full((h, w, 2), 0xFFFFFFFF, np.uint32)
@@ -64,9 +68,9 @@ def render(blob: np.ndarray, camera, params, background: np.ndarray, rgb_init: n
     stats = OracleStats()
     background = np.ascontiguousarray(background, dtype=np.float64)
     blob = np.ascontiguousarray(blob)
-    rc = lib.oracle_render(blob.ctypes.data, blob.nbytes, C.addressof(camera), C.addressof(params),
-                           background.ctypes.data, rgb.ctypes.data, hit_id.ctypes.data, hit_t.ctypes.data,
-                           color.ctypes.data, threads or default_threads(), C.byref(stats))
+    rc = lib.oracle_render_rows(blob.ctypes.data, blob.nbytes, C.addressof(camera), C.addressof(params),
+                                background.ctypes.data, rgb.ctypes.data, hit_id.ctypes.data, hit_t.ctypes.data,
+                                color.ctypes.data, threads or default_threads(), row_stride, row_offset, C.byref(stats))
     return OracleResult(rc, rgb, hit_id, hit_t, color, stats)
 
 

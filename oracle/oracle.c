@@ -959,6 +959,8 @@ typedef struct {
     double* hit_t;
     double* color;
     int tid, n_threads;
+    uint32_t row_stride, row_offset; /* only rows y = row_offset + k * row_stride are rendered (benchmark sampling) */
+    uint32_t* next_row;              /* shared cursor: rows are handed out dynamically, like rayon's work stealing */
 } RenderJob;
 
 static int pixel_owned(const PtRenderParams* p, uint32_t x, uint32_t y) {
@@ -972,12 +974,21 @@ static int pixel_owned(const PtRenderParams* p, uint32_t x, uint32_t y) {
     return 1;
 }
 
+#define ORACLE_SEGMENT 32u
 static void* render_worker(void* arg) {
     RenderJob* j = (RenderJob*)arg;
     const PtRenderParams* p = j->p;
-    /* the pixel loop, src/render.rs:127-150: rows interleaved over threads */
-    for (uint32_t y = (uint32_t)j->tid; y < p->height; y += (uint32_t)j->n_threads) {
-        for (uint32_t x = 0; x < p->width; ++x) {
+    /* the pixel loop, src/render.rs:127-150: the sampled rows of the slice are handed out dynamically in segments of
+     * ORACLE_SEGMENT pixels (rayon's work stealing keeps every thread busy to the end of a frame; so does this) */
+    const uint32_t seg_per_row = (p->width + ORACLE_SEGMENT - 1) / ORACLE_SEGMENT;
+    for (;;) {
+        const uint32_t unit = __atomic_fetch_add(j->next_row, 1u, __ATOMIC_RELAXED);
+        const uint32_t k = unit / seg_per_row, seg = unit % seg_per_row;
+        const uint64_t yy = (uint64_t)p->y1 + j->row_offset + (uint64_t)k * j->row_stride;
+        if (yy > p->y2 || yy >= p->height) break;
+        const uint32_t y = (uint32_t)yy;
+        const uint32_t x_end = (seg + 1) * ORACLE_SEGMENT < p->width ? (seg + 1) * ORACLE_SEGMENT : p->width;
+        for (uint32_t x = seg * ORACLE_SEGMENT; x < x_end; ++x) {
             if (!pixel_owned(p, x, y)) continue;
             uint64_t i = (uint64_t)y * p->width + x;
             double c[3];
@@ -1007,6 +1018,12 @@ static void stats_add(OracleStats* a, const OracleStats* b) {
 int oracle_render(const void* blob, uint64_t bytes, const PtCamera* cam, const PtRenderParams* params,
                   const double* background, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out,
                   double* color_out, int n_threads, OracleStats* stats) {
+    return oracle_render_rows(blob, bytes, cam, params, background, rgb_inout, hit_id_out, hit_t_out, color_out, n_threads, 1, 0, stats);
+}
+
+int oracle_render_rows(const void* blob, uint64_t bytes, const PtCamera* cam, const PtRenderParams* params,
+                       const double* background, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out,
+                       double* color_out, int n_threads, uint32_t row_stride, uint32_t row_offset, OracleStats* stats) {
     Scene sc;
     int rc = scene_view(blob, bytes, &sc);
     if (rc != PT_OK) return rc;
@@ -1015,7 +1032,10 @@ int oracle_render(const void* blob, uint64_t bytes, const PtCamera* cam, const P
     if (n_threads > 256) n_threads = 256;
     RenderJob* jobs = (RenderJob*)calloc((size_t)n_threads, sizeof(RenderJob));
     pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    uint32_t next_row = 0;
+    if (row_stride == 0) row_stride = 1;
     for (int t = 0; t < n_threads; ++t) {
+        jobs[t].row_stride = row_stride; jobs[t].row_offset = row_offset; jobs[t].next_row = &next_row;
         jobs[t].cx.sc = &sc;
         jobs[t].cx.rng_mode = params->rng_mode;
         jobs[t].cx.seed = params->seed;

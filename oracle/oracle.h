@@ -24,6 +24,12 @@ int oracle_render(const void* blob, uint64_t bytes, const PtCamera* cam, const P
                   const double* background, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out,
                   double* color_out, int n_threads, OracleStats* stats);
 
+/* The same over a strided sample of the slice's rows: only rows y1 + row_offset + k * row_stride are rendered (what
+ * bench.py times as the host-CPU baseline of a frame too big to render whole). */
+int oracle_render_rows(const void* blob, uint64_t bytes, const PtCamera* cam, const PtRenderParams* params,
+                       const double* background, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out,
+                       double* color_out, int n_threads, uint32_t row_stride, uint32_t row_offset, OracleStats* stats);
+
 /* Ray::color(scene, background, 0) (src/ray.rs:139-148) for explicit rays. */
 int oracle_trace_rays(const void* blob, uint64_t bytes, uint64_t n, const double* origins, const double* dirs,
                       const double* background3, uint32_t rng_mode, uint64_t seed, uint32_t max_depth, double* color_out,

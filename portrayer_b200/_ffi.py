@@ -1,10 +1,14 @@
-"""ctypes bindings of the two product libraries.
+"""ctypes bindings of the product libraries.
 
-* ``libportrayer_gpu.so``  — the C ABI of ``include/portrayer_gpu.h`` (CUDA, sm_100a).
-* ``libportrayer_host.so`` — the C++ host mirror of the reference's scene API
-  (``portrayer_b200/host/capi.h``): scene programs, flatten, kd build, packing.
+* ``libportrayer_gpu.so``    — the C ABI of ``include/portrayer_gpu.h`` (CUDA, sm_100a).
+* ``libportrayer_host.so``   — the C++ host mirror of the reference's scene API (``portrayer_b200/host/capi.h``):
+  scene programs, flatten, kd build, packing.  GPU-free: it links only ``libportrayer_blob.so`` (the pure-host
+  pack / unpack / tile-ownership part of the C ABI).
+* ``libportrayer_render.so`` — ``Image::render`` of the host mirror, the one part of it that calls the GPU library.
 
-There is no CPU fallback: if the libraries are not built the import raises.
+There is no CPU fallback: if the libraries are not built the import raises.  ``PORTRAYER_NO_GPU_LIB=1`` (set by
+``bench.py --impl reference``, which times the CPU oracle and must not map the CUDA library) loads the GPU-free
+libraries only; every ``gpu.*`` call then fails loudly.
 """
 from __future__ import annotations
 
@@ -27,8 +31,18 @@ def _load(name: str) -> C.CDLL:
     return C.CDLL(path, mode=C.RTLD_GLOBAL)
 
 
-gpu = _load("libportrayer_gpu.so")
+class _NoGpuLibrary:
+    """stands in for the CUDA library in a PORTRAYER_NO_GPU_LIB process: any use is an error, never a fallback"""
+
+    def __getattr__(self, name):
+        raise RuntimeError(f"libportrayer_gpu.so is not loaded in this process (PORTRAYER_NO_GPU_LIB is set): {name} is unavailable")
+
+
+NO_GPU_LIB = os.environ.get("PORTRAYER_NO_GPU_LIB", "") not in ("", "0")
+blob = _load("libportrayer_blob.so")
 host = _load("libportrayer_host.so")
+gpu = _NoGpuLibrary() if NO_GPU_LIB else _load("libportrayer_gpu.so")
+host_render = None if NO_GPU_LIB else _load("libportrayer_render.so")
 
 # ----------------------------------------------------------------------------- constants (portrayer_gpu.h)
 PT_OK = 0
@@ -91,6 +105,8 @@ class PtStats(C.Structure):
         ("err_bit", C.c_uint32), ("err_pixel", C.c_uint32), ("err_sample", C.c_uint32), ("err_pathid", C.c_uint32),
         ("err_where", C.c_uint32), ("reserved3", C.c_uint32),
         ("ms_extend_level", C.c_double * 16), ("ms_shadow_level", C.c_double * 16),
+        ("x_box_tests", C.c_uint64 * 2), ("x_instance_tests", C.c_uint64 * 2), ("x_triangle_tests", C.c_uint64 * 2),
+        ("x_bbox_gates", C.c_uint64 * 2), ("x_prim_flops", C.c_uint64 * 2),
     ]
 
     def as_dict(self) -> dict:
@@ -191,6 +207,8 @@ GPU_SYMBOLS = {
     "pt_scene_set_instances": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 for _name, (_res, _args) in GPU_SYMBOLS.items():
+    if NO_GPU_LIB:
+        break
     _fn = getattr(gpu, _name)  # AttributeError here = the library does not export what the header declares
     _fn.restype = _res
     _fn.argtypes = _args
@@ -234,7 +252,12 @@ HOST_SYMBOLS = {
                                    C.POINTER(PtStats)]),
 }
 for _name, (_res, _args) in HOST_SYMBOLS.items():
-    _fn = getattr(host, _name)
+    if _name == "pth_image_render":
+        if host_render is None:
+            continue
+        _fn = getattr(host_render, _name)
+    else:
+        _fn = getattr(host, _name)
     _fn.restype = _res
     _fn.argtypes = _args
 

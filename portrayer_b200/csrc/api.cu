@@ -733,6 +733,11 @@ void accumulate_stats(PtStats* stats, const BatchCtl& c, uint32_t n_paths) {
         stats->k_triangle_tests[k] += c.work[k][2];
         stats->k_bbox_gates[k] += c.work[k][3];
         stats->k_prim_flops[k] += c.work[k][4];
+        stats->x_box_tests[k] += c.work[k][5];
+        stats->x_instance_tests[k] += c.work[k][6];
+        stats->x_triangle_tests[k] += c.work[k][7];
+        stats->x_bbox_gates[k] += c.work[k][8];
+        stats->x_prim_flops[k] += c.work[k][9];
         stats->kd_splits += c.work[k][0];
         stats->instance_tests += c.work[k][1];
         stats->triangle_tests += c.work[k][2];

@@ -110,7 +110,9 @@ struct BatchCtl {
     // | level << 8 | light << 16, [5] reserved
     uint32_t err_info[6];
     unsigned long long rays_shadow, rays_reflect, rays_refract, rays_depth_cut, shaded_hits, texel_lookups;
-    unsigned long long work[2][5];  // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates, prim_flops]
+    // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates, prim_flops (the reference's work),
+    //                       box tests, instance tests, triangle tests, bbox gates, prim_flops EXECUTED on the device]
+    unsigned long long work[2][10];
 };
 
 // per-frame constants

@@ -51,15 +51,16 @@ PT_D void background_of(const FrameParams& fp, uint32_t pixel, double* bg) {
 
 // warp-aggregated add of per-thread work counters into the batch control block
 PT_D void flush_counters(BatchCtl* ctl, int kind, const WorkCounters& wc) {
-    unsigned long long v[5] = {wc.kd_splits, wc.instance_tests, wc.triangle_tests, wc.bbox_gates, wc.prim_flops};
+    unsigned long long v[10] = {wc.kd_splits, wc.instance_tests, wc.triangle_tests, wc.bbox_gates, wc.prim_flops,
+                                wc.x_box,     wc.x_inst,         wc.x_tri,          wc.x_gate,     wc.x_prim_flops};
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < 10; ++k) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xFFFFFFFFu, v[k], off);
     }
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
+        for (int k = 0; k < 10; ++k)
             if (v[k]) atomicAdd(&ctl->work[kind][k], v[k]);
     }
 }

@@ -27,8 +27,12 @@
 namespace ptd {
 
 struct WorkCounters {
+    // the REFERENCE's work for the rays traced (what the oracle counts, culled or not)
     uint32_t kd_splits = 0, instance_tests = 0, triangle_tests = 0, bbox_gates = 0;
     uint32_t prim_flops = 0;  // sum over instance tests of the primitive's own f64 op count (SURVEY 8d P_type)
+    // what the device EXECUTED (the physical roofline of bench.py): FP32 slab tests, exact f64 instance / triangle
+    // tests and bbox gates that survived the culls, and the primitives' own f64 op counts of those instance tests
+    uint32_t x_box = 0, x_inst = 0, x_tri = 0, x_gate = 0, x_prim_flops = 0;
 };
 // f64 add/mul/div/sqrt count of one analytic ray_hit: sphere 30, cube 150, plane 25, cylinder 70, cone 90;
 // mesh types are accounted through their triangle tests and bbox gates
@@ -384,8 +388,9 @@ PT_D bool probe_covers(const float4* __restrict__ box, const RayF& r, double s, 
 //   exact(k, s, e): the reference's test of list position k over [s, e); on a hit it records it, sets e = t and returns true.
 template <bool ANY, class Exact>
 PT_D bool leaf_fold(const LeafCull& lc, uint32_t set, uint32_t rank, uint32_t gbase, uint32_t count, const RayF& rf, double s, double& e,
-                    Exact& exact) {
+                    Exact& exact, uint32_t& n_box) {
     RangeF rg = make_rangef(s, e);
+    ++n_box;
     if (!box_may_hit(lc.occ + set + 2 * (size_t)rank, rf, rg)) return false;
     const float4* __restrict__ grp = lc.grp + set + 2 * (size_t)gbase;
     const float4* __restrict__ item = lc.item + set + 16 * (size_t)gbase;
@@ -395,7 +400,11 @@ PT_D bool leaf_fold(const LeafCull& lc, uint32_t set, uint32_t rank, uint32_t gb
         uint32_t mask = 0u;
         const uint32_t g_stop = min(gc + 4u, n_groups);
         for (uint32_t g = gc; g < g_stop; ++g) {
-            if (n_groups > 1u && !box_may_hit(grp + 2 * (size_t)g, rf, rg)) continue;  // a single run's box is the occupied box
+            if (n_groups > 1u) {  // a single run's box is the occupied box
+                ++n_box;
+                if (!box_may_hit(grp + 2 * (size_t)g, rf, rg)) continue;
+            }
+            n_box += 8u;
             const float4* __restrict__ ib = item + 16 * (size_t)g;
             uint32_t m8 = 0u;
 #pragma unroll
@@ -408,7 +417,10 @@ PT_D bool leaf_fold(const LeafCull& lc, uint32_t set, uint32_t rank, uint32_t gb
         while (mask) {
             const uint32_t k = (gc << 3) + (uint32_t)__ffs((int)mask) - 1u;
             mask &= mask - 1u;
-            if (found && !box_may_hit(item + 2 * (size_t)k, rf, rg)) continue;  // the range has shrunk since phase 1
+            if (found) {  // the range has shrunk since phase 1
+                ++n_box;
+                if (!box_may_hit(item + 2 * (size_t)k, rf, rg)) continue;
+            }
             if (exact(k, s, e)) {
                 if (ANY) return true;
                 found = true;
@@ -432,9 +444,11 @@ struct BlasLeaf {
     uint32_t tri;
     uint32_t n_tests;
     uint32_t first;
+    uint32_t x_box, x_tri;  // executed slab / triangle tests
     PT_D bool operator()(uint32_t k, double s, double& e) {
         const uint32_t idx = __ldg(items + first + k);
         double tt;
+        ++x_tri;
         if (!triangle_t(tris + idx, o, d, s, e, tt, nullptr)) return false;
         e = tt;
         t = tt;
@@ -446,7 +460,7 @@ struct BlasLeaf {
         first = first_;
         if (!ANY) n_tests += count;
         const uint32_t before = n_tests;
-        const bool found = leaf_fold<ANY>(lc, set, rank, gbase, count, rf, s, e, *this);
+        const bool found = leaf_fold<ANY>(lc, set, rank, gbase, count, rf, s, e, *this, x_box);
         if (ANY && !found) n_tests = before + count;
         return found;
     }
@@ -467,7 +481,7 @@ struct BlasLeaf {
 // A 5 804-triangle fold costs a few dozen FP32 box tests and a handful of f64 triangle tests instead of 5 804 f64 tests.
 template <bool ANY>
 PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3 o, V3 d, double s, double e, double& t_out,
-                    uint32_t& sub, uint32_t& n_tests) {
+                    uint32_t& sub, uint32_t& n_tests, uint32_t& x_box, uint32_t& x_tri) {
     const RayF rf = make_rayf(o, d);
     RangeF rg = make_rangef(s, e);
     const uint32_t* __restrict__ order = sc.fold_order;
@@ -482,6 +496,7 @@ PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3
         int l = k ? min(levels, (__ffs((int)k) - 1) >> 1) : levels;
         bool skipped = false;
         for (; l >= 1; --l) {
+            ++x_box;
             if (!box_may_hit(sc.fold_aabb[l] + 2 * (size_t)(k >> (2 * l)), rf, rg)) {
                 k = min(k + (1u << (2 * l)), end);
                 skipped = true;
@@ -490,8 +505,10 @@ PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3
         }
         if (skipped) continue;
         double tt;
+        ++x_box;
         if (box_may_hit(bb0 + 2 * (size_t)k, rf, rg)) {
             const uint32_t idx = __ldg(order + k);
+            ++x_tri;
             if (triangle_t(sc.tri_pos + idx, o, d, s, e, tt, nullptr, found) && (tt < e || idx < best)) {
                 if (ANY) { n_tests += 1u; t_out = tt; sub = idx - tri_first; return true; }
                 e = tt;
@@ -524,11 +541,12 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     }
     const PtMesh* mesh = sc.meshes + mesh_id;
     const uint32_t tri_first = __ldg(&mesh->tri_first);
-    if (prim == PT_PRIM_TRIANGLE) return triangle_t(sc.tri_pos + tri_first, o, d, s, e, t, nullptr);
-    if (!bbox_gate(mesh, o, d, s, e)) return false;  // counted by the caller, like the Triangle test above
+    if (prim == PT_PRIM_TRIANGLE) { ++wc.x_tri; return triangle_t(sc.tri_pos + tri_first, o, d, s, e, t, nullptr); }
+    ++wc.x_gate;
+    if (!bbox_gate(mesh, o, d, s, e)) return false;  // (the reference's count: by the caller, like the Triangle test above)
     if (prim == PT_PRIM_MESH) {  // fold over every triangle in index order, mesh.rs:157-167
         uint32_t n_tests = 0;
-        const bool found = mesh_fold<ANY>(sc, tri_first, __ldg(&mesh->tri_count), o, d, s, e, t, sub, n_tests);
+        const bool found = mesh_fold<ANY>(sc, tri_first, __ldg(&mesh->tri_count), o, d, s, e, t, sub, n_tests, wc.x_box, wc.x_tri);
         wc.triangle_tests += n_tests;
         return found;
     }
@@ -538,9 +556,11 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     // the walk's first probe ends at s + extent (object-space extent on the world-ray parameter): the
     // clipped triangle boxes hold only if the ray has left the mesh by then
     const uint32_t set = world_exit < (float)((s + extent) * 0.999) ? 0u : sc.bl_cull.set_stride;
-    BlasLeaf<ANY> leaf{sc.bl_cull, set, sc.blas_items + item_first, sc.tri_pos + tri_first, o, d, make_rayf(o, d), 0.0, 0, 0, 0};
+    BlasLeaf<ANY> leaf{sc.bl_cull, set, sc.blas_items + item_first, sc.tri_pos + tri_first, o, d, make_rayf(o, d), 0.0, 0, 0, 0, 0, 0};
     const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), extent, o, d, s, e, blas_stack, leaf, err, wc.kd_splits);
     wc.triangle_tests += leaf.n_tests;
+    wc.x_box += leaf.x_box;
+    wc.x_tri += leaf.x_tri;
     if (hit) { t = leaf.t; sub = leaf.tri; }
     return hit;
 }
@@ -572,6 +592,8 @@ struct TlasLeaf {
         }
         double t;
         uint32_t sub;
+        ++wc.x_inst;
+        wc.x_prim_flops += prim_flop_count(pm.x);
         if (!primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc, world_exit)) return false;
         e = t;  // flat_scene.rs:92
         hit.t = t;
@@ -591,7 +613,7 @@ struct TlasLeaf {
                 wc.triangle_tests += prim == PT_PRIM_TRIANGLE ? 1u : 0u;
             }
         }
-        return leaf_fold<ANY>(sc.tl_cull, set, rank, gbase, count, rf, s, e, *this);
+        return leaf_fold<ANY>(sc.tl_cull, set, rank, gbase, count, rf, s, e, *this, wc.x_box);
     }
 };
 

@@ -7,18 +7,10 @@
 #include "assets.hpp"
 #include "examples/examples.hpp"
 #include "pack.hpp"
-#include "render.hpp"
 
 using namespace portrayer;
 
-struct PthScene {
-    ExampleScene example;
-    std::vector<uint8_t> blob;
-    double prepare_seconds = 0.0;
-    double flatten_seconds = 0.0;     // FlatScene::from alone (matrix products, inverses)
-    std::vector<double> item_bounds;  // n x 6: FlatSceneNode::bounds of every flat instance
-    std::unique_ptr<HierarchyExport> hierarchy;  // built on demand
-};
+#include "capi_internal.hpp"
 
 struct PthKdTree {
     std::vector<PtKdNode> nodes;
@@ -28,8 +20,15 @@ struct PthKdTree {
     double seconds = 0.0;
 };
 
+namespace portrayer {
+std::string& capi_error() {
+    thread_local std::string error;
+    return error;
+}
+}  // namespace portrayer
+
 namespace {
-thread_local std::string g_error;
+#define g_error (portrayer::capi_error())
 
 PthScene* finish(ExampleScene ex, int64_t kd_depth, int linear_tlas) {
     auto out = std::make_unique<PthScene>();
@@ -211,25 +210,5 @@ void pth_background(const PthScene* s, uint32_t width, uint32_t height, double* 
         }
 }
 double pth_prepare_seconds(const PthScene* s) { return s->prepare_seconds; }
-
-int pth_image_render(const PthScene* s, uint32_t width, uint32_t height, uint32_t samples, uint32_t rng_mode,
-                     uint64_t seed, uint8_t* rgb_inout, PtStats* stats) {
-    try {
-        if (s->example.prebuilt) throw std::runtime_error("prebuilt known-answer scenes have no HierScene to render");
-        Image image("", width, height);
-        std::memcpy(image.buffer().data(), rgb_inout, image.buffer().size());
-        RenderOptions opts;
-        opts.samples = samples;
-        opts.rng_mode = rng_mode;
-        opts.seed = seed;
-        opts.stats = stats;
-        image.render<NullProgress>(s->example.scene, s->example.cam, s->example.background, opts);
-        std::memcpy(rgb_inout, image.buffer().data(), image.buffer().size());
-        return 0;
-    } catch (const std::exception& e) {
-        g_error = e.what();
-        return -1;
-    }
-}
 
 }  // extern "C"
