@@ -17,9 +17,6 @@
 #include "device_scene.cuh"
 
 // tuning switches (A/B'd on the box with tools/build_variants.sh + tools/ab_bench.sh)
-#ifndef PT_KD_PREFETCH
-#define PT_KD_PREFETCH 1
-#endif
 #ifndef PT_BLAS_TWO_PHASE
 #define PT_BLAS_TWO_PHASE 1
 #endif
@@ -242,33 +239,39 @@ PT_D bool bbox_gate(const PtMesh* __restrict__ mesh, V3 o, V3 d, double s, doubl
 }
 
 // ------------------------------------------------------------------ kd walk
+// One entry per pending far child: the child's 16-byte record itself (it was fetched together with the near child, so a
+// pop costs ONE local-memory round trip instead of index -> node) and the start of its range.  The END of a pending
+// range is not stored: a push happens with the current range [s, e) and leaves [s, tp) current and [tp, e) pending, so
+// the current `e` is always the `s` of the entry on top of the stack (the walk's initial `e` when the stack is empty),
+// and a popped entry's end is the `s` of the entry below it.
 struct KdStack {
-    uint32_t node[PT_MAX_KD_STACK];
+    uint4 node[PT_MAX_KD_STACK];
     double s[PT_MAX_KD_STACK];
-    double e[PT_MAX_KD_STACK];
 };
 
 // Iterative form of ray_cast_impl (node.rs:66-203). `leaf(rank, gbase, first, count, s, e)` returns true when the
 // leaf's fold produced a hit inside [s, e) — (rank, gbase) locate the leaf's cull boxes, leaf_cull.cu —; the first
 // leaf that does ends the walk.
+// "while-while" form: every lane first descends to its next leaf (a short loop of split steps), and only then do the
+// lanes of the warp run their leaves together.  With one loop whose body is "a split step OR a whole leaf", a lane that
+// is still descending advances ONE split per leaf any other lane of its warp processes — and a leaf can hold a whole
+// KDMesh walk.
 template <class LeafFn>
-PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d, double s, double e, KdStack& stack,
+PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d, double s, const double e0, KdStack& stack,
                   LeafFn& leaf, uint32_t& err, uint32_t& n_splits) {
     int sp = 0;
+    double e = e0;
     const uint4* __restrict__ nodes4 = reinterpret_cast<const uint4*>(nodes);
     uint4 w = __ldg(nodes4);
     for (;;) {
-        const uint32_t a = w.z, b = w.w;
-        const uint32_t axis = a & 3u;
-        if (axis != 3u) {
+        bool dead = false;  // the reference would have panicked in this subtree: it yields nothing
+        while ((w.z & 3u) != 3u) {
+            const uint32_t axis = w.z & 3u;
             const double split = __hiloint2double((int)w.y, (int)w.x);
             ++n_splits;
-            const uint32_t front = a >> 2, back = b;
-#if PT_KD_PREFETCH
             // both children are fetched before the side tests: the loads' latency overlaps the f64 dependency chain
             // below instead of following it (the node fetch was the top long-scoreboard stall of the walk)
-            const uint4 wf = __ldg(nodes4 + front), wb = __ldg(nodes4 + back);
-#endif
+            const uint4 wf = __ldg(nodes4 + (w.z >> 2)), wb = __ldg(nodes4 + w.w);
             // node.rs:119-127
             double t_max = s + extent;
             if (!in_range(s, e, t_max)) t_max = e - kEps;
@@ -279,38 +282,27 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
             const double p1 = oa + da * t_max;
             const bool f0 = (p0 - split) >= 0.0;  // which_side, infinite_plane.rs:27-35
             const bool f1 = (p1 - split) >= 0.0;
-            if (f0 == f1) {  // node.rs:134-137
-#if PT_KD_PREFETCH
-                w = f0 ? wf : wb;
-#else
-                w = __ldg(nodes4 + (f0 ? front : back));
-#endif
-                continue;
-            }
-            const double tp = (split - oa) / da;  // ray_hit_axis_aligned_plane, node.rs:90-110
-            if (in_range(s, e, tp)) {
+            if (f0 != f1) {
+                const double tp = (split - oa) / da;  // ray_hit_axis_aligned_plane, node.rs:90-110
+                if (!in_range(s, e, tp)) {
+                    err |= PT_DEVERR_KD_PLANE;  // .expect("bug: ray should definitely hit infinite plane")
+                    dead = true;
+                    break;
+                }
                 // near child on [s, tp); if it misses, far child on [tp, e). node.rs:150-166
-                stack.node[sp] = f0 ? back : front;
+                stack.node[sp] = f0 ? wb : wf;
                 stack.s[sp] = tp;
-                stack.e[sp] = e;
                 ++sp;
-#if PT_KD_PREFETCH
-                w = f0 ? wf : wb;
-#else
-                w = __ldg(nodes4 + (f0 ? front : back));
-#endif
                 e = tp;
-                continue;
             }
-            err |= PT_DEVERR_KD_PLANE;  // .expect("bug: ray should definitely hit infinite plane")
-        } else if (b != 0u && leaf(w.x, w.y, a >> 2, b, s, e)) {
-            return true;
+            w = f0 ? wf : wb;  // node.rs:134-137
         }
+        if (!dead && w.w != 0u && leaf(w.x, w.y, w.z >> 2, w.w, s, e)) return true;
         if (sp == 0) return false;
         --sp;
-        w = __ldg(nodes4 + stack.node[sp]);
+        w = stack.node[sp];
         s = stack.s[sp];
-        e = stack.e[sp];
+        e = sp ? stack.s[sp - 1] : e0;
     }
 }
 

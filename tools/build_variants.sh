@@ -11,7 +11,7 @@ while [ $# -ge 2 ]; do
   mkdir -p $d
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -Iinclude $flags \
     -shared portrayer_b200/csrc/*.cu build/scene_blob.o build/tiles.o -o $d/libportrayer_gpu.so &
-  cp portrayer_b200/lib/libportrayer_host.so $d/
+  cp portrayer_b200/lib/libportrayer_host.so portrayer_b200/lib/libportrayer_blob.so portrayer_b200/lib/libportrayer_render.so $d/
 done
 wait
 ls build/variants
