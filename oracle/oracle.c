@@ -142,6 +142,7 @@ typedef struct {
     uint32_t rng_mode;
     uint64_t seed;
     uint32_t max_depth;
+    int linear_scene; /* PT_RENDER_LINEAR_TLAS: the scene root is the FlatScene itself (no k-d tree), see scene_ray_cast */
     OracleStats st;
     int error;
 } Ctx;
@@ -640,8 +641,24 @@ static int instance_ray_cast(Ctx* cx, uint32_t inst, const Ray* ray, Range* rang
     return 1;
 }
 
-/* scene.root.ray_cast: KDTreeNode<FlatSceneNode>::ray_cast, node.rs:27-31 */
+/* scene.root.ray_cast: KDTreeNode<FlatSceneNode>::ray_cast, node.rs:27-31.
+ * Cross-check mode: Scene<R> is generic over its RayCast root (scene.rs, ray.rs:139-148); with the
+ * FlatScene as the root the cast is `[FlatSceneNode]::ray_cast`, ray.rs:87-99 over flat_scene.rs:71-99 — every
+ * instance in list order sharing one shrinking range, no tree.  Same nearest hit as the tree walk wherever the tree
+ * loses nothing (the walk's probe / EPSILON quirks can), first-listed instance wins an exact tie in both. */
 static int scene_ray_cast(Ctx* cx, const Ray* ray, Range* range, Isect* out, uint32_t* out_inst) {
+    if (cx->linear_scene) {
+        int found = 0;
+        for (uint32_t inst = 0; inst < cx->sc->h.n_instances; ++inst) {
+            Isect hit;
+            if (instance_ray_cast(cx, inst, ray, range, &hit)) { /* sets range->end, ray.rs:91-95 */
+                *out = hit;
+                *out_inst = inst;
+                found = 1;
+            }
+        }
+        return found;
+    }
     Tree tr = {0, NULL, cx->sc->tlas_nodes, cx->sc->tlas_items};
     return kd_cast(cx, &tr, 0, ray, range, cx->sc->h.tlas_extent, out, out_inst);
 }
@@ -1040,6 +1057,7 @@ int oracle_render_rows(const void* blob, uint64_t bytes, const PtCamera* cam, co
         jobs[t].cx.rng_mode = params->rng_mode;
         jobs[t].cx.seed = params->seed;
         jobs[t].cx.max_depth = params->max_depth ? params->max_depth : PT_MAX_RECURSION_DEPTH;
+        jobs[t].cx.linear_scene = (params->flags & PT_RENDER_LINEAR_TLAS) != 0;
         jobs[t].cam = cam; jobs[t].p = params; jobs[t].bg = background;
         jobs[t].rgb = rgb_inout; jobs[t].hit_id = hit_id_out; jobs[t].hit_t = hit_t_out; jobs[t].color = color_out;
         jobs[t].tid = t; jobs[t].n_threads = n_threads;

@@ -6,10 +6,11 @@ Only what the hot path needs lives here:
 * ``host/``  C++ mirror of the reference's scene API (stays Rust in the target design)
 * this Python layer: ctypes bindings, the ``Image.render`` entry point, multi-GPU plumbing.
 """
-from ._ffi import (PT_RENDER_COUNTERS, PT_RNG_FIXED, PT_RNG_HASH, PortrayerError, PtCamera, PtRenderParams,  # noqa: F401
+from ._ffi import (PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS, PT_RNG_FIXED, PT_RNG_HASH, PortrayerError, PtCamera, PtRenderParams,  # noqa: F401
                    PtStats)
 from .render import DeviceScene, Frame, Image, make_params, samples_from_env  # noqa: F401
 from .scene import Scene, example_names  # noqa: F401
 
 __all__ = ["Scene", "example_names", "Image", "DeviceScene", "Frame", "make_params", "samples_from_env", "PtStats",
-           "PtCamera", "PtRenderParams", "PortrayerError", "PT_RNG_FIXED", "PT_RNG_HASH", "PT_RENDER_COUNTERS"]
+           "PtCamera", "PtRenderParams", "PortrayerError", "PT_RNG_FIXED", "PT_RNG_HASH", "PT_RENDER_COUNTERS",
+           "PT_RENDER_LINEAR_TLAS"]

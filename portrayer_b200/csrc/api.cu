@@ -128,6 +128,7 @@ public:
         cached_ = 0;
     }
     void set_limit(size_t bytes) { limit_ = bytes; }
+    size_t cached_bytes() const { return cached_; }
 
 private:
     static cudaError_t raw_alloc(void** p, size_t bytes) { return PINNED ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes); }
@@ -595,6 +596,33 @@ void free_frame(PtFrame* f) {
     delete f;
 }
 
+// bytes of a node pool of `capacity` nodes (alloc_pool's layout)
+size_t pool_bytes(uint64_t capacity, uint32_t n_lights) {
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    return 12 * up(capacity * sizeof(double)) + 6 * up(capacity * sizeof(uint32_t)) + up(capacity) + up(capacity * std::max<uint32_t>(n_lights, 1));
+}
+size_t free_device_bytes() {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return free_b + g_dev.cached_bytes();
+}
+// Paths per batch when the caller does not say.  Every recursion level of a batch is one launch of each kernel, and a
+// launch ends when its slowest warp does: the more rays a level holds, the smaller the share of that tail.  Measured on
+// graphics-castle 3840x2160 x 16 (profiles/r02_batch_size.txt): 1 Mi paths 965 Mrays/s (castle-hd), 4 Mi 1 465, 8 Mi 1 543,
+// 16 Mi 1 561, 32 Mi 1 575.  16 Mi paths = a 17 GB node pool when materials reflect (8 nodes per path): a tenth of a
+// B200's 180 GB.  Smaller devices (and a B200 that is nearly full, see create_frame) get the 4 Mi batch.
+constexpr uint64_t kSmallBatchPaths = 1ull << 22, kLargeBatchPaths = 1ull << 24;
+uint64_t default_batch_paths() {
+    static uint64_t v = 0;
+    if (!v) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+        v = total_b >= (96ull << 30) ? kLargeBatchPaths : kSmallBatchPaths;
+        if (const char* e = getenv("PT_BATCH_PATHS")) { const long long n = atoll(e); if (n > 0) v = (uint64_t)n; }
+    }
+    return v;
+}
+
 // carve the SoA node pool out of one allocation
 int alloc_pool(unsigned char** d_pool, NodePool* pool, uint32_t capacity, uint32_t n_lights) {
     const size_t cap = capacity;
@@ -693,18 +721,18 @@ struct KernelTimer {
 // Stream path: run the levels of one batch kernel by kernel; the host looks at the control block after every
 // level and stops at the first level without rays.  Leaves the final control block in *h_ctl.
 int run_levels_stream(int slot, uint32_t n_lights, uint64_t capacity, BatchCtl* d_ctl, BatchCtl* h_ctl, uint32_t n_paths,
-                      int n_levels, bool count, cudaStream_t st, uint32_t* launches, KernelTimer* timer) {
+                      int n_levels, bool count, cudaStream_t st, uint32_t* launches, KernelTimer* timer, bool linear = false) {
     for (int level = 0; level < n_levels; ++level) {
         // level d holds at most n_paths * 2^d rays, and never more than the pool
         const uint64_t bound = (uint64_t)n_paths << std::min(level, 31);
         const uint64_t max_items = std::min<uint64_t>(bound, capacity);
         timer->level = level;
         timer->begin(0, st);
-        launch_extend(slot, max_items, count, st);
+        launch_extend(slot, max_items, count, linear, st);
         timer->end(st);
         if (n_lights) {
             timer->begin(1, st);
-            launch_shadow(slot, max_items, n_lights, count, st);
+            launch_shadow(slot, max_items, n_lights, count, linear, st);
             timer->end(st);
         }
         timer->begin(2, st);
@@ -814,23 +842,36 @@ int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* p
                     : p.bg_mode == PT_BG_PER_ROW ? (uint64_t)p.height * 3
                                                  : 3;
     // batch geometry: whole pixels per batch so a pixel's samples are summed in one place, in order
-    uint64_t max_paths = p.max_batch_paths ? p.max_batch_paths : (1ull << 22);
-    uint64_t slots = std::max<uint64_t>(1, max_paths / p.samples);
-    slots = std::min<uint64_t>(slots, std::max<uint64_t>(owned, 1));
-    if (slots * p.samples > 0x7FFFFFFFull) slots = 0x7FFFFFFFull / p.samples;
-    if (slots == 0) { free_frame(f); return fail(PT_ERR_INVALID, "samples too large"); }
+    uint64_t max_paths = p.max_batch_paths ? p.max_batch_paths : default_batch_paths();
+    uint64_t slots = 0, capacity = 0;
+    auto size_batch = [&]() -> int {
+        slots = std::max<uint64_t>(1, max_paths / p.samples);
+        slots = std::min<uint64_t>(slots, std::max<uint64_t>(owned, 1));
+        if (slots * p.samples > 0x7FFFFFFFull) slots = 0x7FFFFFFFull / p.samples;
+        if (slots == 0) return fail(PT_ERR_INVALID, "samples too large");
+        const uint64_t batch_paths = slots * p.samples;
+        capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * kPoolNodesPerPath : batch_paths);
+        capacity = std::max<uint64_t>(capacity, batch_paths);
+        // the shade kernel keeps counting refused allocations after the pool is full (pool_count is how the retry sizes its
+        // batches), and the graph path runs one more level after the pool has filled: up to 5 x capacity in all, which must
+        // not wrap the 32-bit counter
+        capacity = std::min<uint64_t>(capacity, 0x30000000ull);
+        // the shadow kernel's 32-bit work cursor counts (hit, light) pairs
+        capacity = std::min<uint64_t>(capacity, 0xFFF00000ull / std::max<uint32_t>(scene->h.n_lights, 1));
+        if (capacity < batch_paths) return fail(PT_ERR_INVALID, "batch too large for %u lights: lower max_batch_paths", scene->h.n_lights);
+        return PT_OK;
+    };
+    {
+        int rc = size_batch();
+        // the library's own default may be too much for what is free right now: fall back to the small batch
+        while (rc == PT_OK && !p.max_batch_paths && max_paths > kSmallBatchPaths && pool_bytes(capacity, scene->h.n_lights) > free_device_bytes() / 2) {
+            max_paths /= 2;
+            rc = size_batch();
+        }
+        if (rc != PT_OK) { free_frame(f); return rc; }
+    }
     f->batch_slots = (uint32_t)slots;
     f->batch_slots_now = f->batch_slots;
-    const uint64_t batch_paths = slots * p.samples;
-    uint64_t capacity = p.node_pool_capacity ? p.node_pool_capacity : (scene->has_reflective ? batch_paths * kPoolNodesPerPath : batch_paths);
-    capacity = std::max<uint64_t>(capacity, batch_paths);
-    // the shade kernel keeps counting refused allocations after the pool is full (pool_count is how the retry sizes its
-    // batches), and the graph path runs one more level after the pool has filled: up to 5 x capacity in all, which must
-    // not wrap the 32-bit counter
-    capacity = std::min<uint64_t>(capacity, 0x30000000ull);
-    // the shadow kernel's 32-bit work cursor counts (hit, light) pairs
-    capacity = std::min<uint64_t>(capacity, 0xFFF00000ull / std::max<uint32_t>(scene->h.n_lights, 1));
-    if (capacity < batch_paths) { free_frame(f); return fail(PT_ERR_INVALID, "batch too large for %u lights: lower max_batch_paths", scene->h.n_lights); }
     const uint64_t n_batches = owned ? (owned + slots - 1) / slots : 1;
     f->h_ctl_count = (uint32_t)std::min<uint64_t>(n_batches, 1u << 16);
 
@@ -884,7 +925,7 @@ int render_stream_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void*
         launch_camera(f->slot, first_slot, n_slots, S, st);
         *launches_out += 1;
         int rc = run_levels_stream(f->slot, f->scene->h.n_lights, f->pool.capacity, f->d_ctl, f->h_ctl, n_paths, f->n_levels, count,
-                                   st, launches_out, &timer);
+                                   st, launches_out, &timer, (f->params.flags & PT_RENDER_LINEAR_TLAS) != 0);
         if (rc != PT_OK) return rc;
         timer.collect(stats);
         if (f->h_ctl->error_bits & PT_DEVERR_OVERFLOW) {
@@ -1271,7 +1312,7 @@ int pt_frame_enqueue(PtFrame* frame, void* stream) {
     const FrameState state = frame_state(f);
     CUDA_TRY(cudaEventRecord(f->ev_start, st));
     CUDA_TRY(upload_state(f->slot, state, st));
-    const bool want_stream = (f->params.flags & (PT_RENDER_KERNEL_TIMES | PT_RENDER_NO_GRAPH)) != 0 || !graphs_enabled() ||
+    const bool want_stream = (f->params.flags & (PT_RENDER_KERNEL_TIMES | PT_RENDER_NO_GRAPH | PT_RENDER_LINEAR_TLAS)) != 0 || !graphs_enabled() ||
                              f->graph_failed;
     if (owned != 0 && !want_stream) {
         int rc = enqueue_graph_path(f, st);
@@ -1518,6 +1559,20 @@ int pt_render(PtScene* scene, const PtCamera* camera, const PtRenderParams* para
             g_frame_cache.erase(g_frame_cache.begin() + oldest);
         }
         g_frame_cache.push_back(f);
+        // ... and by bytes: node pools of big frames are GBs each; idle frames may hold a quarter of the device at most
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+        for (;;) {
+            size_t held = 0, oldest = g_frame_cache.size();
+            for (size_t i = 0; i < g_frame_cache.size(); ++i) {
+                const PtFrame* c = g_frame_cache[i];
+                held += pool_bytes(c->pool.capacity, c->n_lights_cap);
+                if (c != f && (oldest == g_frame_cache.size() || c->last_use < g_frame_cache[oldest]->last_use)) oldest = i;
+            }
+            if (held <= total_b / 4 || oldest == g_frame_cache.size()) break;
+            free_frame(g_frame_cache[oldest]);
+            g_frame_cache.erase(g_frame_cache.begin() + oldest);
+        }
     }
     f->last_use = ++g_frame_tick;
     if (hit_id_out || hit_t_out) {
@@ -1597,7 +1652,7 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
         launch_load_rays(slot, (uint32_t)first, n_paths, g_stream);
         ++launches;
         KernelTimer timer;
-        rc = run_levels_stream(slot, scene->h.n_lights, capacity, d_ctl, h_ctl, n_paths, n_levels, count, g_stream, &launches, &timer);
+        rc = run_levels_stream(slot, scene->h.n_lights, capacity, d_ctl, h_ctl, n_paths, n_levels, count, g_stream, &launches, &timer, (flags & PT_RENDER_LINEAR_TLAS) != 0);
         if (rc != PT_OK) break;
         if (h_ctl->error_bits & PT_DEVERR_OVERFLOW) {
             if (n_paths == 1) { rc = fail(PT_ERR_OVERFLOW, "%s", panic_text(PT_ERR_OVERFLOW)); break; }

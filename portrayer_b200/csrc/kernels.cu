@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(kBlock) load_rays_kernel(int slot_id, uint32_t
 }
 
 // ------------------------------------------------------------------ extend (closest hit)
-template <bool COUNT>
+// LINEAR: the PT_RENDER_LINEAR_TLAS cross-check (scene_cast_linear: no k-d tree, every instance in list order)
+template <bool COUNT, bool LINEAR = false>
 __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(int slot_id) {
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
         const V3 d = v3(pool.dx[i], pool.dy[i], pool.dz[i]);
         Hit hit{(double)INFINITY, kNone, 0};
         const uint32_t err_before = err;
-        const bool found = scene_cast<false, COUNT>(sc, o, d, hit, tlas_stack, blas_stack, err, wc);
+        const bool found = LINEAR ? scene_cast_linear<false, COUNT>(sc, o, d, hit, blas_stack, err, wc)
+                                  : scene_cast<false, COUNT>(sc, o, d, hit, tlas_stack, blas_stack, err, wc);
         if (err != err_before) record_error(fs.fp, pool, ctl, err & ~err_before, i, 0u | level << 8);
         pool.t[i] = found ? hit.t : (double)INFINITY;
         pool.inst[i] = found ? hit.inst : kNone;
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
 }
 
 // ------------------------------------------------------------------ shadow (any hit), light-major
-template <bool COUNT>
+template <bool COUNT, bool LINEAR = false>
 __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(int slot_id) {
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
@@ -224,7 +226,8 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
         const V3 light_dir = hit_to_light / light_dist;
         Hit hit{(double)INFINITY, kNone, 0};
         const uint32_t err_before = err;
-        const bool occluded = scene_cast<true, COUNT>(sc, hit_point, light_dir, hit, tlas_stack, blas_stack, err, wc);
+        const bool occluded = LINEAR ? scene_cast_linear<true, COUNT>(sc, hit_point, light_dir, hit, blas_stack, err, wc)
+                                     : scene_cast<true, COUNT>(sc, hit_point, light_dir, hit, tlas_stack, blas_stack, err, wc);
         if (err != err_before) record_error(fp, pool, ctl, err & ~err_before, i, 1u | level << 8 | l << 16);
         pool.occl[(size_t)l * pool.capacity + i] = occluded ? 1 : 0;
         ++cast;
@@ -887,14 +890,16 @@ void launch_load_rays(int slot, uint32_t first, uint32_t n_paths, cudaStream_t s
     load_rays_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(slot, first, n_paths);
 }
 // A level can never hold more rays than `max_items`; the persistent grid is capped to it.
-void launch_extend(int slot, uint64_t max_items, bool count, cudaStream_t st) {
+void launch_extend(int slot, uint64_t max_items, bool count, bool linear, cudaStream_t st) {
     const int grid = capped(g_grid_extend[count ? 1 : 0], max_items);
-    if (count) extend_kernel<true><<<grid, kBlock, 0, st>>>(slot);
+    if (linear) extend_kernel<true, true><<<grid, kBlock, 0, st>>>(slot);
+    else if (count) extend_kernel<true><<<grid, kBlock, 0, st>>>(slot);
     else extend_kernel<false><<<grid, kBlock, 0, st>>>(slot);
 }
-void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, bool count, cudaStream_t st) {
+void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, bool count, bool linear, cudaStream_t st) {
     const int grid = capped(g_grid_shadow[count ? 1 : 0], max_items * (n_lights ? n_lights : 1));
-    if (count) shadow_kernel<true><<<grid, kBlock, 0, st>>>(slot);
+    if (linear) shadow_kernel<true, true><<<grid, kBlock, 0, st>>>(slot);
+    else if (count) shadow_kernel<true><<<grid, kBlock, 0, st>>>(slot);
     else shadow_kernel<false><<<grid, kBlock, 0, st>>>(slot);
 }
 void launch_shade(int slot, uint64_t max_items, cudaGraphConditionalHandle loop, cudaStream_t st) {

@@ -44,8 +44,9 @@ void launch_group_bounds(const float4* in, uint32_t n, uint32_t run, float4* out
 // stream path: one launch per call; batch / level bookkeeping lives in the device control block
 void launch_camera(int slot, uint32_t first_slot, uint32_t n_slots, uint32_t samples, cudaStream_t st);
 void launch_load_rays(int slot, uint32_t first, uint32_t n_paths, cudaStream_t st);
-void launch_extend(int slot, uint64_t max_items, bool count, cudaStream_t st);
-void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, bool count, cudaStream_t st);
+// linear: the PT_RENDER_LINEAR_TLAS cross-check kernels (always counting)
+void launch_extend(int slot, uint64_t max_items, bool count, bool linear, cudaStream_t st);
+void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, bool count, bool linear, cudaStream_t st);
 void launch_shade(int slot, uint64_t max_items, cudaGraphConditionalHandle loop, cudaStream_t st);
 void launch_tree_eval(int slot, uint32_t n_paths, cudaStream_t st);
 void launch_resolve(int slot, uint32_t n_slots, cudaStream_t st);

@@ -20,6 +20,9 @@
 #ifndef PT_BLAS_TWO_PHASE
 #define PT_BLAS_TWO_PHASE 1
 #endif
+#ifndef PT_ANY_CHEAP_FIRST
+#define PT_ANY_CHEAP_FIRST 1
+#endif
 
 namespace ptd {
 
@@ -406,6 +409,21 @@ PT_D bool leaf_fold(const LeafCull& lc, uint32_t set, uint32_t rank, uint32_t gb
         }
         const uint32_t left = count - (gc << 3);
         if (left < 32u) mask &= (1u << left) - 1u;  // the padding slots of the last run
+#if PT_ANY_CHEAP_FIRST
+        if (ANY) {
+            // "is there a hit" does not depend on the order of the tests: the analytic candidates go first, a mesh
+            // candidate (a whole KDMesh walk / Mesh fold) only when none of them stopped the ray
+            uint32_t later = 0u;
+            while (mask) {
+                const uint32_t bit = mask & (0u - mask);
+                mask ^= bit;
+                const uint32_t k = (gc << 3) + (uint32_t)__ffs((int)bit) - 1u;
+                if (exact.expensive(k)) { later |= bit; continue; }
+                if (exact(k, s, e)) return true;
+            }
+            mask = later;
+        }
+#endif
         while (mask) {
             const uint32_t k = (gc << 3) + (uint32_t)__ffs((int)mask) - 1u;
             mask &= mask - 1u;
@@ -437,6 +455,7 @@ struct BlasLeaf {
     uint32_t n_tests;
     uint32_t first;
     uint32_t x_box, x_tri;  // executed slab / triangle tests
+    PT_D bool expensive(uint32_t) const { return false; }
     PT_D bool operator()(uint32_t k, double s, double& e) {
         const uint32_t idx = __ldg(items + first + k);
         double tt;
@@ -557,6 +576,25 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     return hit;
 }
 
+// FlatSceneNode::ray_cast of instance `inst` (flat_scene.rs:71-99): the ray in object space, direction NOT renormalised
+// (flat_scene.rs:75, ray.rs:130-135), then the primitive's own test over [s, e).  `pm` = (prim, mesh) of the record.
+template <bool ANY>
+PT_D bool instance_t(const DScene& sc, uint32_t inst, uint2 pm, V3 o, V3 d, const RayF& rf, double s, double e, double& t,
+                     uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc) {
+    const PtInstance* rec = sc.instances + inst;
+    double m[12];
+    load_doubles12(rec->invtrans, m);
+    const V3 lo = xf_point(m, o), ld = xf_dir(m, d);
+    float world_exit = INFINITY;
+    if (pm.x == PT_PRIM_KDMESH) {
+        float tn;
+        box_interval(sc.inst_aabb + 2 * (size_t)inst, rf, tn, world_exit);
+    }
+    ++wc.x_inst;
+    wc.x_prim_flops += prim_flop_count(pm.x);
+    return primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc, world_exit);
+}
+
 // leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99)
 template <bool ANY, bool COUNT>
 struct TlasLeaf {
@@ -569,24 +607,16 @@ struct TlasLeaf {
     uint32_t& err;
     WorkCounters& wc;
     uint32_t first;
-    // FlatSceneNode::ray_cast of list position k: the ray in object space, direction NOT renormalised (flat_scene.rs:75, ray.rs:130-135)
-    PT_D bool operator()(uint32_t k, double s, double& e) {
+    PT_D bool expensive(uint32_t k) const {  // a Mesh / KDMesh candidate
+        const uint32_t prim = __ldg(&sc.instances[__ldg(sc.tlas_items + first + k)].prim);
+        return prim == PT_PRIM_MESH || prim == PT_PRIM_KDMESH;
+    }
+    PT_D bool operator()(uint32_t k, double s, double& e) {  // list position k
         const uint32_t inst = __ldg(sc.tlas_items + first + k);
-        const PtInstance* rec = sc.instances + inst;
-        double m[12];
-        load_doubles12(rec->invtrans, m);
-        const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&rec->prim));
-        const V3 lo = xf_point(m, o), ld = xf_dir(m, d);
-        float world_exit = INFINITY;
-        if (pm.x == PT_PRIM_KDMESH) {
-            float tn;
-            box_interval(sc.inst_aabb + 2 * (size_t)inst, rf, tn, world_exit);
-        }
+        const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&sc.instances[inst].prim));
         double t;
         uint32_t sub;
-        ++wc.x_inst;
-        wc.x_prim_flops += prim_flop_count(pm.x);
-        if (!primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc, world_exit)) return false;
+        if (!instance_t<ANY>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) return false;
         e = t;  // flat_scene.rs:92
         hit.t = t;
         hit.inst = inst;
@@ -617,6 +647,35 @@ PT_D bool scene_cast(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& tlas_stack
     const uint32_t set = probe_covers(sc.tl_root, rf, kEps, sc.tlas_extent) ? 0u : sc.tl_cull.set_stride;
     TlasLeaf<ANY, COUNT> leaf{sc, set, o, d, rf, blas_stack, hit, err, wc, 0};
     return kd_walk(sc.tlas_nodes, sc.tlas_extent, o, d, kEps, (double)INFINITY, tlas_stack, leaf, err, wc.kd_splits);
+}
+
+// PT_RENDER_LINEAR_TLAS: the scene WITHOUT its k-d tree — FlatScene as the root, i.e. `[FlatSceneNode]::ray_cast`
+// (ray.rs:87-99 over flat_scene.rs:71-99): every instance in list order with one shrinking range [EPSILON, inf).
+// The semantic cross-check of the tree walk: no FP32 cull, no tree, O(instances) per ray.
+template <bool ANY, bool COUNT>
+PT_D bool scene_cast_linear(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& blas_stack, uint32_t& err, WorkCounters& wc) {
+    const RayF rf = make_rayf(o, d);
+    const double s = kEps;
+    double e = (double)INFINITY;
+    bool found = false;
+    for (uint32_t inst = 0; inst < sc.n_instances; ++inst) {
+        const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&sc.instances[inst].prim));
+        if (COUNT) {
+            ++wc.instance_tests;
+            wc.prim_flops += prim_flop_count(pm.x);
+            wc.bbox_gates += (pm.x == PT_PRIM_MESH || pm.x == PT_PRIM_KDMESH) ? 1u : 0u;
+            wc.triangle_tests += pm.x == PT_PRIM_TRIANGLE ? 1u : 0u;
+        }
+        double t;
+        uint32_t sub;
+        if (instance_t<ANY>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) {
+            e = t;
+            hit.t = t; hit.inst = inst; hit.sub = sub;
+            found = true;
+            if (ANY) return true;
+        }
+    }
+    return found;
 }
 
 }  // namespace ptd

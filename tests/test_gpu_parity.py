@@ -431,3 +431,24 @@ def test_castle_kd_plane_panic_device(gpu_ready):
     assert (stats.err_pixel % w, stats.err_pixel // w, stats.err_sample) == (x, y, 57)
     ref = parity.render_oracle(scene, samples=64, rng="hash", seed=1, size=(w, h), slice_=(x - 1, y, x - 1, y))
     assert ref.rc == 0 and np.array_equal(img.buffer[y, x - 1], ref.rgb[y, x - 1])
+
+
+# SURVEY 8 row a20, PT_RENDER_LINEAR_TLAS: the scene WITHOUT its k-d tree — `[FlatSceneNode]::ray_cast`
+# (ray.rs:87-99 over flat_scene.rs:71-99) — on the device against the oracle's linear mode (bit-exact like the tree
+# walk), and against the device's own tree walk: the tree is only an index, so hit ids agree wherever the walk's probe /
+# EPSILON quirks lose nothing (they lose nothing on these scenes).
+@pytest.mark.parametrize("name,samples,rng,scale", [
+    ("nonhier", 1, "fixed", 1), ("primitives", 1, "fixed", 1), ("instance", 1, "fixed", 1), ("macho-cows", 1, "fixed", 2),
+    ("glossy-reflection", 2, "hash", 2), ("water-glass", 2, "hash", 2), ("big-scene", 1, "fixed", 8)])
+def test_linear_scene_cross_check(gpu_ready, name, samples, rng, scale):
+    scene = pt.Scene.example(name)
+    size = (scene.width // scale, scene.height // scale)
+    lin = _report(name, samples=samples, rng=rng, size=size, flags=pt.PT_RENDER_LINEAR_TLAS)
+    parity.assert_parity(lin)
+    assert lin["hit_t_bit_identical"], lin
+    img_lin, _ = parity.render_gpu(scene, samples=samples, rng=rng, size=size, flags=pt.PT_RENDER_LINEAR_TLAS)
+    img_kd, _ = parity.render_gpu(scene, samples=samples, rng=rng, size=size)
+    same = np.all(img_lin.hit_id == img_kd.hit_id, axis=2)
+    assert same.mean() >= (0.995 if name == "big-scene" else 0.9999), (name, float(same.mean()))
+    assert np.array_equal(img_lin.hit_t[same], img_kd.hit_t[same])
+    assert (np.abs(img_lin.buffer.astype(int) - img_kd.buffer.astype(int)).max(axis=2) <= 1).mean() >= (0.99 if name == "big-scene" else 0.999)

@@ -113,3 +113,19 @@ def test_mesh_fold_ties_first_listed_wins():
     assert np.array_equal(hit_id[hit, 1].astype(np.int64), expect_sub[hit])
     assert np.array_equal(hit_t[hit], expect_t[hit])
     assert np.all(hit_id[~hit, 0] == 0xFFFFFFFF)
+
+
+# the oracle's linear mode (`[FlatSceneNode]::ray_cast`, ray.rs:87-99 — no k-d tree) is the semantic
+# cross-check of its tree walk: same nearest hit on scenes where the walk's quirks lose nothing.
+@pytest.mark.parametrize("name,scale", [("nonhier", 2), ("primitives", 4), ("instance", 2), ("hier", 2)])
+def test_tree_walk_equals_linear_scan(name, scale):
+    import parity
+    scene = pt.Scene.example(name)
+    size = (scene.width // scale, scene.height // scale)
+    kd = parity.render_oracle(scene, samples=1, rng="fixed", size=size)
+    lin = parity.render_oracle(scene, samples=1, rng="fixed", size=size, flags=pt.PT_RENDER_LINEAR_TLAS)
+    assert kd.rc == 0 and lin.rc == 0
+    assert np.array_equal(kd.hit_id, lin.hit_id)
+    assert np.array_equal(kd.hit_t, lin.hit_t)
+    assert np.array_equal(kd.rgb, lin.rgb)
+    assert lin.stats.kd_splits < kd.stats.kd_splits  # only KDMesh trees are walked in linear mode
