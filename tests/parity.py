@@ -16,11 +16,23 @@ RGB_MIN_FRACTION = 0.999
 DT_EPSILON = 1e-7  # relative: |t_gpu - t_cpu| <= DT_EPSILON * max(1, |t|) at a hit-id mismatch counts as a grazing edge
 
 
-def render_oracle(scene: pt.Scene, samples=1, rng="fixed", seed=1, size=None, threads=None, **kw):
+def render_oracle(scene: pt.Scene, samples=1, rng="fixed", seed=1, size=None, threads=None, row_stride=1, row_offset=0, **kw):
+    """row_stride > 1: the oracle renders only rows row_offset + k * row_stride (a strided sample of a frame that is too
+    big to render whole on the CPU); the other rows of the result are untouched (hit ids kNone, t = inf, rgb 0)."""
     w, h = size or (scene.width, scene.height)
     bg, bg_mode = _background_arg(scene, w, h)
     params = make_params(w, h, samples, rng, seed, bg_mode=bg_mode, **kw)
-    return oracle.render(scene.blob, scene.camera(w, h), params, bg, threads=threads)
+    return oracle.render(scene.blob, scene.camera(w, h), params, bg, threads=threads, row_stride=row_stride, row_offset=row_offset)
+
+
+def compare_rows(gpu_img: pt.Image, ref: "oracle.OracleResult", rows, label: str = "") -> dict:
+    """compare() restricted to the image rows the oracle rendered"""
+    class View:
+        pass
+    g, r = View(), View()
+    g.buffer, g.hit_id, g.hit_t = gpu_img.buffer[rows], gpu_img.hit_id[rows], gpu_img.hit_t[rows]
+    r.rgb, r.hit_id, r.hit_t = ref.rgb[rows], ref.hit_id[rows], ref.hit_t[rows]
+    return compare(g, r, label)
 
 
 def render_gpu(scene: pt.Scene, samples=1, rng="fixed", seed=1, size=None, dscene=None, **kw):
