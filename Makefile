@@ -21,6 +21,7 @@ BLOB_LIB  := $(PKG)/lib/libportrayer_blob.so
 RENDER_LIB := $(PKG)/lib/libportrayer_render.so
 ORACLE_LIB:= oracle/liboracle.so
 HOST_TEST := tests/cpp/test_host
+GROUP_TEST := tests/cpp/test_group
 EXAMPLE_BIN := $(PKG)/lib/portrayer_example
 
 GPU_SRC   := $(wildcard $(PKG)/csrc/*.cu)
@@ -33,7 +34,7 @@ all: gpu host oracle hosttest example
 gpu: $(GPU_LIB)
 host: $(HOST_LIB) $(RENDER_LIB)
 oracle: $(ORACLE_LIB)
-hosttest: $(HOST_TEST)
+hosttest: $(HOST_TEST) $(GROUP_TEST)
 example: $(EXAMPLE_BIN)
 
 $(PKG)/lib:
@@ -67,10 +68,13 @@ $(ORACLE_LIB): oracle/oracle.c oracle/oracle.h include/portrayer_gpu.h
 $(HOST_TEST): tests/cpp/test_host.cpp $(HOST_LIB) $(RENDER_LIB)
 	$(CXX) $(CXXFLAGS) -I$(PKG)/host $< -o $@ -L$(PKG)/lib -lportrayer_render -lportrayer_host -lportrayer_gpu -lportrayer_blob -Wl,-rpath,'$$ORIGIN/../../$(PKG)/lib'
 
+$(GROUP_TEST): tests/cpp/test_group.cpp $(HOST_LIB) $(RENDER_LIB)
+	$(CXX) $(CXXFLAGS) -I$(PKG)/host $< -o $@ -L$(PKG)/lib -lportrayer_render -lportrayer_host -lportrayer_gpu -lportrayer_blob -Wl,-rpath,'$$ORIGIN/../../$(PKG)/lib'
+
 $(EXAMPLE_BIN): $(PKG)/host/tools/example_main.cpp $(HOST_LIB) $(RENDER_LIB)
 	$(CXX) $(CXXFLAGS) -I$(PKG)/host $< -o $@ -L$(PKG)/lib -lportrayer_render -lportrayer_host -lportrayer_gpu -lportrayer_blob -Wl,-rpath,'$$ORIGIN'
 
 clean:
-	rm -rf build $(PKG)/lib $(ORACLE_LIB) $(HOST_TEST)
+	rm -rf build $(PKG)/lib $(ORACLE_LIB) $(HOST_TEST) $(GROUP_TEST)
 
 .PHONY: all gpu host oracle hosttest example clean

@@ -338,6 +338,17 @@ typedef void (*PtProgressFn)(void* user, uint64_t finished_pixels);
 
 /* ---- library ---- */
 int pt_init(int device);                 /* cudaSetDevice + stream; device < 0 -> current */
+/* A device GROUP inside one process: what rayon's thread pool is to the reference's one `Image::render` call
+ * (src/render.rs:127, :216-223 — the call keeps every core of the box busy), this is for the GPUs of a box.
+ * ids[0] becomes the primary device.  Afterwards pt_scene_upload also replicates the scene onto the other members
+ * (textures device to device) and pt_render fans its tiles over all members — member i renders rank r*n+i of world w*n,
+ * (r, w) the caller's own PtRenderParams.rank / world — concurrently, every member's resolve kernel storing its RGB8
+ * pixels straight into one image on the primary (peer stores over NVLink) that one D2H copy brings to the host.
+ * The picture is bit-identical to a one-device render.  pt_frame_*, pt_kd_*, pt_flatten*, pt_trace_rays run on the
+ * primary; pt_scene_set_tlas / pt_scene_set_instances refuse a replicated scene.  n = 1 is pt_init(ids[0]).
+ * Calling it (or pt_init) with another configuration shuts the library down first: handles made before are invalid. */
+int pt_init_devices(const int* ids, int n);
+int pt_device_group_size(void);          /* members of the current group (1 after pt_init; 0 before any init) */
 void pt_shutdown(void);
 const char* pt_last_error(void);
 const char* pt_error_string(int code);   /* the reference's panic text for PT_ERR_* */

@@ -8,9 +8,9 @@ Only what the hot path needs lives here:
 """
 from ._ffi import (PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS, PT_RNG_FIXED, PT_RNG_HASH, PortrayerError, PtCamera, PtRenderParams,  # noqa: F401
                    PtStats)
-from .render import DeviceScene, Frame, Image, make_params, samples_from_env  # noqa: F401
+from .render import DeviceScene, Frame, Image, init_devices, make_params, samples_from_env  # noqa: F401
 from .scene import Scene, example_names  # noqa: F401
 
-__all__ = ["Scene", "example_names", "Image", "DeviceScene", "Frame", "make_params", "samples_from_env", "PtStats",
+__all__ = ["Scene", "example_names", "Image", "DeviceScene", "Frame", "make_params", "samples_from_env", "init_devices", "PtStats",
            "PtCamera", "PtRenderParams", "PortrayerError", "PT_RNG_FIXED", "PT_RNG_HASH", "PT_RENDER_COUNTERS",
            "PT_RENDER_LINEAR_TLAS"]

@@ -147,6 +147,8 @@ TEXTURE_LOADER_FN = C.CFUNCTYPE(None, C.c_char_p)
 # every symbol include/portrayer_gpu.h declares, with its signature
 GPU_SYMBOLS = {
     "pt_init": (C.c_int, [C.c_int]),
+    "pt_init_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "pt_device_group_size": (C.c_int, []),
     "pt_shutdown": (None, []),
     "pt_last_error": (C.c_char_p, []),
     "pt_error_string": (C.c_char_p, [C.c_int]),

@@ -79,6 +79,20 @@ def _texture_loader(path_bytes: bytes) -> None:
     img = load_texture(path)
     _ffi.host.pth_register_texture(path.encode(), img.shape[1], img.shape[0], img.ctypes.data)
     _registered.add(name)
+    if os.environ.get("PORTRAYER_WRITE_DECODED"):
+        write_decoded(name, img)
+
+
+def write_decoded(name: str, img: np.ndarray) -> str:
+    """assets/_decoded/<name>.ptex ("PTEX", u32 width, u32 height, RGB8 rows): the decoded form a process WITHOUT this
+    Python layer reads (host/scene.cpp RgbImageBuffer::open) — the standalone C++ drivers under tests/cpp and host/tools."""
+    out_dir = os.path.join(ASSETS_DIR, "_decoded")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, name + ".ptex")
+    with open(out, "wb") as f:
+        f.write(b"PTEX" + np.array([img.shape[1], img.shape[0]], dtype="<u4").tobytes())
+        f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
+    return out
 
 
 def configure() -> None:

@@ -34,7 +34,6 @@ using namespace ptd;
 namespace {
 
 thread_local std::string g_error;
-cudaStream_t g_stream = nullptr;
 bool g_initialised = false;
 std::recursive_mutex g_mu;  // the ABI is blocking and serialised: one render at a time per process
 using Lock = std::lock_guard<std::recursive_mutex>;
@@ -61,6 +60,7 @@ double now_ms() {
 
 // PT_DEBUG_SYNC=1: synchronise the library stream after every upload-time stage and say which one just finished
 // (stderr) — for locating a hanging or faulting kernel on a box without a debugger
+cudaStream_t current_stream();
 void debug_sync(const char* stage) {
     static int on = -1;
     if (on < 0) {
@@ -70,7 +70,7 @@ void debug_sync(const char* stage) {
     if (!on) return;
     fprintf(stderr, "[pt] %s ...", stage);
     fflush(stderr);
-    const cudaError_t e = cudaStreamSynchronize(g_stream);
+    const cudaError_t e = cudaStreamSynchronize(current_stream());
     fprintf(stderr, " %s\n", cudaGetErrorString(e));
     fflush(stderr);
 }
@@ -142,8 +142,7 @@ private:
     size_t limit_ = size_t(24) << 30;
 };
 
-Arena<false> g_dev;
-Arena<true> g_pin;
+Arena<true> g_pin;  // pinned host memory: one arena for the process (pinned allocations are usable from every device under UVA)
 
 // ------------------------------------------------------------------ texture residency cache
 struct ResidentTexture {
@@ -153,9 +152,55 @@ struct ResidentTexture {
     uint32_t refs = 0;
     uint64_t last_use = 0;
 };
-std::unordered_map<uint64_t, ResidentTexture> g_textures;
-uint64_t g_texture_bytes = 0, g_texture_tick = 0;
-uint64_t g_texture_limit = uint64_t(32) << 30;  // of 180 GB
+
+// ------------------------------------------------------------------ per-device state
+// Everything the library keeps per GPU.  A process that never calls pt_init_devices has exactly one context (the device
+// pt_init chose); a device GROUP (pt_init_devices) has one per member, and pt_scene_upload / pt_render fan out over them.
+// The ABI is serialised by g_mu, so ONE "current context" pointer is enough: every entry point that takes a handle
+// switches to the handle's context (CtxScope) for the duration of the call, and the g_* names below — the names this
+// file used when it knew one device only — resolve through it.
+struct DeviceCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    Arena<false> dev;
+    std::unordered_map<uint64_t, ResidentTexture> textures;
+    uint64_t texture_bytes = 0, texture_tick = 0;
+    double* gamma_lut = nullptr;  // 256 doubles, filled once by the device
+    uint32_t slots_used = 0;      // bitmap of __constant__ FrameState slots in use
+    std::vector<PtFrame*> frame_cache;  // frames pt_render keeps between calls (LRU, small)
+    uint8_t* group_image = nullptr;     // primary of a group: the full RGB8 image every member's resolve kernel stores into
+    uint64_t group_image_bytes = 0;
+    bool peer_to_primary = false;       // this member's kernels can store into the primary's memory
+    bool ready = false;
+};
+constexpr int kMaxDevices = 16;
+DeviceCtx g_ctxs[kMaxDevices];
+DeviceCtx* g_cur = &g_ctxs[0];
+int g_group_size = 1;  // contexts [0, g_group_size) form the device group; [0] is the primary
+#define g_stream (g_cur->stream)
+#define g_dev (g_cur->dev)
+#define g_textures (g_cur->textures)
+#define g_texture_bytes (g_cur->texture_bytes)
+#define g_texture_tick (g_cur->texture_tick)
+#define g_gamma_lut (g_cur->gamma_lut)
+#define g_slots_used (g_cur->slots_used)
+#define g_frame_cache (g_cur->frame_cache)
+cudaStream_t current_stream() { return g_stream; }
+
+// switch the current context (and the CUDA device) for the duration of an API call
+struct CtxScope {
+    DeviceCtx* prev;
+    explicit CtxScope(DeviceCtx* ctx) : prev(g_cur) {
+        if (ctx && ctx != g_cur) { g_cur = ctx; cudaSetDevice(ctx->device); }
+    }
+    ~CtxScope() {
+        if (prev != g_cur) { g_cur = prev; if (prev->device >= 0) cudaSetDevice(prev->device); }
+    }
+    CtxScope(const CtxScope&) = delete;
+    CtxScope& operator=(const CtxScope&) = delete;
+};
+
+uint64_t g_texture_limit = uint64_t(32) << 30;  // of 180 GB, per device
 
 void evict_textures(uint64_t need) {
     while (g_texture_bytes + need > g_texture_limit) {
@@ -170,9 +215,6 @@ void evict_textures(uint64_t need) {
     }
 }
 
-double* g_gamma_lut = nullptr;  // 256 doubles, filled once by the device
-
-uint32_t g_slots_used = 0;  // bitmap of __constant__ FrameState slots in use
 int take_slot() {
     for (int i = 0; i < kStateSlots - 1; ++i)
         if (!(g_slots_used & (1u << i))) { g_slots_used |= 1u << i; return i; }
@@ -185,6 +227,9 @@ void give_slot(int slot) {
 }  // namespace
 
 struct PtScene {
+    DeviceCtx* ctx = nullptr;               // the device this copy lives on
+    std::vector<PtScene*> replicas;         // device group: the copies on the other members (owned by this handle)
+    std::vector<TextureDev> tex_table;      // host copy of d_textures (where each texture's texels lie on this device)
     unsigned char* d_records = nullptr;  // blob sections [0, off_texels) (+ inline texels when not cached)
     uint64_t bytes = 0;
     PtBlobHeader h{};
@@ -214,12 +259,15 @@ struct PtScene {
 
 struct PtKdTree {
     ptd::KdTreeDev* dev = nullptr;
+    DeviceCtx* ctx = nullptr;
 };
 struct PtFlatScene {
     ptd::FlatSceneDev* dev = nullptr;
+    DeviceCtx* ctx = nullptr;
 };
 
 struct PtFrame {
+    DeviceCtx* ctx = nullptr;
     PtScene* scene = nullptr;
     PtCamera cam{};
     PtRenderParams params{};
@@ -269,7 +317,6 @@ struct PtFrame {
 
 namespace {
 
-std::vector<PtFrame*> g_frame_cache;  // frames pt_render keeps between calls (LRU, small)
 // Ray-tree nodes the pool holds per path of a batch when a material reflects (129 B + 1 B / light each: 4.3 GB for the
 // default 4 Mi-path batch — HBM is 180 GB).  The reference's scenes average 2-5 nodes per path, but a batch that looks at
 // a dielectric needs far more, and every overflow costs that batch a second pass (pt_frame_finish).
@@ -348,6 +395,9 @@ void fill_view(PtScene* s) {
 
 void free_scene(PtScene* s) {
     if (!s) return;
+    for (PtScene* r : s->replicas) free_scene(r);
+    s->replicas.clear();
+    CtxScope scope(s->ctx);
     for (uint64_t key : s->resident_keys) {
         auto it = g_textures.find(key);
         if (it != g_textures.end() && it->second.refs > 0) --it->second.refs;
@@ -410,12 +460,14 @@ int adopt_header(PtScene* s, const void* host_blob, uint64_t bytes, bool* texels
     return PT_OK;
 }
 
-// Bind every texture of the scene to device texels: resident copy (by key), or a fresh upload from
-// `texel_src` (host or device pointer to the blob's texel section; nullptr = records-only upload).
-int bind_textures(PtScene* s, const PtTexture* tex, const unsigned char* texel_src, cudaMemcpyKind kind) {
+// Bind every texture of the scene to device texels: resident copy (by key), or a fresh copy from `texel_src` — host
+// or device pointer to the blob's texel section; nullptr = records-only upload — or, per texture, from `srcs[i]`
+// (replicating a scene from another device of the group: where the texture lies THERE; `kind` = cudaMemcpyDefault).
+int bind_textures(PtScene* s, const PtTexture* tex, const unsigned char* texel_src, cudaMemcpyKind kind, const TextureDev* srcs = nullptr) {
     const uint32_t n = s->h.n_textures;
     if (n == 0) return PT_OK;
-    std::vector<TextureDev> table(n);
+    std::vector<TextureDev>& table = s->tex_table;
+    table.assign(n, TextureDev{});
     for (uint32_t i = 0; i < n; ++i) {
         const PtTexture& t = tex[i];
         const uint64_t bytes = (uint64_t)t.width * t.height * 3;
@@ -431,15 +483,21 @@ int bind_textures(PtScene* s, const PtTexture* tex, const unsigned char* texel_s
             }
         }
         if (!d) {
-            if (!texel_src) return fail(PT_ERR_INVALID, "texture %u (key %llx) is not resident and the blob carries no texels", i,
-                                        (unsigned long long)t.key);
-            if (t.offset > s->h.n_texel_bytes || bytes > s->h.n_texel_bytes - t.offset)
-                return fail(PT_ERR_INVALID, "texture %u lies outside the texel pool", i);
+            const unsigned char* src = nullptr;
+            if (srcs) {
+                src = srcs[i].texels;
+            } else if (texel_src) {
+                if (t.offset > s->h.n_texel_bytes || bytes > s->h.n_texel_bytes - t.offset)
+                    return fail(PT_ERR_INVALID, "texture %u lies outside the texel pool", i);
+                src = texel_src + t.offset;
+            }
+            if (!src) return fail(PT_ERR_INVALID, "texture %u (key %llx) is not resident and the blob carries no texels", i,
+                                  (unsigned long long)t.key);
             if (t.key != 0) evict_textures(bytes);
             cudaError_t e;
             d = static_cast<uint8_t*>(g_dev.alloc(bytes, &e));
             if (!d) return fail(PT_ERR_CUDA, "texture allocation failed: %s", cudaGetErrorString(e));
-            e = cudaMemcpyAsync(d, texel_src + t.offset, bytes, kind, g_stream);
+            e = cudaMemcpyAsync(d, src, bytes, kind, g_stream);
             if (e != cudaSuccess) { g_dev.release(d); return fail(PT_ERR_CUDA, "texture upload failed: %s", cudaGetErrorString(e)); }
             if (kind == cudaMemcpyHostToDevice) s->h2d_bytes += bytes;
             if (t.key != 0 && g_textures.find(t.key) == g_textures.end()) {
@@ -457,7 +515,7 @@ int bind_textures(PtScene* s, const PtTexture* tex, const unsigned char* texel_s
     cudaError_t e;
     s->d_textures = static_cast<TextureDev*>(g_dev.alloc(n * sizeof(TextureDev), &e));
     if (!s->d_textures) return fail(PT_ERR_CUDA, "texture table allocation failed: %s", cudaGetErrorString(e));
-    // pageable source: the copy is staged before the call returns, so `table` may go out of scope
+    // pageable source: the copy is staged before the call returns
     CUDA_TRY(cudaMemcpyAsync(s->d_textures, table.data(), n * sizeof(TextureDev), cudaMemcpyHostToDevice, g_stream));
     s->h2d_bytes += n * sizeof(TextureDev);
     return PT_OK;
@@ -580,6 +638,7 @@ void destroy_graphs(PtFrame* f) {
 
 void free_frame(PtFrame* f) {
     if (!f) return;
+    CtxScope scope(f->ctx);
     destroy_graphs(f);
     g_dev.release(f->d_pixel_index);
     g_dev.release(f->d_background);
@@ -822,6 +881,7 @@ int create_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams* p
         return fail(PT_ERR_INVALID, "PT_RENDER_ROW_MAJOR needs world <= 1 (ranks own interleaved tiles)");
 
     PtFrame* f = new PtFrame();
+    f->ctx = scene->ctx;
     f->scene = scene;
     f->cam = *camera;
     f->params = p;
@@ -1033,39 +1093,155 @@ void collect_graph_path(PtFrame* f, PtProgressFn progress, void* user, PtStats* 
 // =================================================================== library
 extern "C" {
 
+// bring one context up on `device` (no-op when it already is)
+static int init_context(DeviceCtx* c, int device) {
+    if (c->ready && c->device == device) return PT_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    c->device = device;
+    CtxScope scope(c);
+    if (!c->stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (!c->gamma_lut) {
+        CUDA_TRY(cudaMalloc(&c->gamma_lut, 256 * sizeof(double)));
+        launch_gamma_lut(c->gamma_lut, c->stream);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->ready = true;
+    return PT_OK;
+}
+
+static void shutdown_context(DeviceCtx* c) {
+    if (c->device < 0) return;
+    CtxScope scope(c);
+    cudaSetDevice(c->device);
+    for (PtFrame* f : c->frame_cache) free_frame(f);
+    c->frame_cache.clear();
+    for (auto& kv : c->textures) c->dev.release(kv.second.d_texels);  // (scenes still alive keep dangling texel pointers: shutdown is final)
+    c->textures.clear();
+    c->texture_bytes = 0;
+    c->dev.release(c->group_image);
+    c->group_image = nullptr;
+    c->group_image_bytes = 0;
+    c->dev.trim();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    c->stream = nullptr;
+    cudaFree(c->gamma_lut);
+    c->gamma_lut = nullptr;
+    c->slots_used = 0;
+    c->ready = false;
+    c->device = -1;
+}
+
+static void shutdown_all() {
+    for (int i = 0; i < kMaxDevices; ++i) shutdown_context(&g_ctxs[i]);
+    g_pin.trim();
+    g_cur = &g_ctxs[0];
+    g_group_size = 1;
+    g_initialised = false;
+}
+
 int pt_init(int device) {
     Lock lock(g_mu);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(PT_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
-    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
-    if (!g_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= count) return fail(PT_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+    if (g_initialised && (g_group_size != 1 || g_ctxs[0].device != device)) shutdown_all();  // another configuration: start over
+    g_cur = &g_ctxs[0];
+    int rc = init_context(&g_ctxs[0], device);
+    if (rc != PT_OK) return rc;
+    CUDA_TRY(cudaSetDevice(device));
     kernels_init();
-    if (!g_gamma_lut) {
-        CUDA_TRY(cudaMalloc(&g_gamma_lut, 256 * sizeof(double)));
-        launch_gamma_lut(g_gamma_lut, g_stream);
-        CUDA_TRY(cudaStreamSynchronize(g_stream));
-    }
-    CUDA_TRY(cudaGetLastError());
+    g_group_size = 1;
     g_initialised = true;
     return PT_OK;
 }
 
+// A device GROUP in one process (the reference's one `Image::render` call keeps every core of the box busy through
+// rayon, render.rs:127,216-223; this is that for the GPUs of a box): ids[0] becomes the primary — the device every
+// handle-less call and every pt_frame_* / pt_kd_* / pt_flatten call runs on — and from then on
+//   * pt_scene_upload puts the scene on the primary from the host blob and REPLICATES records, textures and the
+//     upload-time acceleration data to the other members device-to-device (NVLink / NVSwitch when peer access exists);
+//   * pt_render splits its tiles over the members (tile k -> member k mod n, the ownership rule of PtRenderParams.rank /
+//     world, nested inside the caller's own rank / world), runs all members concurrently, and every member's resolve
+//     kernel stores its RGB8 pixels straight into ONE image on the primary (peer stores) that is then copied to the host.
+// Results are bit-identical to a one-device render (RNG draws are keyed by the global pixel index).
+int pt_init_devices(const int* ids, int n) {
+    if (!ids || n < 1 || n > kMaxDevices) return fail(PT_ERR_INVALID, "pt_init_devices: need 1..%d device ids", kMaxDevices);
+    Lock lock(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PT_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || ids[i] >= count) return fail(PT_ERR_INVALID, "device %d out of range (%d devices)", ids[i], count);
+        for (int j = 0; j < i; ++j)
+            if (ids[j] == ids[i]) return fail(PT_ERR_INVALID, "device %d listed twice", ids[i]);
+    }
+    bool same = g_initialised && g_group_size == n;
+    for (int i = 0; same && i < n; ++i) same = g_ctxs[i].ready && g_ctxs[i].device == ids[i];
+    if (same) return PT_OK;
+    if (g_initialised) shutdown_all();
+    g_cur = &g_ctxs[0];
+    for (int i = 0; i < n; ++i) {
+        int rc = init_context(&g_ctxs[i], ids[i]);
+        if (rc != PT_OK) { shutdown_all(); return rc; }
+    }
+    // peer access both ways between the primary and every other member (scene replication reads the primary's memory,
+    // resolve kernels store into it); without it copies are staged by the driver and the image is gathered on the host
+    for (int i = 1; i < n; ++i) {
+        int can_a = 0, can_b = 0;
+        cudaDeviceCanAccessPeer(&can_a, ids[i], ids[0]);
+        cudaDeviceCanAccessPeer(&can_b, ids[0], ids[i]);
+        g_ctxs[i].peer_to_primary = false;
+        if (can_a) {
+            cudaSetDevice(ids[i]);
+            e = cudaDeviceEnablePeerAccess(ids[0], 0);
+            g_ctxs[i].peer_to_primary = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
+        }
+        if (can_b) {
+            cudaSetDevice(ids[0]);
+            cudaDeviceEnablePeerAccess(ids[i], 0);
+        }
+        cudaGetLastError();
+    }
+    g_ctxs[0].peer_to_primary = true;
+    CUDA_TRY(cudaSetDevice(ids[0]));
+    kernels_init();
+    g_group_size = n;
+    g_initialised = true;
+    return PT_OK;
+}
+
+int pt_device_group_size(void) {
+    Lock lock(g_mu);
+    return g_initialised ? g_group_size : 0;
+}
+
 void pt_release_cached_memory(void) {
     Lock lock(g_mu);
-    for (PtFrame* f : g_frame_cache) free_frame(f);
-    g_frame_cache.clear();
-    for (auto it = g_textures.begin(); it != g_textures.end();) {
-        if (it->second.refs == 0) {
-            g_dev.release(it->second.d_texels);
-            g_texture_bytes -= it->second.bytes;
-            it = g_textures.erase(it);
-        } else {
-            ++it;
+    for (int i = 0; i < kMaxDevices; ++i) {
+        DeviceCtx* c = &g_ctxs[i];
+        if (!c->ready) continue;
+        CtxScope scope(c);
+        for (PtFrame* f : g_frame_cache) free_frame(f);
+        g_frame_cache.clear();
+        for (auto it = g_textures.begin(); it != g_textures.end();) {
+            if (it->second.refs == 0) {
+                g_dev.release(it->second.d_texels);
+                g_texture_bytes -= it->second.bytes;
+                it = g_textures.erase(it);
+            } else {
+                ++it;
+            }
         }
+        g_dev.release(c->group_image);
+        c->group_image = nullptr;
+        c->group_image_bytes = 0;
+        g_dev.trim();
     }
-    g_dev.trim();
     g_pin.trim();
 }
 
@@ -1119,12 +1295,7 @@ uint64_t pt_resident_texture_bytes(void) {
 
 void pt_shutdown(void) {
     Lock lock(g_mu);
-    pt_release_cached_memory();
-    if (g_stream) cudaStreamDestroy(g_stream);
-    g_stream = nullptr;
-    cudaFree(g_gamma_lut);
-    g_gamma_lut = nullptr;
-    g_initialised = false;
+    shutdown_all();
 }
 
 const char* pt_last_error(void) { return g_error.c_str(); }
@@ -1137,15 +1308,23 @@ int pt_device_count(void) {
 }
 
 // =================================================================== scene
-int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out) {
-    if (!blob || !out) return fail(PT_ERR_INVALID, "null argument");
-    Lock lock(g_mu);
-    int rc = ensure_init();
-    if (rc != PT_OK) return rc;
+// the scene on the CURRENT context from a host blob.  `texel_from` (replication inside a device group): the copy of the
+// same scene on the primary — its textures are copied device to device instead of crossing PCIe once per member.
+// `sync`: wait for the upload before returning (the caller may then free / reuse `blob`).
+static int upload_scene_host(const void* blob, uint64_t bytes, const PtScene* texel_from, bool sync, PtScene** out) {
     PtScene* s = new PtScene();
+    s->ctx = g_cur;
     bool texels_present = false;
-    rc = adopt_header(s, blob, bytes, &texels_present);
-    if (rc != PT_OK) { delete s; return rc; }
+    int rc = PT_OK;
+    if (texel_from) {  // validated once, on the primary
+        s->h = texel_from->h;
+        s->has_reflective = texel_from->has_reflective;
+        s->fold_sort = texel_from->fold_sort;
+        s->blas_trees = texel_from->blas_trees;
+    } else {
+        rc = adopt_header(s, blob, bytes, &texels_present);
+        if (rc != PT_OK) { delete s; return rc; }
+    }
     // records: everything before the texel section, verbatim
     s->bytes = std::min<uint64_t>(s->h.off_texels, s->h.total_bytes);
     cudaError_t e;
@@ -1158,15 +1337,43 @@ int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out) {
     }
     s->h2d_bytes = s->bytes;
     const unsigned char* base = static_cast<const unsigned char*>(blob);
-    rc = bind_textures(s, reinterpret_cast<const PtTexture*>(base + s->h.off_textures),
-                       texels_present ? base + s->h.off_texels : nullptr, cudaMemcpyHostToDevice);
+    const PtTexture* tex = reinterpret_cast<const PtTexture*>(base + s->h.off_textures);
+    if (texel_from) rc = bind_textures(s, tex, nullptr, cudaMemcpyDefault, texel_from->tex_table.data());
+    else rc = bind_textures(s, tex, texels_present ? base + s->h.off_texels : nullptr, cudaMemcpyHostToDevice);
     if (rc == PT_OK) rc = build_instance_bounds(s);
-    if (rc == PT_OK) {
-        e = cudaStreamSynchronize(g_stream);  // the caller may free / reuse `blob` when this returns
+    if (rc == PT_OK && sync) {
+        e = cudaStreamSynchronize(g_stream);
         if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
     }
     if (rc != PT_OK) { free_scene(s); return rc; }
     fill_view(s);
+    *out = s;
+    return PT_OK;
+}
+
+int pt_scene_upload(const void* blob, uint64_t bytes, PtScene** out) {
+    if (!blob || !out) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
+    int rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    CtxScope scope(&g_ctxs[0]);
+    PtScene* s = nullptr;
+    rc = upload_scene_host(blob, bytes, nullptr, true, &s);
+    if (rc != PT_OK) return rc;
+    // device group: the other members' copies; every member builds its acceleration data on its own stream, at once
+    for (int i = 1; i < g_group_size && rc == PT_OK; ++i) {
+        CtxScope member(&g_ctxs[i]);
+        PtScene* r = nullptr;
+        rc = upload_scene_host(blob, bytes, s, false, &r);
+        if (rc == PT_OK) s->replicas.push_back(r);
+    }
+    for (PtScene* r : s->replicas) {
+        CtxScope member(r->ctx);
+        const cudaError_t e = cudaStreamSynchronize(g_stream);
+        if (e != cudaSuccess && rc == PT_OK) rc = fail(PT_ERR_CUDA, "scene replication failed: %s", cudaGetErrorString(e));
+        s->h2d_bytes += r->h2d_bytes;
+    }
+    if (rc != PT_OK) { free_scene(s); return rc; }
     *out = s;
     return PT_OK;
 }
@@ -1185,6 +1392,7 @@ int pt_scene_upload_device(const void* d_blob, uint64_t bytes, PtScene** out) {
     std::vector<unsigned char> host(texels_present ? h.total_bytes : h.off_texels);
     CUDA_TRY(cudaMemcpy(host.data(), d_blob, h.off_texels, cudaMemcpyDeviceToHost));
     PtScene* s = new PtScene();
+    s->ctx = g_cur;
     bool present2 = false;
     rc = adopt_header(s, host.data(), host.size(), &present2);
     if (rc != PT_OK) { delete s; return rc; }
@@ -1216,8 +1424,12 @@ uint64_t pt_scene_uploaded_bytes(const PtScene* scene) { return scene ? scene->h
 void pt_scene_free(PtScene* scene) {
     if (!scene) return;
     Lock lock(g_mu);
-    for (PtFrame* f : g_frame_cache)
-        if (f->scene == scene) f->scene = nullptr;
+    auto forget = [](PtScene* sc) {
+        for (PtFrame* f : sc->ctx->frame_cache)
+            if (f->scene == sc) f->scene = nullptr;
+    };
+    forget(scene);
+    for (PtScene* r : scene->replicas) forget(r);
     free_scene(scene);
 }
 
@@ -1225,6 +1437,7 @@ void pt_scene_free(PtScene* scene) {
 int pt_frame_create(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, PtFrame** out) {
     if (!scene || !camera || !params || !out) return fail(PT_ERR_INVALID, "null argument");
     Lock lock(g_mu);
+    CtxScope scope(scene->ctx);
     PtFrame* f = nullptr;
     int rc = create_frame(scene, camera, params, &f);
     if (rc != PT_OK) return rc;
@@ -1238,8 +1451,10 @@ int pt_frame_create(PtScene* scene, const PtCamera* camera, const PtRenderParams
 int pt_frame_rebind(PtFrame* frame, PtScene* scene, const PtCamera* camera, const uint64_t* seed, const uint32_t* rng_mode) {
     if (!frame) return fail(PT_ERR_INVALID, "null frame");
     Lock lock(g_mu);
+    CtxScope scope(frame->ctx);
     if (frame->pending == PtFrame::IN_FLIGHT) return fail(PT_ERR_INVALID, "the frame has a render in flight");
     if (scene) {
+        if (scene->ctx != frame->ctx) return fail(PT_ERR_INVALID, "the scene lives on another device than the frame");
         if (scene->h.n_lights != frame->n_lights_cap || scene->has_reflective != frame->reflective_cap)
             return fail(PT_ERR_INVALID, "scene has %u lights / reflective=%d, the frame was sized for %u / %d", scene->h.n_lights,
                         (int)scene->has_reflective, frame->n_lights_cap, (int)frame->reflective_cap);
@@ -1256,7 +1471,7 @@ int pt_frame_rebind(PtFrame* frame, PtScene* scene, const PtCamera* camera, cons
 
 void pt_frame_free(PtFrame* frame) {
     Lock lock(g_mu);
-    free_frame(frame);
+    free_frame(frame);  // switches to the frame's device itself
 }
 uint64_t pt_frame_owned_pixels(const PtFrame* frame) { return frame ? frame->pixel_index.size() : 0; }
 uint64_t pt_frame_background_doubles(const PtFrame* frame) { return frame ? frame->bg_doubles : 0; }
@@ -1264,6 +1479,7 @@ uint64_t pt_frame_background_doubles(const PtFrame* frame) { return frame ? fram
 int pt_frame_set_background(PtFrame* frame, const double* background) {
     if (!frame || !background) return fail(PT_ERR_INVALID, "null argument");
     Lock lock(g_mu);
+    CtxScope scope(frame->ctx);
     CUDA_TRY(cudaMemcpyAsync(frame->d_background, background, frame->bg_doubles * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     return PT_OK;
@@ -1271,6 +1487,7 @@ int pt_frame_set_background(PtFrame* frame, const double* background) {
 int pt_frame_set_background_device(PtFrame* frame, const double* d_background) {
     if (!frame || !d_background) return fail(PT_ERR_INVALID, "null argument");
     Lock lock(g_mu);
+    CtxScope scope(frame->ctx);
     CUDA_TRY(cudaMemcpyAsync(frame->d_background, d_background, frame->bg_doubles * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     return PT_OK;
@@ -1301,6 +1518,7 @@ static int render_blocking_stream(PtFrame* f, cudaStream_t st, PtProgressFn prog
 int pt_frame_enqueue(PtFrame* frame, void* stream) {
     if (!frame) return fail(PT_ERR_INVALID, "null frame");
     Lock lock(g_mu);
+    CtxScope scope(frame->ctx);
     PtFrame* f = frame;
     if (!f->scene) return fail(PT_ERR_INVALID, "the frame's scene has been freed");
     if (f->pending == PtFrame::IN_FLIGHT) return fail(PT_ERR_INVALID, "the frame already has a render in flight: call pt_frame_finish first");
@@ -1338,6 +1556,7 @@ int pt_frame_enqueue(PtFrame* frame, void* stream) {
 int pt_frame_finish(PtFrame* frame, PtStats* stats) {
     if (!frame) return fail(PT_ERR_INVALID, "null frame");
     Lock lock(g_mu);
+    CtxScope scope(frame->ctx);
     PtFrame* f = frame;
     if (f->pending == PtFrame::IDLE) return fail(PT_ERR_INVALID, "no render was enqueued on this frame");
     const double h2d_ms = stats ? stats->h2d_ms : 0.0, d2h_ms = stats ? stats->d2h_ms : 0.0;
@@ -1404,6 +1623,7 @@ int pt_frame_finish(PtFrame* frame, PtStats* stats) {
 int pt_frame_render(PtFrame* frame, void* stream, PtProgressFn progress, void* user, PtStats* stats) {
     if (!frame) return fail(PT_ERR_INVALID, "null frame");
     Lock lock(g_mu);
+    CtxScope scope(frame->ctx);
     frame->progress = progress;
     frame->progress_user = user;
     int rc = pt_frame_enqueue(frame, stream);
@@ -1479,6 +1699,7 @@ int pt_frame_pixel_index(const PtFrame* frame, uint32_t* index_out) {
 int pt_frame_read(PtFrame* frame, uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtStats* stats) {
     if (!frame) return fail(PT_ERR_INVALID, "null frame");
     Lock lock(g_mu);
+    CtxScope scope(frame->ctx);
     const size_t owned = frame->pixel_index.size();
     const double t0 = now_ms();
     uint64_t bytes = 0;
@@ -1531,16 +1752,10 @@ static bool same_geometry(const PtRenderParams& a, const PtRenderParams& b) {
            a.node_pool_capacity == b.node_pool_capacity && ((a.flags ^ b.flags) & PT_RENDER_ROW_MAJOR) == 0;
 }
 
-int pt_render(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, const double* background,
-              uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtProgressFn progress, void* user,
-              PtStats* stats) {
-    if (!scene || !camera || !params || !background || !rgb_inout) return fail(PT_ERR_INVALID, "null argument");
-    Lock lock(g_mu);
-    PtRenderParams p = *params;
-    if (p.world <= 1) p.flags |= PT_RENDER_ROW_MAJOR;  // single rank: resolve writes the image in place, D2H is one 2-D copy
-    else p.flags &= ~PT_RENDER_ROW_MAJOR;
-    // Frames (device buffers + CUDA graph) are kept between calls and re-bound to whatever scene comes next: a
-    // program that renders many scenes at one resolution (examples/normal-mapping.rs) allocates once.
+// The frame pt_render uses for (scene, params) on the CURRENT context.  Frames (device buffers + CUDA graph) are kept
+// between calls and re-bound to whatever scene comes next: a program that renders many scenes at one resolution
+// (examples/normal-mapping.rs) allocates once.
+static int cached_frame(PtScene* scene, const PtCamera* camera, const PtRenderParams& p, PtFrame** out) {
     PtFrame* f = nullptr;
     for (PtFrame* c : g_frame_cache)
         if (same_geometry(c->params, p) && c->n_lights_cap == scene->h.n_lights && c->reflective_cap == scene->has_reflective) { f = c; break; }
@@ -1575,8 +1790,152 @@ int pt_render(PtScene* scene, const PtCamera* camera, const PtRenderParams* para
         }
     }
     f->last_use = ++g_frame_tick;
+    f->image_target = nullptr;
+    *out = f;
+    return PT_OK;
+}
+
+// sums / maxima of the members' statistics of one group render
+static void merge_stats(PtStats* into, const PtStats& s) {
+    into->rays_primary += s.rays_primary; into->rays_shadow += s.rays_shadow; into->rays_reflect += s.rays_reflect;
+    into->rays_refract += s.rays_refract; into->rays_depth_cut += s.rays_depth_cut;
+    into->kd_splits += s.kd_splits; into->instance_tests += s.instance_tests; into->triangle_tests += s.triangle_tests;
+    into->bbox_gates += s.bbox_gates; into->shaded_hits += s.shaded_hits; into->texel_lookups += s.texel_lookups;
+    into->nodes_total += s.nodes_total; into->batches += s.batches; into->retries += s.retries;
+    into->max_level = std::max(into->max_level, s.max_level);
+    into->device_error_bits |= s.device_error_bits;
+    into->kernel_launches += s.kernel_launches;
+    into->device_ms = std::max(into->device_ms, s.device_ms);  // the members run concurrently
+    into->h2d_ms += s.h2d_ms; into->d2h_ms += s.d2h_ms; into->h2d_bytes += s.h2d_bytes; into->d2h_bytes += s.d2h_bytes;
+    for (int k = 0; k < 2; ++k) {
+        into->k_kd_splits[k] += s.k_kd_splits[k]; into->k_instance_tests[k] += s.k_instance_tests[k];
+        into->k_triangle_tests[k] += s.k_triangle_tests[k]; into->k_bbox_gates[k] += s.k_bbox_gates[k];
+        into->k_prim_flops[k] += s.k_prim_flops[k];
+        into->x_box_tests[k] += s.x_box_tests[k]; into->x_instance_tests[k] += s.x_instance_tests[k];
+        into->x_triangle_tests[k] += s.x_triangle_tests[k]; into->x_bbox_gates[k] += s.x_bbox_gates[k];
+        into->x_prim_flops[k] += s.x_prim_flops[k];
+    }
+    into->ms_extend = std::max(into->ms_extend, s.ms_extend); into->ms_shadow = std::max(into->ms_shadow, s.ms_shadow);
+    into->ms_shade = std::max(into->ms_shade, s.ms_shade);
+    into->n_extend += s.n_extend; into->n_shadow += s.n_shadow; into->n_shade += s.n_shade;
+    for (int l = 0; l < 16; ++l) {
+        into->ms_extend_level[l] = std::max(into->ms_extend_level[l], s.ms_extend_level[l]);
+        into->ms_shadow_level[l] = std::max(into->ms_shadow_level[l], s.ms_shadow_level[l]);
+    }
+    if (s.err_bit && !into->err_bit) {
+        into->err_bit = s.err_bit; into->err_pixel = s.err_pixel; into->err_sample = s.err_sample;
+        into->err_pathid = s.err_pathid; into->err_where = s.err_where;
+    }
+}
+
+// pt_render over a device group: the scene's copies render interleaved tiles concurrently (member i = rank r0 * n + i
+// of world w0 * n, r0 / w0 the caller's own rank / world), every resolve kernel stores its pixels into one image on the
+// primary, one D2H brings the slice rectangle to the host.
+static int render_group(PtScene* scene, const PtCamera* camera, const PtRenderParams& p0, const double* background,
+                        uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtProgressFn progress, void* user,
+                        PtStats* stats) {
+    const int n = 1 + (int)scene->replicas.size();
+    const uint32_t w0 = std::max<uint32_t>(p0.world, 1), r0 = p0.world > 1 ? p0.rank : 0;
+    std::vector<PtScene*> members(n);
+    std::vector<PtFrame*> frames(n, nullptr);
+    members[0] = scene;
+    for (int i = 1; i < n; ++i) members[i] = scene->replicas[i - 1];
+    // one image on the primary needs every member to reach it, and every slice pixel to be rendered by this call
+    bool image_path = p0.world <= 1;
+    for (int i = 0; i < n; ++i) image_path = image_path && members[i]->ctx->peer_to_primary;
+    PtStats total{};
+    for (int i = 0; i < n; ++i) {
+        CtxScope member(members[i]->ctx);
+        PtRenderParams pi = p0;
+        pi.world = w0 * (uint32_t)n;
+        pi.rank = r0 * (uint32_t)n + (uint32_t)i;
+        pi.flags &= ~PT_RENDER_ROW_MAJOR;
+        int rc = cached_frame(members[i], camera, pi, &frames[i]);
+        if (rc == PT_OK && (hit_id_out || hit_t_out)) rc = ensure_id_buffers(frames[i]);
+        if (rc != PT_OK) return rc;
+    }
+    DeviceCtx* primary = scene->ctx;
+    const uint64_t image_bytes = (uint64_t)p0.width * p0.height * 3;
+    if (image_path) {
+        CtxScope scope(primary);
+        if (primary->group_image_bytes < image_bytes) {
+            g_dev.release(primary->group_image);
+            cudaError_t e;
+            primary->group_image = static_cast<uint8_t*>(g_dev.alloc(image_bytes, &e));
+            primary->group_image_bytes = primary->group_image ? image_bytes : 0;
+            if (!primary->group_image) return fail(PT_ERR_CUDA, "group image allocation failed: %s", cudaGetErrorString(e));
+        }
+        for (PtFrame* f : frames) f->image_target = primary->group_image;
+    }
+    // background: host -> primary, primary -> the other members device to device (a per-pixel 4K background is 199 MB)
+    const double t0 = now_ms();
+    const uint64_t bg_bytes = frames[0]->bg_doubles * sizeof(double);
+    cudaEvent_t bg_ready = nullptr;
+    {
+        CtxScope scope(primary);
+        CUDA_TRY(cudaMemcpyAsync(frames[0]->d_background, background, bg_bytes, cudaMemcpyHostToDevice, g_stream));
+        CUDA_TRY(cudaEventCreateWithFlags(&bg_ready, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(bg_ready, g_stream));
+    }
+    for (int i = 1; i < n; ++i) {
+        CtxScope member(members[i]->ctx);
+        cudaError_t e = cudaStreamWaitEvent(g_stream, bg_ready, 0);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(frames[i]->d_background, g_cur->device, frames[0]->d_background, primary->device, bg_bytes, g_stream);
+        if (e != cudaSuccess) { cudaEventDestroy(bg_ready); return fail(PT_ERR_CUDA, "background replication failed: %s", cudaGetErrorString(e)); }
+    }
+    total.h2d_ms = now_ms() - t0;
+    total.h2d_bytes = bg_bytes;
+    // all members enqueue before anyone waits
+    int rc = PT_OK;
+    int enqueued = 0;
+    for (int i = 0; i < n && rc == PT_OK; ++i) {
+        frames[i]->progress = progress;
+        frames[i]->progress_user = user;
+        rc = pt_frame_enqueue(frames[i], nullptr);
+        if (rc == PT_OK) ++enqueued;
+    }
+    for (int i = 0; i < enqueued; ++i) {
+        PtStats st{};
+        const int rc_i = pt_frame_finish(frames[i], &st);
+        if (rc_i != PT_OK && rc == PT_OK) rc = rc_i;
+        merge_stats(&total, st);
+    }
+    for (PtFrame* f : frames) { f->progress = nullptr; f->progress_user = nullptr; }
+    cudaEventDestroy(bg_ready);
+    int rc2 = PT_OK;
+    if (image_path) {
+        CtxScope scope(primary);
+        const double t1 = now_ms();
+        const size_t W = p0.width, w = p0.x2 - p0.x1 + 1, hgt = p0.y2 - p0.y1 + 1;
+        const size_t first = (size_t)p0.y1 * W + p0.x1;
+        cudaError_t e = cudaMemcpy2DAsync(rgb_inout + first * 3, W * 3, primary->group_image + first * 3, W * 3, w * 3, hgt, cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+        if (e != cudaSuccess) rc2 = fail(PT_ERR_CUDA, "group image read failed: %s", cudaGetErrorString(e));
+        total.d2h_ms += now_ms() - t1;
+        total.d2h_bytes += w * hgt * 3;
+    }
+    for (int i = 0; i < n && rc2 == PT_OK; ++i)
+        if (!image_path || hit_id_out || hit_t_out) rc2 = pt_frame_read(frames[i], image_path ? nullptr : rgb_inout, hit_id_out, hit_t_out, &total);
+    if (stats) *stats = total;
+    return rc != PT_OK ? rc : rc2;
+}
+
+int pt_render(PtScene* scene, const PtCamera* camera, const PtRenderParams* params, const double* background,
+              uint8_t* rgb_inout, uint32_t* hit_id_out, double* hit_t_out, PtProgressFn progress, void* user,
+              PtStats* stats) {
+    if (!scene || !camera || !params || !background || !rgb_inout) return fail(PT_ERR_INVALID, "null argument");
+    Lock lock(g_mu);
+    if (!scene->replicas.empty())
+        return render_group(scene, camera, *params, background, rgb_inout, hit_id_out, hit_t_out, progress, user, stats);
+    CtxScope scope(scene->ctx);
+    PtRenderParams p = *params;
+    if (p.world <= 1) p.flags |= PT_RENDER_ROW_MAJOR;  // single rank: resolve writes the image in place, D2H is one 2-D copy
+    else p.flags &= ~PT_RENDER_ROW_MAJOR;
+    PtFrame* f = nullptr;
+    int rc = cached_frame(scene, camera, p, &f);
+    if (rc != PT_OK) return rc;
     if (hit_id_out || hit_t_out) {
-        int rc = ensure_id_buffers(f);
+        rc = ensure_id_buffers(f);
         if (rc != PT_OK) return rc;
     }
     PtStats local{};
@@ -1584,7 +1943,7 @@ int pt_render(PtScene* scene, const PtCamera* camera, const PtRenderParams* para
     CUDA_TRY(cudaMemcpyAsync(f->d_background, background, f->bg_doubles * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     local.h2d_ms = now_ms() - t0;
     local.h2d_bytes = f->bg_doubles * sizeof(double);
-    int rc = pt_frame_render(f, nullptr, progress, user, &local);
+    rc = pt_frame_render(f, nullptr, progress, user, &local);
     int rc2 = pt_frame_read(f, rgb_inout, hit_id_out, hit_t_out, &local);
     if (stats) *stats = local;
     return rc != PT_OK ? rc : rc2;
@@ -1599,6 +1958,7 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
     if (n == 0) return PT_OK;
     if (n > 0x7FFFFFFFull) return fail(PT_ERR_INVALID, "too many rays");
     Lock lock(g_mu);
+    CtxScope scope(scene->ctx);
     const uint32_t depth = max_depth ? max_depth : PT_MAX_RECURSION_DEPTH;
     if (depth > PT_MAX_DEPTH_SUPPORTED) return fail(PT_ERR_INVALID, "max_depth > %u is not supported", PT_MAX_DEPTH_SUPPORTED);
     const int n_levels = scene->has_reflective ? (int)depth + 1 : 1;
@@ -1706,7 +2066,7 @@ int pt_kd_build_device(const double* d_bounds, uint32_t n, const PtKdBuildConfig
     const cudaError_t e = ptd::kd_build_device(d_bounds, n, *config, al, stream ? (cudaStream_t)stream : g_stream, &dev);
     if (e == cudaErrorInvalidValue) return fail(PT_ERR_INVALID, "k-d tree does not fit 30-bit node / item indices");
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "k-d tree build failed: %s", cudaGetErrorString(e));
-    *out = new PtKdTree{dev};
+    *out = new PtKdTree{dev, g_cur};
     return PT_OK;
 }
 
@@ -1772,6 +2132,8 @@ int pt_kd_tree_build_stats(const PtKdTree* tree, double* device_ms_out, uint32_t
 int pt_scene_set_tlas(PtScene* scene, const PtKdTree* tree) {
     if (!scene || !tree) return fail(PT_ERR_INVALID, "null argument");
     Lock lock(g_mu);
+    if (!scene->replicas.empty()) return fail(PT_ERR_INVALID, "not supported for a scene replicated over a device group (pt_init_devices): upload it on one device");
+    CtxScope scope(scene->ctx);
     const uint32_t nn = ptd::kd_tree_node_count(tree->dev), ni = ptd::kd_tree_item_count(tree->dev);
     if (ptd::kd_tree_depth(tree->dev) > PT_MAX_KD_STACK) return fail(PT_ERR_KD_TOO_DEEP, "%s", panic_text(PT_ERR_KD_TOO_DEEP));
     cudaError_t e = cudaSuccess;
@@ -1835,7 +2197,7 @@ int pt_flatten(const PtHierNode* nodes, uint32_t n_nodes, const uint32_t* childr
     cleanup();
     if (e == cudaErrorInvalidValue) return fail(PT_ERR_INVALID, "the hierarchy has a cycle or expands to more than 2^31 instances");
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "flatten failed: %s", cudaGetErrorString(e));
-    *out = new PtFlatScene{dev};
+    *out = new PtFlatScene{dev, g_cur};
     return PT_OK;
 }
 
@@ -1869,6 +2231,8 @@ int pt_flat_build_stats(const PtFlatScene* flat, double* device_ms_out, uint32_t
 int pt_scene_set_instances(PtScene* scene, const PtFlatScene* flat, const PtKdTree* tree) {
     if (!scene || !flat || !tree) return fail(PT_ERR_INVALID, "null argument");
     Lock lock(g_mu);
+    if (!scene->replicas.empty()) return fail(PT_ERR_INVALID, "not supported for a scene replicated over a device group (pt_init_devices): upload it on one device");
+    CtxScope scope(scene->ctx);
     const uint32_t n = ptd::flat_instance_count(flat->dev);
     cudaError_t e = cudaSuccess;
     PtInstance* d_inst = static_cast<PtInstance*>(g_dev.alloc(std::max<size_t>(n, 1) * sizeof(PtInstance), &e));

@@ -259,8 +259,14 @@ struct KdStack {
 // lanes of the warp run their leaves together.  With one loop whose body is "a split step OR a whole leaf", a lane that
 // is still descending advances ONE split per leaf any other lane of its warp processes — and a leaf can hold a whole
 // KDMesh walk.
+// `od`: the ray as an ARRAY (origin x, y, z, direction x, y, z) that the split step indexes by the node's axis: one
+// local-memory load per operand (an L1 hit) where selecting among three register pairs costs a branch and six moves
+// per operand, and the ray does not occupy twelve registers for the length of the walk.
+#ifndef PT_KD_RAY_ARRAY
+#define PT_KD_RAY_ARRAY 1
+#endif
 template <class LeafFn>
-PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d, double s, const double e0, KdStack& stack,
+PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, const double (&od)[6], double s, const double e0, KdStack& stack,
                   LeafFn& leaf, uint32_t& err, uint32_t& n_splits) {
     int sp = 0;
     double e = e0;
@@ -279,8 +285,12 @@ PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, V3 o, V3 d,
             double t_max = s + extent;
             if (!in_range(s, e, t_max)) t_max = e - kEps;
             const double t_min = s + kEps;
-            const double oa = axis == 0 ? o.x : (axis == 1 ? o.y : o.z);
-            const double da = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
+#if PT_KD_RAY_ARRAY
+            const double oa = od[axis], da = od[3 + axis];
+#else
+            const double oa = axis == 0 ? od[0] : (axis == 1 ? od[1] : od[2]);
+            const double da = axis == 0 ? od[3] : (axis == 1 ? od[4] : od[5]);
+#endif
             const double p0 = oa + da * t_min;
             const double p1 = oa + da * t_max;
             const bool f0 = (p0 - split) >= 0.0;  // which_side, infinite_plane.rs:27-35
@@ -568,7 +578,8 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     // clipped triangle boxes hold only if the ray has left the mesh by then
     const uint32_t set = world_exit < (float)((s + extent) * 0.999) ? 0u : sc.bl_cull.set_stride;
     BlasLeaf<ANY> leaf{sc.bl_cull, set, sc.blas_items + item_first, sc.tri_pos + tri_first, o, d, make_rayf(o, d), 0.0, 0, 0, 0, 0, 0};
-    const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), extent, o, d, s, e, blas_stack, leaf, err, wc.kd_splits);
+    const double od[6] = {o.x, o.y, o.z, d.x, d.y, d.z};
+    const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), extent, od, s, e, blas_stack, leaf, err, wc.kd_splits);
     wc.triangle_tests += leaf.n_tests;
     wc.x_box += leaf.x_box;
     wc.x_tri += leaf.x_tri;
@@ -646,7 +657,8 @@ PT_D bool scene_cast(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& tlas_stack
     const RayF rf = make_rayf(o, d);
     const uint32_t set = probe_covers(sc.tl_root, rf, kEps, sc.tlas_extent) ? 0u : sc.tl_cull.set_stride;
     TlasLeaf<ANY, COUNT> leaf{sc, set, o, d, rf, blas_stack, hit, err, wc, 0};
-    return kd_walk(sc.tlas_nodes, sc.tlas_extent, o, d, kEps, (double)INFINITY, tlas_stack, leaf, err, wc.kd_splits);
+    const double od[6] = {o.x, o.y, o.z, d.x, d.y, d.z};
+    return kd_walk(sc.tlas_nodes, sc.tlas_extent, od, kEps, (double)INFINITY, tlas_stack, leaf, err, wc.kd_splits);
 }
 
 // PT_RENDER_LINEAR_TLAS: the scene WITHOUT its k-d tree — FlatScene as the root, i.e. `[FlatSceneNode]::ray_cast`

@@ -50,6 +50,15 @@ def _background_arg(scene: Scene, width: int, height: int) -> tuple[np.ndarray, 
     return np.ascontiguousarray(scene.background(width, height)), PT_BG_PER_PIXEL
 
 
+def init_devices(ids) -> int:
+    """pt_init_devices: make ``ids`` one device group in this process (ids[0] = primary); from then on ``Image.render`` /
+    ``DeviceScene.render`` fan their tiles over all members.  Handles created before the call are invalid."""
+    ids = [int(i) for i in ids]
+    arr = (C.c_int * len(ids))(*ids)
+    check(gpu.pt_init_devices(arr, len(ids)))
+    return gpu.pt_device_group_size()
+
+
 class DeviceScene:
     """A scene blob resident in HBM (``PtScene``)."""
 
