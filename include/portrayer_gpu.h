@@ -341,7 +341,7 @@ int pt_init(int device);                 /* cudaSetDevice + stream; device < 0 -
 /* A device GROUP inside one process: what rayon's thread pool is to the reference's one `Image::render` call
  * (src/render.rs:127, :216-223 — the call keeps every core of the box busy), this is for the GPUs of a box.
  * ids[0] becomes the primary device.  Afterwards pt_scene_upload also replicates the scene onto the other members
- * (textures device to device) and pt_render fans its tiles over all members — member i renders rank r*n+i of world w*n,
+ * (textures device to device) and pt_render fans its tiles over all members — member i renders rank r+w*i of world w*n,
  * (r, w) the caller's own PtRenderParams.rank / world — concurrently, every member's resolve kernel storing its RGB8
  * pixels straight into one image on the primary (peer stores over NVLink) that one D2H copy brings to the host.
  * The picture is bit-identical to a one-device render.  pt_frame_*, pt_kd_*, pt_flatten*, pt_trace_rays run on the

@@ -1828,7 +1828,7 @@ static void merge_stats(PtStats* into, const PtStats& s) {
     }
 }
 
-// pt_render over a device group: the scene's copies render interleaved tiles concurrently (member i = rank r0 * n + i
+// pt_render over a device group: the scene's copies render interleaved tiles concurrently (member i = rank r0 + w0 * i
 // of world w0 * n, r0 / w0 the caller's own rank / world), every resolve kernel stores its pixels into one image on the
 // primary, one D2H brings the slice rectangle to the host.
 static int render_group(PtScene* scene, const PtCamera* camera, const PtRenderParams& p0, const double* background,
@@ -1848,7 +1848,7 @@ static int render_group(PtScene* scene, const PtCamera* camera, const PtRenderPa
         CtxScope member(members[i]->ctx);
         PtRenderParams pi = p0;
         pi.world = w0 * (uint32_t)n;
-        pi.rank = r0 * (uint32_t)n + (uint32_t)i;
+        pi.rank = r0 + w0 * (uint32_t)i;  // the caller's tiles are k = r0 (mod w0): member i takes every n-th of THOSE
         pi.flags &= ~PT_RENDER_ROW_MAJOR;
         int rc = cached_frame(members[i], camera, pi, &frames[i]);
         if (rc == PT_OK && (hit_id_out || hit_t_out)) rc = ensure_id_buffers(frames[i]);

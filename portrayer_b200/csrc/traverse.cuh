@@ -545,33 +545,22 @@ PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3
     return found;
 }
 
-// Primitive::ray_hit in object space (primitive.rs:55-61), t + sub id only.
+// Mesh / KDMesh::ray_hit in object space: the bounding-box gate (mesh.rs:153, kdmesh.rs:67), then the fold over every
+// triangle (mesh.rs:157-167) or the walk of the mesh's own k-d tree on a clone of the range (node.rs:33-51).
 // `world_exit`: upper bound of the ray parameter at which the ray leaves the instance's box (KDMesh only: decides
 // whether the KDMesh walk may use the clipped triangle boxes, see probe_covers).
 template <bool ANY>
-PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V3 d, double s, double e, double& t,
-                      uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc, float world_exit) {
-    sub = 0;
-    switch (prim) {
-        case PT_PRIM_SPHERE: return sphere_t(o, d, s, e, t);
-        case PT_PRIM_CUBE: return cube_t<ANY>(o, d, s, e, t, sub);
-        case PT_PRIM_PLANE: return plane_t(o, d, s, e, t);
-        case PT_PRIM_CYLINDER: return cylinder_t<ANY>(o, d, s, e, t, sub);
-        case PT_PRIM_CONE: return cone_t<ANY>(o, d, s, e, t, sub);
-        default: break;
-    }
-    const PtMesh* mesh = sc.meshes + mesh_id;
+PT_D bool mesh_kinds_t(const DScene& sc, uint32_t prim, const PtMesh* mesh, V3 o, V3 d, double s, double e, double& t, uint32_t& sub,
+                       KdStack& blas_stack, uint32_t& err, WorkCounters& wc, float world_exit) {
     const uint32_t tri_first = __ldg(&mesh->tri_first);
-    if (prim == PT_PRIM_TRIANGLE) { ++wc.x_tri; return triangle_t(sc.tri_pos + tri_first, o, d, s, e, t, nullptr); }
     ++wc.x_gate;
-    if (!bbox_gate(mesh, o, d, s, e)) return false;  // (the reference's count: by the caller, like the Triangle test above)
-    if (prim == PT_PRIM_MESH) {  // fold over every triangle in index order, mesh.rs:157-167
+    if (!bbox_gate(mesh, o, d, s, e)) return false;  // (the reference's count: by the caller)
+    if (prim == PT_PRIM_MESH) {
         uint32_t n_tests = 0;
         const bool found = mesh_fold<ANY>(sc, tri_first, __ldg(&mesh->tri_count), o, d, s, e, t, sub, n_tests, wc.x_box, wc.x_tri);
         wc.triangle_tests += n_tests;
         return found;
     }
-    // KDMesh: KDTreeNode<Triangle>::ray_hit on a clone of the range (node.rs:33-51)
     const uint32_t item_first = __ldg(&mesh->item_first);
     const double extent = __ldg(&mesh->extent);
     // the walk's first probe ends at s + extent (object-space extent on the world-ray parameter): the
@@ -587,9 +576,27 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     return hit;
 }
 
+// Primitive::ray_hit in object space (primitive.rs:55-61), t + sub id only.
+template <bool ANY, bool COUNT>
+PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V3 d, double s, double e, double& t,
+                      uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc, float world_exit) {
+    sub = 0;
+    switch (prim) {
+        case PT_PRIM_SPHERE: return sphere_t(o, d, s, e, t);
+        case PT_PRIM_CUBE: return cube_t<ANY>(o, d, s, e, t, sub);
+        case PT_PRIM_PLANE: return plane_t(o, d, s, e, t);
+        case PT_PRIM_CYLINDER: return cylinder_t<ANY>(o, d, s, e, t, sub);
+        case PT_PRIM_CONE: return cone_t<ANY>(o, d, s, e, t, sub);
+        default: break;
+    }
+    const PtMesh* mesh = sc.meshes + mesh_id;
+    if (prim == PT_PRIM_TRIANGLE) { ++wc.x_tri; return triangle_t(sc.tri_pos + __ldg(&mesh->tri_first), o, d, s, e, t, nullptr); }
+    return mesh_kinds_t<ANY>(sc, prim, mesh, o, d, s, e, t, sub, blas_stack, err, wc, world_exit);
+}
+
 // FlatSceneNode::ray_cast of instance `inst` (flat_scene.rs:71-99): the ray in object space, direction NOT renormalised
 // (flat_scene.rs:75, ray.rs:130-135), then the primitive's own test over [s, e).  `pm` = (prim, mesh) of the record.
-template <bool ANY>
+template <bool ANY, bool COUNT>
 PT_D bool instance_t(const DScene& sc, uint32_t inst, uint2 pm, V3 o, V3 d, const RayF& rf, double s, double e, double& t,
                      uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc) {
     const PtInstance* rec = sc.instances + inst;
@@ -603,7 +610,7 @@ PT_D bool instance_t(const DScene& sc, uint32_t inst, uint2 pm, V3 o, V3 d, cons
     }
     ++wc.x_inst;
     wc.x_prim_flops += prim_flop_count(pm.x);
-    return primitive_t<ANY>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc, world_exit);
+    return primitive_t<ANY, COUNT>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc, world_exit);
 }
 
 // leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99)
@@ -627,7 +634,7 @@ struct TlasLeaf {
         const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&sc.instances[inst].prim));
         double t;
         uint32_t sub;
-        if (!instance_t<ANY>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) return false;
+        if (!instance_t<ANY, COUNT>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) return false;
         e = t;  // flat_scene.rs:92
         hit.t = t;
         hit.inst = inst;
@@ -680,7 +687,7 @@ PT_D bool scene_cast_linear(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& bla
         }
         double t;
         uint32_t sub;
-        if (instance_t<ANY>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) {
+        if (instance_t<ANY, COUNT>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) {
             e = t;
             hit.t = t; hit.inst = inst; hit.sub = sub;
             found = true;
