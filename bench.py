@@ -690,11 +690,16 @@ def run_ours(args, rank, world, local_rank):
     _ffi.check(_ffi.gpu.pt_measure_fp64_rate(20.0, C.byref(fp64_peak)))
     flops_per_launch = flops / launches_per_pass
     fp64_achieved = flops_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
+    # the same roof as ncu saw it: FP64-pipe warp instructions of the captured launches against one per two cycles per scheduler
+    ncu_fp64_frac = None
+    if pk.get("fp64_inst_per_launch") and pk.get("avg_us_under_ncu"):
+        sms_ = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        ncu_fp64_frac = pk["fp64_inst_per_launch"] / (pk["avg_us_under_ncu"] * 1e-6) / (sms_ * 4 * sm_max_mhz * 1e6 * 0.5)
     roofline_fp64 = {"bound": "fp64 issue (no FMA)", "kernel": kname, "achieved": fp64_achieved, "peak": fp64_peak.value,
                      "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak.value if fp64_peak.value else None,
                      "peak_source": "pt_measure_fp64_rate: DMUL+DADD chains, measured in this run",
                      "executed_flops_per_launch": flops_per_launch,
-                     "ncu_fp64_pipe_active_pct": pk.get("fp64_pipe_pct"),
+                     "ncu_fp64_pipe_active_frac": ncu_fp64_frac,
                      "note": "f64 operations executed: 14 per kd split walked + (42 + primitive) per exact instance test + 58 per "
                              "exact triangle test + 150 per bbox gate; tests the FP32 box cull rejected are not counted"}
     # (3) issue slots: warp instructions per launch from the ncu capture of the same kernels (profiles/), against

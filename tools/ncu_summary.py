@@ -86,6 +86,8 @@ def traffic(path: str, source: str) -> None:
             v = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
         except ValueError:
             continue
+        if "_kernel<(bool)1" in r[ki] or "_kernel<1" in r[ki]:
+            continue  # the counting variants of the traversal kernels (bench.py's counting pass): not what the timed region runs
         name = r[ki].split("(")[0].replace("void ", "").replace("ptd::<unnamed>::", "").split("<")[0]
         per[name][r[mi]] += v
         ids[name].add(r[ii])
@@ -95,6 +97,15 @@ def traffic(path: str, source: str) -> None:
         rd, wr = m.get("dram__bytes_read.sum", 0.0) / n, m.get("dram__bytes_write.sum", 0.0) / n
         out[name] = {"launches": n, "dram_bytes_per_launch": rd + wr, "dram_read_bytes_per_launch": rd,
                      "dram_write_bytes_per_launch": wr, "avg_us_under_ncu": m.get("gpu__time_duration.sum", 0.0) / n}
+        # issue-slot / lane / FP64-pipe figures when the capture carried them (tools/profile_launches.sh)
+        inst, tinst = m.get("smsp__inst_executed.sum", 0.0), m.get("smsp__thread_inst_executed.sum", 0.0)
+        if inst:
+            out[name]["inst_per_launch"] = inst / n
+            if tinst:
+                out[name]["lanes_per_inst"] = tinst / inst
+            f64 = m.get("smsp__inst_executed_pipe_fp64.sum", 0.0)
+            if f64:
+                out[name]["fp64_inst_per_launch"] = f64 / n
     out["_source"] = source
     print(json.dumps(out, indent=1))
 
