@@ -292,6 +292,13 @@ typedef struct PtRenderParams {
  * offending ray treats that split as a miss of both children (what the device does anyway before it reports), the bit
  * stays in PtStats.device_error_bits and PtStats.err_* say where it happened. */
 #define PT_RENDER_TOLERATE_KD_PLANE 32u
+/* By default the k-d walks (scene tree and KDMesh trees) do not enter a subtree when the ray certainly misses the union
+ * box of everything the subtree's leaves hold, inside the range the subtree would be walked with: nothing down there can
+ * return a hit, so pictures, hit ids and hit parameters are exactly those of the reference's full walk.  What a skipped
+ * subtree can hide is the reference's kd-plane panic (above), should the reference have tripped it DOWN THERE — on a ray
+ * segment that cannot hit anything.  This flag makes the device walk every subtree the reference walks: every such panic
+ * is reproduced, at about 1.3x the traversal time.  PT_RENDER_COUNTERS implies it (the counters are the reference's work). */
+#define PT_RENDER_EXACT_WALK 64u
 
 typedef struct PtStats {
     /* rays = every ray_cast issued against the scene root */

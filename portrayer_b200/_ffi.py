@@ -54,6 +54,7 @@ PT_BG_PER_PIXEL, PT_BG_PER_ROW, PT_BG_CONSTANT = 0, 1, 2
 PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS, PT_RENDER_KERNEL_TIMES = 1, 2, 4
 PT_RENDER_ROW_MAJOR, PT_RENDER_NO_GRAPH = 8, 16
 PT_RENDER_TOLERATE_KD_PLANE = 32
+PT_RENDER_EXACT_WALK = 64
 PT_DEVERR_NORMALMAP, PT_DEVERR_TEXTURE, PT_DEVERR_KD_PLANE, PT_DEVERR_TIR, PT_DEVERR_OVERFLOW = 1, 2, 4, 8, 16
 PT_EPSILON = 0.00001
 PT_MAX_RECURSION_DEPTH = 10

@@ -299,9 +299,9 @@ struct PtFrame {
     int n_levels = 1;
     // __constant__ slot + graph
     int slot = -1;
-    cudaGraph_t graph[2] = {nullptr, nullptr};  // [0] plain, [1] counting kernels
-    cudaGraphExec_t exec[2] = {nullptr, nullptr};
-    cudaGraphNode_t camera_node[2] = {nullptr, nullptr};
+    cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};  // one per walk_mode(): exact, counting, pruned traversal kernels
+    cudaGraphExec_t exec[3] = {nullptr, nullptr, nullptr};
+    cudaGraphNode_t camera_node[3] = {nullptr, nullptr, nullptr};
     bool graph_failed = false;
     uint64_t last_use = 0;
     // a render that has been enqueued but not finished (pt_frame_enqueue / pt_frame_finish)
@@ -530,7 +530,7 @@ ptd::KdAllocator arena_allocator() {
 
 // leaf cull structure (leaf_cull.cu) of one forest; `extra` float4 are appended to the storage (the scene tree keeps its root box there)
 int build_leaf_cull(PtKdNode* d_nodes, uint32_t n_nodes, const uint32_t* d_items, uint32_t n_items, const std::vector<ptd::LcTree>& trees,
-                    const float4* d_item_boxes, size_t extra, float4** d_storage, ptd::LeafCull* out) {
+                    uint32_t max_depth, const float4* d_item_boxes, size_t extra, float4** d_storage, ptd::LeafCull* out) {
     const ptd::LeafCullSizes sz = ptd::leaf_cull_sizes(n_nodes, n_items);
     cudaError_t e;
     g_dev.release(*d_storage);
@@ -545,7 +545,7 @@ int build_leaf_cull(PtKdNode* d_nodes, uint32_t n_nodes, const uint32_t* d_items
         if (e != cudaSuccess) { g_dev.release(scratch); return fail(PT_ERR_CUDA, "leaf cull upload failed: %s", cudaGetErrorString(e)); }
     }
     debug_sync("leaf cull: before launch");
-    e = ptd::launch_leaf_cull(d_nodes, n_nodes, d_items, n_items, d_trees, (uint32_t)trees.size(), d_item_boxes, *d_storage, scratch,
+    e = ptd::launch_leaf_cull(d_nodes, n_nodes, d_items, n_items, d_trees, (uint32_t)trees.size(), max_depth + 1, d_item_boxes, *d_storage, scratch,
                               arena_allocator(), out, g_stream);
     debug_sync("leaf cull: built");
     g_dev.release(scratch);  // stream-ordered reuse
@@ -557,8 +557,8 @@ int build_leaf_cull(PtKdNode* d_nodes, uint32_t n_nodes, const uint32_t* d_items
 int build_tlas_cull(PtScene* s) {
     fill_view(s);
     const std::vector<ptd::LcTree> one{ptd::LcTree{0u, s->h.n_tlas_nodes, 0u, 0u}};
-    int rc = build_leaf_cull(const_cast<PtKdNode*>(s->view.tlas_nodes), s->h.n_tlas_nodes, s->view.tlas_items, s->h.n_tlas_items, one, s->d_aabb,
-                             2, &s->d_tl_cull, &s->tl_cull);
+    int rc = build_leaf_cull(const_cast<PtKdNode*>(s->view.tlas_nodes), s->h.n_tlas_nodes, s->view.tlas_items, s->h.n_tlas_items, one,
+                             s->h.tlas_depth, s->d_aabb, 2, &s->d_tl_cull, &s->tl_cull);
     if (rc != PT_OK) return rc;
     ptd::launch_root_box(s->d_aabb, s->h.n_instances, s->d_tl_cull + 2 * ptd::leaf_cull_sizes(s->h.n_tlas_nodes, s->h.n_tlas_items).set_float4, g_stream);
     debug_sync("root box");
@@ -620,7 +620,7 @@ int build_instance_bounds(PtScene* s, bool with_tlas = true) {
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "instance bounds kernel failed: %s", cudaGetErrorString(e));
     // leaf cull structures: KDMesh trees (the blob's node records, patched in place), then the scene tree
     int rc = build_leaf_cull(const_cast<PtKdNode*>(s->view.blas_nodes), s->h.n_blas_nodes, s->view.blas_items, s->h.n_blas_items, s->blas_trees,
-                             s->d_tri_aabb, 0, &s->d_bl_cull, &s->bl_cull);
+                             s->h.blas_max_depth, s->d_tri_aabb, 0, &s->d_bl_cull, &s->bl_cull);
     if (rc != PT_OK) return rc;
     if (with_tlas) rc = build_tlas_cull(s);
     else fill_view(s);
@@ -628,7 +628,7 @@ int build_instance_bounds(PtScene* s, bool with_tlas = true) {
 }
 
 void destroy_graphs(PtFrame* f) {
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 3; ++k) {
         if (f->exec[k]) cudaGraphExecDestroy(f->exec[k]);
         if (f->graph[k]) cudaGraphDestroy(f->graph[k]);
         f->exec[k] = nullptr;
@@ -780,18 +780,18 @@ struct KernelTimer {
 // Stream path: run the levels of one batch kernel by kernel; the host looks at the control block after every
 // level and stops at the first level without rays.  Leaves the final control block in *h_ctl.
 int run_levels_stream(int slot, uint32_t n_lights, uint64_t capacity, BatchCtl* d_ctl, BatchCtl* h_ctl, uint32_t n_paths,
-                      int n_levels, bool count, cudaStream_t st, uint32_t* launches, KernelTimer* timer, bool linear = false) {
+                      int n_levels, int mode, cudaStream_t st, uint32_t* launches, KernelTimer* timer, bool linear = false) {
     for (int level = 0; level < n_levels; ++level) {
         // level d holds at most n_paths * 2^d rays, and never more than the pool
         const uint64_t bound = (uint64_t)n_paths << std::min(level, 31);
         const uint64_t max_items = std::min<uint64_t>(bound, capacity);
         timer->level = level;
         timer->begin(0, st);
-        launch_extend(slot, max_items, count, linear, st);
+        launch_extend(slot, max_items, mode, linear, st);
         timer->end(st);
         if (n_lights) {
             timer->begin(1, st);
-            launch_shadow(slot, max_items, n_lights, count, linear, st);
+            launch_shadow(slot, max_items, n_lights, mode, linear, st);
             timer->end(st);
         }
         timer->begin(2, st);
@@ -854,11 +854,20 @@ bool graphs_enabled() {
     return v == 1;
 }
 
-int ensure_graph(PtFrame* f, bool count) {
-    const int k = count ? 1 : 0;
+// which traversal kernels a render with these flags runs (kernels.h)
+int walk_mode(uint32_t flags) {
+    if (flags & PT_RENDER_COUNTERS) return ptd::kWalkCount;  // the counters are the REFERENCE's work: the full walk
+    if (flags & PT_RENDER_EXACT_WALK) return ptd::kWalkExact;
+    static int forced = -1;  // PT_EXACT_WALK=1 in the environment: the flag for every render (A/B runs)
+    if (forced < 0) { const char* e = getenv("PT_EXACT_WALK"); forced = (e && *e && *e != '0') ? 1 : 0; }
+    return forced ? ptd::kWalkExact : ptd::kWalkPrune;
+}
+
+int ensure_graph(PtFrame* f, int mode) {
+    const int k = mode;
     if (f->exec[k]) return PT_OK;
     cudaError_t e = build_frame_graph(f->slot, f->batch_slots, f->params.samples, std::max<uint32_t>(f->n_lights_cap, 1),
-                                      f->pool.capacity, count, &f->graph[k], &f->exec[k], &f->camera_node[k]);
+                                      f->pool.capacity, mode, &f->graph[k], &f->exec[k], &f->camera_node[k]);
     if (e != cudaSuccess) {
         cudaGetLastError();
         f->graph_failed = true;
@@ -972,7 +981,7 @@ int ensure_id_buffers(PtFrame* f) {
 // careful mode: one batch at a time, host check after every level, halve the batch on node-pool overflow
 int render_stream_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void* user, PtStats* stats, uint32_t* launches_out,
                        uint32_t* batches_out, uint32_t* retries_out, uint32_t* error_bits_out) {
-    const bool count = (f->params.flags & PT_RENDER_COUNTERS) != 0;
+    const int count = walk_mode(f->params.flags);
     const uint32_t owned = (uint32_t)f->pixel_index.size();
     const uint32_t S = f->params.samples;
     KernelTimer timer;
@@ -1010,9 +1019,8 @@ int render_stream_path(PtFrame* f, cudaStream_t st, PtProgressFn progress, void*
 // graph path, part 1: every batch is one replay of the frame graph; control blocks come back through a pinned ring.
 // Nothing here waits for the device.
 int enqueue_ranges(PtFrame* f, cudaStream_t st, const std::vector<std::pair<uint32_t, uint32_t>>& ranges) {
-    const bool count = (f->params.flags & PT_RENDER_COUNTERS) != 0;
-    const int k = count ? 1 : 0;
-    int rc = ensure_graph(f, count);
+    const int k = walk_mode(f->params.flags);
+    int rc = ensure_graph(f, k);
     if (rc != PT_OK) return rc;
     const uint32_t S = f->params.samples;
     const size_t n_batches = ranges.size();
@@ -1962,7 +1970,7 @@ int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const doubl
     const uint32_t depth = max_depth ? max_depth : PT_MAX_RECURSION_DEPTH;
     if (depth > PT_MAX_DEPTH_SUPPORTED) return fail(PT_ERR_INVALID, "max_depth > %u is not supported", PT_MAX_DEPTH_SUPPORTED);
     const int n_levels = scene->has_reflective ? (int)depth + 1 : 1;
-    const bool count = (flags & PT_RENDER_COUNTERS) != 0;
+    const int count = walk_mode(flags);
     const uint32_t batch = (uint32_t)std::min<uint64_t>(n, 1u << 20);
     const uint32_t capacity = scene->has_reflective ? batch * 8 : batch;
 

@@ -23,6 +23,7 @@ struct LeafCull {
     float4* occ;          // [2 * leaves]       occ[2 * rank], occ[2 * rank + 1] = lo, hi
     float4* grp;          // [2 * runs]         grp[2 * (gbase + g)]
     float4* item;         // [2 * 8 * runs]     item[2 * ((gbase + g) * 8 + j)]
+    float4* node;         // [2 * nodes]        node[2 * i]: union of the occupied boxes of the leaves below node i (forest index)
     uint32_t set_stride;  // in float4
     uint32_t pad_;
 };

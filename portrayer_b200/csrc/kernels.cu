@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(kBlock) load_rays_kernel(int slot_id, uint32_t
 
 // ------------------------------------------------------------------ extend (closest hit)
 // LINEAR: the PT_RENDER_LINEAR_TLAS cross-check (scene_cast_linear: no k-d tree, every instance in list order)
-template <bool COUNT, bool LINEAR = false>
+// PRUNE: the walk skips subtrees whose node box the ray misses (traverse.cuh kd_walk); off for PT_RENDER_EXACT_WALK and
+// for the counting kernels, which report the reference's work
+template <bool COUNT, bool LINEAR = false, bool PRUNE = false>
 __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(int slot_id) {
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
         Hit hit{(double)INFINITY, kNone, 0};
         const uint32_t err_before = err;
         const bool found = LINEAR ? scene_cast_linear<false, COUNT>(sc, o, d, hit, blas_stack, err, wc)
-                                  : scene_cast<false, COUNT>(sc, o, d, hit, tlas_stack, blas_stack, err, wc);
+                                  : scene_cast<false, COUNT, PRUNE>(sc, o, d, hit, tlas_stack, blas_stack, err, wc);
         if (err != err_before) record_error(fs.fp, pool, ctl, err & ~err_before, i, 0u | level << 8);
         pool.t[i] = found ? hit.t : (double)INFINITY;
         pool.inst[i] = found ? hit.inst : kNone;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
 }
 
 // ------------------------------------------------------------------ shadow (any hit), light-major
-template <bool COUNT, bool LINEAR = false>
+template <bool COUNT, bool LINEAR = false, bool PRUNE = false>
 __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(int slot_id) {
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
         Hit hit{(double)INFINITY, kNone, 0};
         const uint32_t err_before = err;
         const bool occluded = LINEAR ? scene_cast_linear<true, COUNT>(sc, hit_point, light_dir, hit, blas_stack, err, wc)
-                                     : scene_cast<true, COUNT>(sc, hit_point, light_dir, hit, tlas_stack, blas_stack, err, wc);
+                                     : scene_cast<true, COUNT, PRUNE>(sc, hit_point, light_dir, hit, tlas_stack, blas_stack, err, wc);
         if (err != err_before) record_error(fp, pool, ctl, err & ~err_before, i, 1u | level << 8 | l << 16);
         pool.occl[(size_t)l * pool.capacity + i] = occluded ? 1 : 0;
         ++cast;
@@ -819,7 +821,7 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* __restrict__ sin
     if (s == 12345.678) sink[0] = s;  // never true: keeps the chains alive
 }
 
-int g_grid_extend[2] = {0, 0}, g_grid_shadow[2] = {0, 0}, g_grid_shade = 0;
+int g_grid_extend[3] = {0, 0, 0}, g_grid_shadow[3] = {0, 0, 0}, g_grid_shade = 0;  // [kWalkExact | kWalkCount | kWalkPrune]
 
 template <class K>
 int persistent_grid(K kernel) {
@@ -839,6 +841,8 @@ void kernels_init() {
     g_grid_extend[1] = persistent_grid(extend_kernel<true>);
     g_grid_shadow[0] = persistent_grid(shadow_kernel<false>);
     g_grid_shadow[1] = persistent_grid(shadow_kernel<true>);
+    g_grid_extend[2] = persistent_grid(extend_kernel<false, false, true>);
+    g_grid_shadow[2] = persistent_grid(shadow_kernel<false, false, true>);
     g_grid_shade = persistent_grid(shade_kernel);
 }
 
@@ -890,16 +894,18 @@ void launch_load_rays(int slot, uint32_t first, uint32_t n_paths, cudaStream_t s
     load_rays_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(slot, first, n_paths);
 }
 // A level can never hold more rays than `max_items`; the persistent grid is capped to it.
-void launch_extend(int slot, uint64_t max_items, bool count, bool linear, cudaStream_t st) {
-    const int grid = capped(g_grid_extend[count ? 1 : 0], max_items);
+void launch_extend(int slot, uint64_t max_items, int mode, bool linear, cudaStream_t st) {
+    const int grid = capped(g_grid_extend[mode], max_items);
     if (linear) extend_kernel<true, true><<<grid, kBlock, 0, st>>>(slot);
-    else if (count) extend_kernel<true><<<grid, kBlock, 0, st>>>(slot);
+    else if (mode == kWalkCount) extend_kernel<true><<<grid, kBlock, 0, st>>>(slot);
+    else if (mode == kWalkPrune) extend_kernel<false, false, true><<<grid, kBlock, 0, st>>>(slot);
     else extend_kernel<false><<<grid, kBlock, 0, st>>>(slot);
 }
-void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, bool count, bool linear, cudaStream_t st) {
-    const int grid = capped(g_grid_shadow[count ? 1 : 0], max_items * (n_lights ? n_lights : 1));
+void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, int mode, bool linear, cudaStream_t st) {
+    const int grid = capped(g_grid_shadow[mode], max_items * (n_lights ? n_lights : 1));
     if (linear) shadow_kernel<true, true><<<grid, kBlock, 0, st>>>(slot);
-    else if (count) shadow_kernel<true><<<grid, kBlock, 0, st>>>(slot);
+    else if (mode == kWalkCount) shadow_kernel<true><<<grid, kBlock, 0, st>>>(slot);
+    else if (mode == kWalkPrune) shadow_kernel<false, false, true><<<grid, kBlock, 0, st>>>(slot);
     else shadow_kernel<false><<<grid, kBlock, 0, st>>>(slot);
 }
 void launch_shade(int slot, uint64_t max_items, cudaGraphConditionalHandle loop, cudaStream_t st) {
@@ -919,7 +925,7 @@ void launch_export_rays(int slot, uint32_t n_paths, cudaStream_t st) {
 // sized for a full batch of `n_slots` pixels; the camera node's (first_slot, n_slots) parameters are patched
 // per batch (cudaGraphExecKernelNodeSetParams), everything else is read from c_state[slot] / the control block.
 cudaError_t build_frame_graph(int slot, uint32_t n_slots, uint32_t samples, uint32_t n_lights_max, uint64_t capacity,
-                              bool count, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out, cudaGraphNode_t* camera_node) {
+                              int mode, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out, cudaGraphNode_t* camera_node) {
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaGraphCreate(&graph, 0);
     if (e != cudaSuccess) return e;
@@ -954,12 +960,12 @@ cudaError_t build_frame_graph(int slot, uint32_t n_slots, uint32_t samples, uint
         cudaKernelNodeParams k{};
         k.blockDim = dim3(kBlock);
         k.kernelParams = args1;
-        k.func = count ? (void*)extend_kernel<true> : (void*)extend_kernel<false>;
-        k.gridDim = dim3(capped(g_grid_extend[count ? 1 : 0], capacity));
+        k.func = mode == kWalkCount ? (void*)extend_kernel<true> : mode == kWalkPrune ? (void*)extend_kernel<false, false, true> : (void*)extend_kernel<false>;
+        k.gridDim = dim3(capped(g_grid_extend[mode], capacity));
         e = cudaGraphAddKernelNode(&n_ext, body, nullptr, 0, &k);
         if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
-        k.func = count ? (void*)shadow_kernel<true> : (void*)shadow_kernel<false>;
-        k.gridDim = dim3(capped(g_grid_shadow[count ? 1 : 0], capacity * (n_lights_max ? n_lights_max : 1)));
+        k.func = mode == kWalkCount ? (void*)shadow_kernel<true> : mode == kWalkPrune ? (void*)shadow_kernel<false, false, true> : (void*)shadow_kernel<false>;
+        k.gridDim = dim3(capped(g_grid_shadow[mode], capacity * (n_lights_max ? n_lights_max : 1)));
         e = cudaGraphAddKernelNode(&n_shd, body, &n_ext, 1, &k);
         if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
         void* args2[2] = {&slot, &handle};

@@ -28,8 +28,10 @@ struct LeafCullSizes {
 };
 LeafCullSizes leaf_cull_sizes(uint32_t n_nodes, uint32_t n_items);
 // nodes: the forest's node array in device memory — the leaves' `split` fields are overwritten with rank | gbase << 32
+// max_depth: the deepest tree of the forest (sweeps of the bottom-up node-box union)
 cudaError_t launch_leaf_cull(PtKdNode* nodes, uint32_t n_nodes, const uint32_t* items, uint32_t n_items, const LcTree* d_trees, uint32_t n_trees,
-                             const float4* item_boxes, float4* storage, void* scratch, const KdAllocator& al, LeafCull* out, cudaStream_t st);
+                             uint32_t max_depth, const float4* item_boxes, float4* storage, void* scratch, const KdAllocator& al, LeafCull* out,
+                             cudaStream_t st);
 void launch_root_box(const float4* boxes, uint32_t n, float4* out2, cudaStream_t st);
 // upload time: padded FP32 object-space boxes of all triangles
 void launch_triangle_bounds(const PtTriPos* tri_pos, uint32_t n, float4* tri_aabb, cudaStream_t st);
@@ -44,9 +46,12 @@ void launch_group_bounds(const float4* in, uint32_t n, uint32_t run, float4* out
 // stream path: one launch per call; batch / level bookkeeping lives in the device control block
 void launch_camera(int slot, uint32_t first_slot, uint32_t n_slots, uint32_t samples, cudaStream_t st);
 void launch_load_rays(int slot, uint32_t first, uint32_t n_paths, cudaStream_t st);
+// which variant of the traversal kernels walks the trees: the reference's walk as it is (PT_RENDER_EXACT_WALK), the same
+// with the work counters (PT_RENDER_COUNTERS), or the walk that skips subtrees the ray cannot hit anything in (default)
+enum { kWalkExact = 0, kWalkCount = 1, kWalkPrune = 2 };
 // linear: the PT_RENDER_LINEAR_TLAS cross-check kernels (always counting)
-void launch_extend(int slot, uint64_t max_items, bool count, bool linear, cudaStream_t st);
-void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, bool count, bool linear, cudaStream_t st);
+void launch_extend(int slot, uint64_t max_items, int mode, bool linear, cudaStream_t st);
+void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, int mode, bool linear, cudaStream_t st);
 void launch_shade(int slot, uint64_t max_items, cudaGraphConditionalHandle loop, cudaStream_t st);
 void launch_tree_eval(int slot, uint32_t n_paths, cudaStream_t st);
 void launch_resolve(int slot, uint32_t n_slots, cudaStream_t st);
@@ -54,7 +59,7 @@ void launch_export_rays(int slot, uint32_t n_paths, cudaStream_t st);
 
 // graph path: camera -> WHILE(level has rays){extend, shadow, shade} -> tree_eval -> resolve
 cudaError_t build_frame_graph(int slot, uint32_t n_slots, uint32_t samples, uint32_t n_lights_max, uint64_t capacity,
-                              bool count, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out, cudaGraphNode_t* camera_node);
+                              int mode, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out, cudaGraphNode_t* camera_node);
 cudaError_t set_graph_batch(cudaGraphExec_t exec, cudaGraphNode_t camera_node, int slot, uint32_t first_slot, uint32_t n_slots,
                             uint32_t grid_slots, uint32_t samples);
 }  // namespace ptd

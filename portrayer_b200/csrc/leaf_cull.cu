@@ -23,6 +23,13 @@
 //
 // A leaf's record in the device copy of the node array is patched to carry where its boxes are: the `split` field
 // (unused for leaves, portrayer_gpu.h PtKdNode) becomes rank | gbase << 32.
+//
+//   node[i]                    union of the occupied boxes of every leaf below node i (a leaf's own occupied box for a leaf)
+//
+// With the node boxes the walk can PRUNE: a subtree whose box the ray misses inside the range it would be visited with
+// holds no leaf that can return a hit, so the walk need not descend into it (traverse.cuh kd_walk, PRUNE).  The reference
+// descends anyway and finds nothing; on graphics-castle that is most of what a ray does (52 split steps per ray, a
+// third of them below the last subtree that holds anything near the ray).
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -172,7 +179,40 @@ __global__ void __launch_bounds__(kB) lc_build_kernel(PtKdNode* __restrict__ nod
             if (lane == 0) {
                 store_box(out.occ, rank, occ_clip);
                 store_box(out.occ + out.set_stride, rank, occ_full);
+                store_box(out.node, i, occ_clip);
+                store_box(out.node + out.set_stride, i, occ_full);
                 nodes[i].split = __longlong_as_double((long long)((unsigned long long)rank | (unsigned long long)gbase << 32));
+            }
+        }
+    }
+}
+
+// node boxes of the inner nodes: empty first, then `depth` sweeps of box[i] = box[front] U box[back] (children lie after
+// their parents in the arrays, so sweep k settles every node whose subtree is at most k levels high)
+__global__ void __launch_bounds__(kB) lc_node_init_kernel(const PtKdNode* __restrict__ nodes, uint32_t n_nodes, LeafCull out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
+        if ((nodes[i].a & 3u) == 3u && nodes[i].b != 0u) continue;  // a leaf with candidates: written by lc_build_kernel
+        store_box(out.node, i, empty_box());
+        store_box(out.node + out.set_stride, i, empty_box());
+    }
+}
+__global__ void __launch_bounds__(kB) lc_node_union_kernel(const PtKdNode* __restrict__ nodes, const LcTree* __restrict__ trees, uint32_t n_trees,
+                                                            LeafCull out) {
+    for (uint32_t t = blockIdx.y; t < n_trees; t += gridDim.y) {
+        const LcTree tr = trees[t];
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < tr.node_count; j += gridDim.x * blockDim.x) {
+            const uint32_t i = tr.node_first + j;
+            const PtKdNode n = nodes[i];
+            if ((n.a & 3u) == 3u) continue;
+            const uint32_t front = n.a >> 2, back = n.b;
+            if (front >= tr.node_count || back >= tr.node_count) continue;
+#pragma unroll
+            for (int set = 0; set < 2; ++set) {
+                float4* __restrict__ nb = out.node + (size_t)set * out.set_stride;
+                const float4 fl = nb[2 * (size_t)(tr.node_first + front)], fh = nb[2 * (size_t)(tr.node_first + front) + 1];
+                const float4 bl = nb[2 * (size_t)(tr.node_first + back)], bh = nb[2 * (size_t)(tr.node_first + back) + 1];
+                nb[2 * (size_t)i] = make_float4(fminf(fl.x, bl.x), fminf(fl.y, bl.y), fminf(fl.z, bl.z), 0.f);
+                nb[2 * (size_t)i + 1] = make_float4(fmaxf(fh.x, bh.x), fmaxf(fh.y, bh.y), fmaxf(fh.z, bh.z), 0.f);
             }
         }
     }
@@ -207,18 +247,20 @@ LeafCullSizes leaf_cull_sizes(uint32_t n_nodes, uint32_t n_items) {
     LeafCullSizes s;
     s.n_leaf_cap = std::max<uint32_t>(n_nodes, 1);
     s.n_grp_cap = (uint32_t)std::min<uint64_t>((uint64_t)n_items / 8 + n_nodes + 1, 0x0FFFFFFFull);
-    s.set_float4 = 2 * ((size_t)s.n_leaf_cap + (size_t)s.n_grp_cap * 9);
+    s.set_float4 = 2 * ((size_t)s.n_leaf_cap + (size_t)s.n_grp_cap * 9 + (size_t)std::max<uint32_t>(n_nodes, 1));
     s.scratch_bytes = (size_t)std::max<uint32_t>(n_nodes, 1) * 20 + 128;
     return s;
 }
 
 // storage: 2 * set_float4 float4 (clipped set, then full set); scratch: leaf_cull_sizes().scratch_bytes + the scan's tile buffer
 cudaError_t launch_leaf_cull(PtKdNode* nodes, uint32_t n_nodes, const uint32_t* items, uint32_t n_items, const LcTree* d_trees, uint32_t n_trees,
-                             const float4* item_boxes, float4* storage, void* scratch, const KdAllocator& al, LeafCull* out, cudaStream_t st) {
+                             uint32_t max_depth, const float4* item_boxes, float4* storage, void* scratch, const KdAllocator& al, LeafCull* out,
+                             cudaStream_t st) {
     const LeafCullSizes sz = leaf_cull_sizes(n_nodes, n_items);
     out->occ = storage;
     out->grp = storage + 2 * (size_t)sz.n_leaf_cap;
     out->item = out->grp + 2 * (size_t)sz.n_grp_cap;
+    out->node = out->item + 16 * (size_t)sz.n_grp_cap;
     out->set_stride = (uint32_t)sz.set_float4;
     if (!n_nodes || !n_trees) return cudaSuccess;
     uint32_t* parent = static_cast<uint32_t*>(scratch);
@@ -238,8 +280,10 @@ cudaError_t launch_leaf_cull(PtKdNode* nodes, uint32_t n_nodes, const uint32_t* 
     if (e != cudaSuccess) { tiles.release(); return e; }
     if (getenv("PT_DEBUG_SYNC")) fprintf(stderr, "[pt] lc scan: %s\n", cudaGetErrorString(cudaStreamSynchronize(st)));
     const dim3 grid_b(std::min<uint32_t>(blocks((uint64_t)n_nodes * 32), 4096u), std::min<uint32_t>(n_trees, 1024u));
+    lc_node_init_kernel<<<std::min<uint32_t>(blocks(n_nodes), 4096u), kB, 0, st>>>(nodes, n_nodes, *out);
     lc_build_kernel<<<grid_b, kB, 0, st>>>(nodes, items, d_trees, n_trees, parent, scan_out, item_boxes, *out, sz.n_leaf_cap, sz.n_grp_cap);
     tiles.release();  // stream-ordered reuse
+    for (uint32_t sweep = 0; sweep < max_depth; ++sweep) lc_node_union_kernel<<<grid, kB, 0, st>>>(nodes, d_trees, n_trees, *out);
     return cudaGetLastError();
 }
 

@@ -241,84 +241,6 @@ PT_D bool bbox_gate(const PtMesh* __restrict__ mesh, V3 o, V3 d, double s, doubl
     return cube_t<true>(lo, ld, s, e, t, face);
 }
 
-// ------------------------------------------------------------------ kd walk
-// One entry per pending far child: the child's 16-byte record itself (it was fetched together with the near child, so a
-// pop costs ONE local-memory round trip instead of index -> node) and the start of its range.  The END of a pending
-// range is not stored: a push happens with the current range [s, e) and leaves [s, tp) current and [tp, e) pending, so
-// the current `e` is always the `s` of the entry on top of the stack (the walk's initial `e` when the stack is empty),
-// and a popped entry's end is the `s` of the entry below it.
-struct KdStack {
-    uint4 node[PT_MAX_KD_STACK];
-    double s[PT_MAX_KD_STACK];
-};
-
-// Iterative form of ray_cast_impl (node.rs:66-203). `leaf(rank, gbase, first, count, s, e)` returns true when the
-// leaf's fold produced a hit inside [s, e) — (rank, gbase) locate the leaf's cull boxes, leaf_cull.cu —; the first
-// leaf that does ends the walk.
-// "while-while" form: every lane first descends to its next leaf (a short loop of split steps), and only then do the
-// lanes of the warp run their leaves together.  With one loop whose body is "a split step OR a whole leaf", a lane that
-// is still descending advances ONE split per leaf any other lane of its warp processes — and a leaf can hold a whole
-// KDMesh walk.
-// `od`: the ray as an ARRAY (origin x, y, z, direction x, y, z) that the split step indexes by the node's axis: one
-// local-memory load per operand (an L1 hit) where selecting among three register pairs costs a branch and six moves
-// per operand, and the ray does not occupy twelve registers for the length of the walk.
-#ifndef PT_KD_RAY_ARRAY
-#define PT_KD_RAY_ARRAY 1
-#endif
-template <class LeafFn>
-PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, const double (&od)[6], double s, const double e0, KdStack& stack,
-                  LeafFn& leaf, uint32_t& err, uint32_t& n_splits) {
-    int sp = 0;
-    double e = e0;
-    const uint4* __restrict__ nodes4 = reinterpret_cast<const uint4*>(nodes);
-    uint4 w = __ldg(nodes4);
-    for (;;) {
-        bool dead = false;  // the reference would have panicked in this subtree: it yields nothing
-        while ((w.z & 3u) != 3u) {
-            const uint32_t axis = w.z & 3u;
-            const double split = __hiloint2double((int)w.y, (int)w.x);
-            ++n_splits;
-            // both children are fetched before the side tests: the loads' latency overlaps the f64 dependency chain
-            // below instead of following it (the node fetch was the top long-scoreboard stall of the walk)
-            const uint4 wf = __ldg(nodes4 + (w.z >> 2)), wb = __ldg(nodes4 + w.w);
-            // node.rs:119-127
-            double t_max = s + extent;
-            if (!in_range(s, e, t_max)) t_max = e - kEps;
-            const double t_min = s + kEps;
-#if PT_KD_RAY_ARRAY
-            const double oa = od[axis], da = od[3 + axis];
-#else
-            const double oa = axis == 0 ? od[0] : (axis == 1 ? od[1] : od[2]);
-            const double da = axis == 0 ? od[3] : (axis == 1 ? od[4] : od[5]);
-#endif
-            const double p0 = oa + da * t_min;
-            const double p1 = oa + da * t_max;
-            const bool f0 = (p0 - split) >= 0.0;  // which_side, infinite_plane.rs:27-35
-            const bool f1 = (p1 - split) >= 0.0;
-            if (f0 != f1) {
-                const double tp = (split - oa) / da;  // ray_hit_axis_aligned_plane, node.rs:90-110
-                if (!in_range(s, e, tp)) {
-                    err |= PT_DEVERR_KD_PLANE;  // .expect("bug: ray should definitely hit infinite plane")
-                    dead = true;
-                    break;
-                }
-                // near child on [s, tp); if it misses, far child on [tp, e). node.rs:150-166
-                stack.node[sp] = f0 ? wb : wf;
-                stack.s[sp] = tp;
-                ++sp;
-                e = tp;
-            }
-            w = f0 ? wf : wb;  // node.rs:134-137
-        }
-        if (!dead && w.w != 0u && leaf(w.x, w.y, w.z >> 2, w.w, s, e)) return true;
-        if (sp == 0) return false;
-        --sp;
-        w = stack.node[sp];
-        s = stack.s[sp];
-        e = sp ? stack.s[sp - 1] : e0;
-    }
-}
-
 // ------------------------------------------------------------------ conservative FP32 cull
 // Before a candidate is tested exactly (f64, object space) a padded FP32 box that contains every hit it could return
 // is slab-tested against the ray.  The test may only answer "certainly no hit inside [s, e)": every rounding source
@@ -375,6 +297,19 @@ PT_D bool box_may_hit(const float4* __restrict__ bb, const RayF& r, const RangeF
     box_interval(bb, r, tn, tf);
     return !(tn > tf) && !(tf < rg.s) && !(tn > rg.e);
 }
+// the same for a box that may be EMPTY (lo > hi: a subtree without a single candidate): nothing to hit
+PT_D bool box_may_hit_nonempty(const float4* __restrict__ bb, const RayF& r, const RangeF& rg) {
+    const float4 lo = __ldg(bb), hi = __ldg(bb + 1);
+    if (lo.x > hi.x) return false;
+    const float ax = __fmaf_rn(lo.x, r.ix, r.cx_lo), bx = __fmaf_rn(hi.x, r.ix, r.cx_hi);
+    const float ay = __fmaf_rn(lo.y, r.iy, r.cy_lo), by = __fmaf_rn(hi.y, r.iy, r.cy_hi);
+    const float az = __fmaf_rn(lo.z, r.iz, r.cz_lo), bz = __fmaf_rn(hi.z, r.iz, r.cz_hi);
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    tn = __fmaf_rn(-2e-5f, fabsf(tn), tn);
+    tf = __fmaf_rn(2e-5f, fabsf(tf), tf) + kClipPadT;
+    return !(tn > tf) && !(tf < rg.s) && !(tn > rg.e);
+}
 // The probe segment of the walk ends at s + extent (node.rs:119): does the ray leave `box` — a box around everything
 // the tree holds — before that?  Then no hit lies beyond the probe and the clipped boxes are valid for the whole walk.
 // A ray that misses the box altogether cannot hit anything: any box set will do.
@@ -382,6 +317,105 @@ PT_D bool probe_covers(const float4* __restrict__ box, const RayF& r, double s, 
     float tn, tf;
     box_interval(box, r, tn, tf);
     return (tn > tf) || (tf < (float)((s + extent) * 0.999));  // NaN / inf anywhere: false
+}
+
+// ------------------------------------------------------------------ kd walk
+// One entry per pending far child: the child's 16-byte record itself (it was fetched together with the near child, so a
+// pop costs ONE local-memory round trip instead of index -> node) and the start of its range.  The END of a pending
+// range is not stored: a push happens with the current range [s, e) and leaves [s, tp) current and [tp, e) pending, so
+// the current `e` is always the `s` of the entry on top of the stack (the walk's initial `e` when the stack is empty),
+// and a popped entry's end is the `s` of the entry below it.
+struct KdStack {
+    uint4 node[PT_MAX_KD_STACK];
+    double s[PT_MAX_KD_STACK];
+};
+
+// Iterative form of ray_cast_impl (node.rs:66-203). `leaf(rank, gbase, first, count, s, e)` returns true when the
+// leaf's fold produced a hit inside [s, e) — (rank, gbase) locate the leaf's cull boxes, leaf_cull.cu —; the first
+// leaf that does ends the walk.
+// "while-while" form: every lane first descends to its next leaf (a short loop of split steps), and only then do the
+// lanes of the warp run their leaves together.  With one loop whose body is "a split step OR a whole leaf", a lane that
+// is still descending advances ONE split per leaf any other lane of its warp processes — and a leaf can hold a whole
+// KDMesh walk.
+// `od`: the ray as an ARRAY (origin x, y, z, direction x, y, z) that the split step indexes by the node's axis: one
+// local-memory load per operand (an L1 hit) where selecting among three register pairs costs a branch and six moves
+// per operand, and the ray does not occupy twelve registers for the length of the walk.
+#ifndef PT_KD_RAY_ARRAY
+#define PT_KD_RAY_ARRAY 1
+#endif
+// PRUNE: before the walk enters a child it slab-tests the child's NODE BOX — the union of the occupied boxes of every
+// leaf below it (leaf_cull.cu) — against the range the child would be walked with; a subtree the ray certainly misses
+// there is not entered (the far child is not even pushed).  Such a subtree holds no leaf that can return a hit, so
+// hits, hit ids and `t` are exactly those of the full walk; what is lost is the reference's WORK below (the counting
+// kernels walk in full) and a kd-plane panic (PT_DEVERR_KD_PLANE) the reference would have hit down there.
+template <bool PRUNE, class LeafFn>
+PT_D bool kd_walk(const PtKdNode* __restrict__ nodes, double extent, const double (&od)[6], double s, const double e0, KdStack& stack,
+                  LeafFn& leaf, uint32_t& err, uint32_t& n_splits, const float4* __restrict__ node_boxes, const RayF& rf) {
+    int sp = 0;
+    double e = e0;
+    const uint4* __restrict__ nodes4 = reinterpret_cast<const uint4*>(nodes);
+    uint4 w = __ldg(nodes4);
+    if (PRUNE && (w.z & 3u) != 3u && !box_may_hit_nonempty(node_boxes, rf, make_rangef(s, e))) return false;
+    for (;;) {
+        bool dead = false;  // this subtree yields nothing: the reference would have panicked in it, or (PRUNE) the ray misses its box
+        while ((w.z & 3u) != 3u) {
+            const uint32_t axis = w.z & 3u;
+            const double split = __hiloint2double((int)w.y, (int)w.x);
+            ++n_splits;
+            const uint32_t front = w.z >> 2, back = w.w;
+            // both children are fetched before the side tests: the loads' latency overlaps the f64 dependency chain
+            // below instead of following it (the node fetch was the top long-scoreboard stall of the walk)
+            const uint4 wf = __ldg(nodes4 + front), wb = __ldg(nodes4 + back);
+            // node.rs:119-127
+            double t_max = s + extent;
+            if (!in_range(s, e, t_max)) t_max = e - kEps;
+            const double t_min = s + kEps;
+#if PT_KD_RAY_ARRAY
+            const double oa = od[axis], da = od[3 + axis];
+#else
+            const double oa = axis == 0 ? od[0] : (axis == 1 ? od[1] : od[2]);
+            const double da = axis == 0 ? od[3] : (axis == 1 ? od[4] : od[5]);
+#endif
+            const double p0 = oa + da * t_min;
+            const double p1 = oa + da * t_max;
+            const bool f0 = (p0 - split) >= 0.0;  // which_side, infinite_plane.rs:27-35
+            const bool f1 = (p1 - split) >= 0.0;
+            if (f0 != f1) {
+                const double tp = (split - oa) / da;  // ray_hit_axis_aligned_plane, node.rs:90-110
+                if (!in_range(s, e, tp)) {
+                    err |= PT_DEVERR_KD_PLANE;  // .expect("bug: ray should definitely hit infinite plane")
+                    dead = true;
+                    break;
+                }
+                // near child on [s, tp); if it misses, far child on [tp, e). node.rs:150-166
+                const uint4 wfar = f0 ? wb : wf;
+                // (a far LEAF is pushed as it is: its fold starts with the same test of the same box)
+                if (!PRUNE || (wfar.z & 3u) == 3u || box_may_hit_nonempty(node_boxes + 2 * (size_t)(f0 ? back : front), rf, make_rangef(tp, e))) {
+                    stack.node[sp] = wfar;
+                    stack.s[sp] = tp;
+                    ++sp;
+                } else {
+                    // not pushed: the walk's "current end = start of the entry on top" bookkeeping needs the entry all
+                    // the same when the near side comes back empty — push a marker that pops to nothing
+                    stack.node[sp] = make_uint4(0u, 0u, 3u, 0u);  // an empty leaf
+                    stack.s[sp] = tp;
+                    ++sp;
+                }
+                e = tp;
+            }
+            w = f0 ? wf : wb;  // node.rs:134-137
+            if (PRUNE && (w.z & 3u) != 3u && !box_may_hit_nonempty(node_boxes + 2 * (size_t)(f0 ? front : back), rf, make_rangef(s, e))) {
+                dead = true;
+                break;
+            }
+        }
+        if (!dead && w.w != 0u && leaf(w.x, w.y, w.z >> 2, w.w, s, e)) return true;
+        if (sp == 0) return false;
+        --sp;
+        w = stack.node[sp];
+        s = stack.s[sp];
+        e = sp ? stack.s[sp - 1] : e0;
+    }
 }
 
 // One leaf of a k-d tree: the fold over its candidate list with a shrinking range (ray.rs:50-63 / :87-99), restricted
@@ -549,7 +583,7 @@ PT_D bool mesh_fold(const DScene& sc, uint32_t tri_first, uint32_t tri_count, V3
 // triangle (mesh.rs:157-167) or the walk of the mesh's own k-d tree on a clone of the range (node.rs:33-51).
 // `world_exit`: upper bound of the ray parameter at which the ray leaves the instance's box (KDMesh only: decides
 // whether the KDMesh walk may use the clipped triangle boxes, see probe_covers).
-template <bool ANY>
+template <bool ANY, bool PRUNE>
 PT_D bool mesh_kinds_t(const DScene& sc, uint32_t prim, const PtMesh* mesh, V3 o, V3 d, double s, double e, double& t, uint32_t& sub,
                        KdStack& blas_stack, uint32_t& err, WorkCounters& wc, float world_exit) {
     const uint32_t tri_first = __ldg(&mesh->tri_first);
@@ -568,7 +602,9 @@ PT_D bool mesh_kinds_t(const DScene& sc, uint32_t prim, const PtMesh* mesh, V3 o
     const uint32_t set = world_exit < (float)((s + extent) * 0.999) ? 0u : sc.bl_cull.set_stride;
     BlasLeaf<ANY> leaf{sc.bl_cull, set, sc.blas_items + item_first, sc.tri_pos + tri_first, o, d, make_rayf(o, d), 0.0, 0, 0, 0, 0, 0};
     const double od[6] = {o.x, o.y, o.z, d.x, d.y, d.z};
-    const bool hit = kd_walk(sc.blas_nodes + __ldg(&mesh->node_first), extent, od, s, e, blas_stack, leaf, err, wc.kd_splits);
+    const uint32_t node_first = __ldg(&mesh->node_first);
+    const bool hit = kd_walk<PRUNE>(sc.blas_nodes + node_first, extent, od, s, e, blas_stack, leaf, err, wc.kd_splits,
+                                    sc.bl_cull.node + set + 2 * (size_t)node_first, leaf.rf);
     wc.triangle_tests += leaf.n_tests;
     wc.x_box += leaf.x_box;
     wc.x_tri += leaf.x_tri;
@@ -577,7 +613,7 @@ PT_D bool mesh_kinds_t(const DScene& sc, uint32_t prim, const PtMesh* mesh, V3 o
 }
 
 // Primitive::ray_hit in object space (primitive.rs:55-61), t + sub id only.
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool PRUNE>
 PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V3 d, double s, double e, double& t,
                       uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc, float world_exit) {
     sub = 0;
@@ -591,12 +627,12 @@ PT_D bool primitive_t(const DScene& sc, uint32_t prim, uint32_t mesh_id, V3 o, V
     }
     const PtMesh* mesh = sc.meshes + mesh_id;
     if (prim == PT_PRIM_TRIANGLE) { ++wc.x_tri; return triangle_t(sc.tri_pos + __ldg(&mesh->tri_first), o, d, s, e, t, nullptr); }
-    return mesh_kinds_t<ANY>(sc, prim, mesh, o, d, s, e, t, sub, blas_stack, err, wc, world_exit);
+    return mesh_kinds_t<ANY, PRUNE>(sc, prim, mesh, o, d, s, e, t, sub, blas_stack, err, wc, world_exit);
 }
 
 // FlatSceneNode::ray_cast of instance `inst` (flat_scene.rs:71-99): the ray in object space, direction NOT renormalised
 // (flat_scene.rs:75, ray.rs:130-135), then the primitive's own test over [s, e).  `pm` = (prim, mesh) of the record.
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool PRUNE>
 PT_D bool instance_t(const DScene& sc, uint32_t inst, uint2 pm, V3 o, V3 d, const RayF& rf, double s, double e, double& t,
                      uint32_t& sub, KdStack& blas_stack, uint32_t& err, WorkCounters& wc) {
     const PtInstance* rec = sc.instances + inst;
@@ -610,11 +646,11 @@ PT_D bool instance_t(const DScene& sc, uint32_t inst, uint2 pm, V3 o, V3 d, cons
     }
     ++wc.x_inst;
     wc.x_prim_flops += prim_flop_count(pm.x);
-    return primitive_t<ANY, COUNT>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc, world_exit);
+    return primitive_t<ANY, COUNT, PRUNE>(sc, pm.x, pm.y, lo, ld, s, e, t, sub, blas_stack, err, wc, world_exit);
 }
 
 // leaf of the scene tree: RayCast for [FlatSceneNode] sharing one shrinking range (ray.rs:87-99)
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool PRUNE>
 struct TlasLeaf {
     const DScene& sc;
     uint32_t set;
@@ -634,7 +670,7 @@ struct TlasLeaf {
         const uint2 pm = __ldg(reinterpret_cast<const uint2*>(&sc.instances[inst].prim));
         double t;
         uint32_t sub;
-        if (!instance_t<ANY, COUNT>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) return false;
+        if (!instance_t<ANY, COUNT, PRUNE>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) return false;
         e = t;  // flat_scene.rs:92
         hit.t = t;
         hit.inst = inst;
@@ -658,14 +694,15 @@ struct TlasLeaf {
 };
 
 // scene.root.ray_cast(ray, [EPSILON, inf)) — ray.rs:140-141, material.rs:174-179
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool PRUNE>
 PT_D bool scene_cast(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& tlas_stack, KdStack& blas_stack, uint32_t& err,
                      WorkCounters& wc) {
     const RayF rf = make_rayf(o, d);
     const uint32_t set = probe_covers(sc.tl_root, rf, kEps, sc.tlas_extent) ? 0u : sc.tl_cull.set_stride;
-    TlasLeaf<ANY, COUNT> leaf{sc, set, o, d, rf, blas_stack, hit, err, wc, 0};
+    TlasLeaf<ANY, COUNT, PRUNE> leaf{sc, set, o, d, rf, blas_stack, hit, err, wc, 0};
     const double od[6] = {o.x, o.y, o.z, d.x, d.y, d.z};
-    return kd_walk(sc.tlas_nodes, sc.tlas_extent, od, kEps, (double)INFINITY, tlas_stack, leaf, err, wc.kd_splits);
+    return kd_walk<PRUNE>(sc.tlas_nodes, sc.tlas_extent, od, kEps, (double)INFINITY, tlas_stack, leaf, err, wc.kd_splits,
+                          sc.tl_cull.node + set, rf);
 }
 
 // PT_RENDER_LINEAR_TLAS: the scene WITHOUT its k-d tree — FlatScene as the root, i.e. `[FlatSceneNode]::ray_cast`
@@ -687,7 +724,7 @@ PT_D bool scene_cast_linear(const DScene& sc, V3 o, V3 d, Hit& hit, KdStack& bla
         }
         double t;
         uint32_t sub;
-        if (instance_t<ANY, COUNT>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) {
+        if (instance_t<ANY, COUNT, false>(sc, inst, pm, o, d, rf, s, e, t, sub, blas_stack, err, wc)) {
             e = t;
             hit.t = t; hit.inst = inst; hit.sub = sub;
             found = true;

@@ -410,9 +410,11 @@ def test_graphics_castle(gpu_ready, kd_depth):
            (ref.stats.rays_primary, ref.stats.rays_shadow, ref.stats.rays_reflect, ref.stats.rays_refract)
 
 
-# configs[4] at full size holds one ray on which the reference's kd walk panics (see tests/test_oracle_kats.py): the
-# device fails with the reference's panic text and says where; with PT_RENDER_TOLERATE_KD_PLANE the frame is finished,
-# the event stays visible in the stats, and every other sample is the oracle's
+# configs[4] at full size holds one ray on which the reference's kd walk panics (see tests/test_oracle_kats.py).  With
+# PT_RENDER_EXACT_WALK — the device walks every subtree the reference walks — the call fails with the reference's panic
+# text and says where; with PT_RENDER_TOLERATE_KD_PLANE on top the frame is finished, the event stays visible in the
+# stats, and every other sample is the oracle's.  The default walk skips subtrees the ray cannot hit anything in: it
+# either reports the same event or never walks the subtree that holds it — and renders the same pixels either way.
 @pytest.mark.skipif(not has_reference_assets(), reason="reference assets not synced")
 def test_castle_kd_plane_panic_device(gpu_ready):
     from portrayer_b200 import _ffi
@@ -423,14 +425,43 @@ def test_castle_kd_plane_panic_device(gpu_ready):
     x, y = CASTLE_PANIC_PIXEL
     kw = dict(samples=64, rng="hash", seed=1, size=(w, h), slice_=(x - 1, y, x, y))
     with pytest.raises(pt.PortrayerError) as err:
-        parity.render_gpu(scene, **kw)
+        parity.render_gpu(scene, flags=_ffi.PT_RENDER_EXACT_WALK, **kw)
     assert err.value.code == _ffi.PT_ERR_KD_PLANE_MISS
     assert "bug: ray should definitely hit infinite plane" in str(err.value) and f"pixel ({x}, {y}) sample 57" in str(err.value)
-    img, stats = parity.render_gpu(scene, flags=_ffi.PT_RENDER_TOLERATE_KD_PLANE, **kw)
+    img, stats = parity.render_gpu(scene, flags=_ffi.PT_RENDER_TOLERATE_KD_PLANE | _ffi.PT_RENDER_EXACT_WALK, **kw)
     assert stats.device_error_bits == _ffi.PT_DEVERR_KD_PLANE and stats.err_bit == _ffi.PT_DEVERR_KD_PLANE
     assert (stats.err_pixel % w, stats.err_pixel // w, stats.err_sample) == (x, y, 57)
     ref = parity.render_oracle(scene, samples=64, rng="hash", seed=1, size=(w, h), slice_=(x - 1, y, x - 1, y))
     assert ref.rc == 0 and np.array_equal(img.buffer[y, x - 1], ref.rgb[y, x - 1])
+    # the default (pruning) walk: same pixels; the event, if the walk still meets it, is the same one
+    fast, fstats = parity.render_gpu(scene, flags=_ffi.PT_RENDER_TOLERATE_KD_PLANE, **kw)
+    assert np.array_equal(fast.buffer[y, x - 1:x + 1], img.buffer[y, x - 1:x + 1])
+    assert np.array_equal(fast.hit_id[y, x - 1:x + 1], img.hit_id[y, x - 1:x + 1]) and np.array_equal(fast.hit_t[y, x - 1:x + 1], img.hit_t[y, x - 1:x + 1])
+    assert fstats.device_error_bits in (0, _ffi.PT_DEVERR_KD_PLANE)
+    print("default walk met the kd-plane event:", bool(fstats.device_error_bits))
+
+
+# The default walk prunes subtrees (PT_RENDER_EXACT_WALK unset) and is what every other test of this file runs; here the
+# exact walk — every subtree the reference walks — is held against the oracle and against the pruning walk: identical
+# pictures, hit ids, hit parameters and ray counts.
+@pytest.mark.parametrize("name,samples,rng,scale", [
+    ("nonhier", 1, "fixed", 1), ("primitives", 2, "hash", 1), ("big-scene", 1, "hash", 4), ("glossy-reflection", 2, "hash", 2),
+    ("graphics-castle", 1, "hash", 6), ("macho-cows", 1, "fixed", 2), ("kat-mesh-equivalence-kdmesh", 1, "fixed", 1)])
+def test_exact_walk_and_pruning_walk_agree(gpu_ready, name, samples, rng, scale):
+    from portrayer_b200 import _ffi
+
+    scene = pt.Scene.example(name)
+    size = (max(scene.width // scale, 16), max(scene.height // scale, 16))
+    exact, st_e = parity.render_gpu(scene, samples=samples, rng=rng, size=size, flags=_ffi.PT_RENDER_EXACT_WALK)
+    fast, st_f = parity.render_gpu(scene, samples=samples, rng=rng, size=size)
+    ref = parity.render_oracle(scene, samples=samples, rng=rng, size=size)
+    rep = parity.compare(exact, ref, name + " exact walk")
+    parity.assert_parity(rep)
+    assert rep["hit_t_bit_identical"], rep
+    assert np.array_equal(exact.buffer, fast.buffer)
+    assert np.array_equal(exact.hit_id, fast.hit_id) and np.array_equal(exact.hit_t, fast.hit_t)
+    assert (st_e.rays_primary, st_e.rays_shadow, st_e.rays_reflect, st_e.rays_refract) == \
+           (st_f.rays_primary, st_f.rays_shadow, st_f.rays_reflect, st_f.rays_refract)
 
 
 # SURVEY 8 row a20, PT_RENDER_LINEAR_TLAS: the scene WITHOUT its k-d tree — `[FlatSceneNode]::ray_cast`
