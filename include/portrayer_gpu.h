@@ -372,6 +372,35 @@ uint64_t pt_abi_sizeof(int which);
  * runs a register-resident microbenchmark for about `milliseconds` and returns TFLOP/s in *tflops_out. */
 int pt_measure_fp64_rate(double milliseconds, double* tflops_out);
 
+/* ---- texture ingest: what follows the file decode in RgbImageBuffer::open, src/texture.rs:96-102 —
+ * image::open(path)?.to_rgb() — on the device.  `pixels` is the decoder's output as it is (host memory, row-major, no
+ * padding) in one of the DynamicImage layouts of image 0.21; the library copies it to the device, converts it to RGB8
+ * there (to_rgb: gray replicated, alpha dropped, BGR swapped) and keeps the texels resident under `key` (non-zero; the
+ * PtTexture.key of the scenes that use it).  A scene blob whose textures are all resident may then be uploaded
+ * records-only (pt_scene_upload with bytes = header.off_texels).  In a device group every member gets a copy. */
+#define PT_PIXELS_LUMA8 1u
+#define PT_PIXELS_LUMAA8 2u
+#define PT_PIXELS_RGB8 3u
+#define PT_PIXELS_RGBA8 4u
+#define PT_PIXELS_BGR8 5u
+#define PT_PIXELS_BGRA8 6u
+int pt_texture_ingest(const void* pixels, uint32_t width, uint32_t height, uint32_t layout, uint64_t key);
+/* the resident texels of `key` back on the host (width * height * 3 bytes), e.g. to hand the same bytes to the oracle */
+int pt_texture_read(uint64_t key, uint8_t* rgb_out, uint64_t capacity, uint32_t* width_out, uint32_t* height_out);
+
+/* ---- PNG encode: Image::save, src/render.rs:200-208 (image::ImageBuffer::save -> 8-bit RGB PNG), on
+ * the device: filter-0 scanlines in stored deflate blocks, Adler-32 and CRC-32 computed in parallel, IHDR / IDAT / IEND
+ * assembled in HBM — the finished FILE crosses PCIe once.  Any PNG decoder returns exactly the rendered pixels; the
+ * file's bytes are not the `image` crate's (that deflates with compression). */
+uint64_t pt_png_size(uint32_t width, uint32_t height);   /* bytes of the file for an image of this size */
+/* device image (row-major RGB8, width * height * 3 bytes) -> device file (pt_png_size bytes); enqueued on `stream`
+ * (NULL: the library's stream, and the call waits for it) */
+int pt_png_encode_device(const uint8_t* d_rgb, uint32_t width, uint32_t height, uint8_t* d_png_out, void* stream);
+/* host image -> host file: H2D, encode, D2H (what Image::save calls when the pixels are in host memory) */
+int pt_png_encode(const uint8_t* rgb, uint32_t width, uint32_t height, uint8_t* png_out, uint64_t capacity, uint64_t* png_bytes_out);
+/* the picture the frame's last render left in HBM, as a PNG file in host memory (row-major frames: world <= 1) */
+int pt_frame_encode_png(PtFrame* frame, uint8_t* png_out, uint64_t capacity, uint64_t* png_bytes_out);
+
 /* ---- scene (replaces nothing in the reference: it is the glue's output) ---- */
 /* bytes needed to pack desc; pack it. Pure host code, works without a GPU. */
 uint64_t pt_scene_blob_size(const PtSceneDesc* desc);

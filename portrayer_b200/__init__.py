@@ -8,9 +8,10 @@ Only what the hot path needs lives here:
 """
 from ._ffi import (PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS, PT_RNG_FIXED, PT_RNG_HASH, PortrayerError, PtCamera, PtRenderParams,  # noqa: F401
                    PtStats)
-from .render import DeviceScene, Frame, Image, init_devices, make_params, samples_from_env  # noqa: F401
+from .render import (DeviceScene, Frame, Image, init_devices, make_params, png_encode, samples_from_env,  # noqa: F401
+                     texture_ingest, texture_read)
 from .scene import Scene, example_names  # noqa: F401
 
-__all__ = ["Scene", "example_names", "Image", "DeviceScene", "Frame", "make_params", "samples_from_env", "init_devices", "PtStats",
+__all__ = ["Scene", "example_names", "Image", "DeviceScene", "Frame", "make_params", "samples_from_env", "init_devices", "png_encode", "texture_ingest", "texture_read", "PtStats",
            "PtCamera", "PtRenderParams", "PortrayerError", "PT_RNG_FIXED", "PT_RNG_HASH", "PT_RENDER_COUNTERS",
            "PT_RENDER_LINEAR_TLAS"]

@@ -55,6 +55,7 @@ PT_RENDER_COUNTERS, PT_RENDER_LINEAR_TLAS, PT_RENDER_KERNEL_TIMES = 1, 2, 4
 PT_RENDER_ROW_MAJOR, PT_RENDER_NO_GRAPH = 8, 16
 PT_RENDER_TOLERATE_KD_PLANE = 32
 PT_RENDER_EXACT_WALK = 64
+PT_PIXELS_LUMA8, PT_PIXELS_LUMAA8, PT_PIXELS_RGB8, PT_PIXELS_RGBA8, PT_PIXELS_BGR8, PT_PIXELS_BGRA8 = 1, 2, 3, 4, 5, 6
 PT_DEVERR_NORMALMAP, PT_DEVERR_TEXTURE, PT_DEVERR_KD_PLANE, PT_DEVERR_TIR, PT_DEVERR_OVERFLOW = 1, 2, 4, 8, 16
 PT_EPSILON = 0.00001
 PT_MAX_RECURSION_DEPTH = 10
@@ -149,6 +150,12 @@ TEXTURE_LOADER_FN = C.CFUNCTYPE(None, C.c_char_p)
 GPU_SYMBOLS = {
     "pt_init": (C.c_int, [C.c_int]),
     "pt_init_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "pt_texture_ingest": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]),
+    "pt_texture_read": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "pt_png_size": (C.c_uint64, [C.c_uint32, C.c_uint32]),
+    "pt_png_encode_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "pt_png_encode": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "pt_frame_encode_png": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pt_device_group_size": (C.c_int, []),
     "pt_shutdown": (None, []),
     "pt_last_error": (C.c_char_p, []),

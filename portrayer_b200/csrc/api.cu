@@ -1957,6 +1957,137 @@ int pt_render(PtScene* scene, const PtCamera* camera, const PtRenderParams* para
     return rc != PT_OK ? rc : rc2;
 }
 
+// =================================================================== texture ingest / PNG encode (image_io.cu)
+int pt_texture_ingest(const void* pixels, uint32_t width, uint32_t height, uint32_t layout, uint64_t key) {
+    if (!pixels || width == 0 || height == 0 || key == 0) return fail(PT_ERR_INVALID, "null pixels, empty image or zero key");
+    uint32_t channels = 0, r_at = 0, g_at = 0, b_at = 0;
+    switch (layout) {
+        case PT_PIXELS_LUMA8: channels = 1; break;
+        case PT_PIXELS_LUMAA8: channels = 2; break;
+        case PT_PIXELS_RGB8: channels = 3; g_at = 1; b_at = 2; break;
+        case PT_PIXELS_RGBA8: channels = 4; g_at = 1; b_at = 2; break;
+        case PT_PIXELS_BGR8: channels = 3; r_at = 2; g_at = 1; break;
+        case PT_PIXELS_BGRA8: channels = 4; r_at = 2; g_at = 1; break;
+        default: return fail(PT_ERR_INVALID, "unknown pixel layout %u", layout);
+    }
+    Lock lock(g_mu);
+    int rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    const uint64_t n = (uint64_t)width * height, bytes = n * 3;
+    uint8_t* d_primary = nullptr;
+    for (int i = 0; i < g_group_size; ++i) {
+        CtxScope member(&g_ctxs[i]);
+        auto it = g_textures.find(key);
+        if (it != g_textures.end()) {
+            if (it->second.width == width && it->second.height == height) { if (i == 0) d_primary = it->second.d_texels; continue; }  // already resident
+            if (it->second.refs) return fail(PT_ERR_INVALID, "texture key %llx is in use with another size", (unsigned long long)key);
+            g_dev.release(it->second.d_texels);
+            g_texture_bytes -= it->second.bytes;
+            g_textures.erase(it);
+        }
+        evict_textures(bytes);
+        cudaError_t e;
+        uint8_t* d = static_cast<uint8_t*>(g_dev.alloc(bytes, &e));
+        if (!d) return fail(PT_ERR_CUDA, "texture allocation failed: %s", cudaGetErrorString(e));
+        if (i == 0 || !d_primary) {
+            uint8_t* d_src = static_cast<uint8_t*>(g_dev.alloc(n * channels, &e));
+            if (!d_src) { g_dev.release(d); return fail(PT_ERR_CUDA, "texture staging allocation failed: %s", cudaGetErrorString(e)); }
+            e = cudaMemcpyAsync(d_src, pixels, n * channels, cudaMemcpyHostToDevice, g_stream);
+            if (e == cudaSuccess) e = ptd::launch_to_rgb(d_src, n, channels, r_at, g_at, b_at, d, g_stream);
+            g_dev.release(d_src);  // stream-ordered reuse
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);  // the caller may free `pixels`; the group's copies read d
+            if (e != cudaSuccess) { g_dev.release(d); return fail(PT_ERR_CUDA, "texture ingest failed: %s", cudaGetErrorString(e)); }
+            if (i == 0) d_primary = d;
+        } else {  // device group: the converted texels from the primary, device to device
+            e = cudaMemcpyAsync(d, d_primary, bytes, cudaMemcpyDefault, g_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+            if (e != cudaSuccess) { g_dev.release(d); return fail(PT_ERR_CUDA, "texture replication failed: %s", cudaGetErrorString(e)); }
+        }
+        ResidentTexture r;
+        r.d_texels = d; r.bytes = bytes; r.width = width; r.height = height; r.refs = 0; r.last_use = ++g_texture_tick;
+        g_textures.emplace(key, r);
+        g_texture_bytes += bytes;
+    }
+    return PT_OK;
+}
+
+int pt_texture_read(uint64_t key, uint8_t* rgb_out, uint64_t capacity, uint32_t* width_out, uint32_t* height_out) {
+    Lock lock(g_mu);
+    int rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    CtxScope scope(&g_ctxs[0]);
+    auto it = g_textures.find(key);
+    if (it == g_textures.end()) return fail(PT_ERR_INVALID, "texture key %llx is not resident", (unsigned long long)key);
+    if (width_out) *width_out = it->second.width;
+    if (height_out) *height_out = it->second.height;
+    if (!rgb_out) return PT_OK;
+    if (capacity < it->second.bytes) return fail(PT_ERR_INVALID, "buffer too small: %llu bytes needed", (unsigned long long)it->second.bytes);
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, it->second.d_texels, it->second.bytes, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return PT_OK;
+}
+
+uint64_t pt_png_size(uint32_t width, uint32_t height) { return (width && height) ? ptd::png_file_bytes(width, height) : 0; }
+
+int pt_png_encode_device(const uint8_t* d_rgb, uint32_t width, uint32_t height, uint8_t* d_png_out, void* stream) {
+    if (!d_rgb || !d_png_out || width == 0 || height == 0) return fail(PT_ERR_INVALID, "null argument or empty image");
+    Lock lock(g_mu);
+    int rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_stream;
+    cudaError_t e;
+    void* scratch = g_dev.alloc(ptd::png_scratch_bytes(width, height), &e);
+    if (!scratch) return fail(PT_ERR_CUDA, "PNG scratch allocation failed: %s", cudaGetErrorString(e));
+    e = ptd::launch_png_encode(d_rgb, width, height, d_png_out, scratch, st);
+    if (e == cudaSuccess && (!stream || st != g_stream)) e = cudaStreamSynchronize(st);  // the scratch goes back to the arena, which orders reuse on g_stream only
+    g_dev.release(scratch);
+    if (e == cudaErrorInvalidValue) return fail(PT_ERR_INVALID, "image too large for a single-IDAT PNG");
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "PNG encode failed: %s", cudaGetErrorString(e));
+    return PT_OK;
+}
+
+// device image -> host file through a pinned staging buffer
+static int png_to_host(const uint8_t* d_rgb, uint32_t width, uint32_t height, uint8_t* png_out, uint64_t capacity, uint64_t* png_bytes_out) {
+    const uint64_t bytes = ptd::png_file_bytes(width, height);
+    if (png_bytes_out) *png_bytes_out = bytes;
+    if (!png_out || capacity < bytes) return fail(PT_ERR_INVALID, "PNG buffer too small: %llu bytes needed", (unsigned long long)bytes);
+    cudaError_t e;
+    uint8_t* d_png = static_cast<uint8_t*>(g_dev.alloc(bytes, &e));
+    if (!d_png) return fail(PT_ERR_CUDA, "PNG allocation failed: %s", cudaGetErrorString(e));
+    int rc = pt_png_encode_device(d_rgb, width, height, d_png, g_stream);
+    if (rc == PT_OK) {
+        e = cudaMemcpyAsync(png_out, d_png, bytes, cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+        if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, "PNG download failed: %s", cudaGetErrorString(e));
+    }
+    g_dev.release(d_png);
+    return rc;
+}
+
+int pt_png_encode(const uint8_t* rgb, uint32_t width, uint32_t height, uint8_t* png_out, uint64_t capacity, uint64_t* png_bytes_out) {
+    if (!rgb || width == 0 || height == 0) return fail(PT_ERR_INVALID, "null argument or empty image");
+    Lock lock(g_mu);
+    int rc = ensure_init();
+    if (rc != PT_OK) return rc;
+    const uint64_t n = (uint64_t)width * height * 3;
+    cudaError_t e;
+    uint8_t* d_rgb = static_cast<uint8_t*>(g_dev.alloc(n, &e));
+    if (!d_rgb) return fail(PT_ERR_CUDA, "image allocation failed: %s", cudaGetErrorString(e));
+    e = cudaMemcpyAsync(d_rgb, rgb, n, cudaMemcpyHostToDevice, g_stream);
+    rc = e == cudaSuccess ? png_to_host(d_rgb, width, height, png_out, capacity, png_bytes_out) : fail(PT_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+    g_dev.release(d_rgb);
+    return rc;
+}
+
+int pt_frame_encode_png(PtFrame* frame, uint8_t* png_out, uint64_t capacity, uint64_t* png_bytes_out) {
+    if (!frame) return fail(PT_ERR_INVALID, "null frame");
+    Lock lock(g_mu);
+    CtxScope scope(frame->ctx);
+    if (frame->pending == PtFrame::IN_FLIGHT) return fail(PT_ERR_INVALID, "a render of this frame is in flight");
+    if (!frame->row_major) return fail(PT_ERR_INVALID, "the frame's device image is in compact owned-pixel order (world > 1): encode the gathered image instead");
+    return png_to_host(frame->d_rgb, frame->params.width, frame->params.height, png_out, capacity, png_bytes_out);
+}
+
 // Ray::color(scene, background, 0) for explicit rays (ray.rs:139-148) — what the
 // reference's own mesh_equivalence test evaluates per ray (kdmesh.rs:155-163).
 int pt_trace_rays(PtScene* scene, uint64_t n, const double* origins, const double* dirs, const double* background3,

@@ -57,6 +57,13 @@ void launch_tree_eval(int slot, uint32_t n_paths, cudaStream_t st);
 void launch_resolve(int slot, uint32_t n_slots, cudaStream_t st);
 void launch_export_rays(int slot, uint32_t n_paths, cudaStream_t st);
 
+// image_io.cu: the byte-moving steps either side of the render loop
+cudaError_t launch_to_rgb(const uint8_t* src, uint64_t n_pixels, uint32_t channels, uint32_t r_at, uint32_t g_at, uint32_t b_at, uint8_t* dst,
+                          cudaStream_t st);
+uint64_t png_file_bytes(uint32_t width, uint32_t height);
+uint64_t png_scratch_bytes(uint32_t width, uint32_t height);
+cudaError_t launch_png_encode(const uint8_t* d_rgb, uint32_t width, uint32_t height, uint8_t* d_png, void* d_scratch, cudaStream_t st);
+
 // graph path: camera -> WHILE(level has rays){extend, shadow, shade} -> tree_eval -> resolve
 cudaError_t build_frame_graph(int slot, uint32_t n_slots, uint32_t samples, uint32_t n_lights_max, uint64_t capacity,
                               int mode, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out, cudaGraphNode_t* camera_node);

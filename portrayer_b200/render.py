@@ -50,6 +50,39 @@ def _background_arg(scene: Scene, width: int, height: int) -> tuple[np.ndarray, 
     return np.ascontiguousarray(scene.background(width, height)), PT_BG_PER_PIXEL
 
 
+def png_encode(rgb: np.ndarray) -> bytes:
+    """Image::save's encode step (src/render.rs:200-208) on the device: [H, W, 3] uint8 -> the bytes of a PNG file"""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w = rgb.shape[:2]
+    buf = np.empty(gpu.pt_png_size(w, h), np.uint8)
+    n = C.c_uint64(0)
+    check(gpu.pt_png_encode(rgb.ctypes.data, w, h, buf.ctypes.data, buf.nbytes, C.byref(n)))
+    return buf[: n.value].tobytes()
+
+
+_LAYOUTS = {1: _ffi.PT_PIXELS_LUMA8, 2: _ffi.PT_PIXELS_LUMAA8, 3: _ffi.PT_PIXELS_RGB8, 4: _ffi.PT_PIXELS_RGBA8}
+
+
+def texture_ingest(pixels: np.ndarray, key: int, bgr: bool = False) -> None:
+    """RgbImageBuffer::open's `.to_rgb()` + upload (src/texture.rs:96-102) on the device: the decoder's output
+    ([H, W] or [H, W, C] uint8, C = 1..4) becomes resident RGB8 texels under ``key``."""
+    pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+    h, w = pixels.shape[:2]
+    c = 1 if pixels.ndim == 2 else pixels.shape[2]
+    layout = _LAYOUTS[c]
+    if bgr:
+        layout = {3: _ffi.PT_PIXELS_BGR8, 4: _ffi.PT_PIXELS_BGRA8}[c]
+    check(gpu.pt_texture_ingest(pixels.ctypes.data, w, h, layout, key))
+
+
+def texture_read(key: int) -> np.ndarray:
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    check(gpu.pt_texture_read(key, None, 0, C.byref(w), C.byref(h)))
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    check(gpu.pt_texture_read(key, out.ctypes.data, out.nbytes, C.byref(w), C.byref(h)))
+    return out
+
+
 def init_devices(ids) -> int:
     """pt_init_devices: make ``ids`` one device group in this process (ids[0] = primary); from then on ``Image.render`` /
     ``DeviceScene.render`` fan their tiles over all members.  Handles created before the call are invalid."""
@@ -193,6 +226,14 @@ class Frame:
                                 hit_t.ctypes.data if hit_t is not None else None, C.byref(stats)))
         return stats
 
+    def encode_png(self) -> bytes:
+        """the picture of the last render as a PNG FILE, assembled on the device (pt_frame_encode_png; world <= 1)"""
+        n = C.c_uint64(0)
+        gpu.pt_frame_encode_png(self._h, None, 0, C.byref(n))  # size query (fails with "too small" and fills n)
+        buf = np.empty(n.value, np.uint8)
+        check(gpu.pt_frame_encode_png(self._h, buf.ctypes.data, buf.nbytes, C.byref(n)))
+        return buf[: n.value].tobytes()
+
     def close(self) -> None:
         if self._h:
             gpu.pt_frame_free(self._h)
@@ -231,9 +272,14 @@ class Image:
         return self.buffer.shape[0]
 
     def save(self, path: str | None = None) -> None:
+        path = path or self.path
+        if str(path).lower().endswith(".png") and os.environ.get("PORTRAYER_PNG", "device") == "device" and gpu.pt_device_count() > 0:
+            with open(path, "wb") as f:  # Image::save, render.rs:200-208: the file is assembled on the device
+                f.write(png_encode(self.buffer))
+            return
         from PIL import Image as PILImage
 
-        PILImage.fromarray(self.buffer).save(path or self.path)
+        PILImage.fromarray(self.buffer).save(path)
 
     def render(self, scene: Scene, samples: int | None = None, rng: str | int = "hash", seed: int = 1, slice_=None,
                want_hit_ids: bool = False, progress=None, flags: int = 0, dscene: DeviceScene | None = None,
