@@ -131,8 +131,10 @@ SceneNode robot_head(const MaterialRef& mat_robot_metal, const MaterialRef& mat_
     });
 }
 
-SceneNode robot() {
-    auto mat_robot_metal = Arc(Material{.diffuse = {0.006449, 0.417885, 0.025384}, .specular = {0.8, 0.8, 0.8}, .shininess = 100.0,
+// `metal`: the robot's diffuse colour — the example source ships green and keeps the other three as commented-out
+// lines (examples/robot-alarm-clock.rs:98-101); upstream published a render of each (render/10_robot-alarm-clock*.png)
+SceneNode robot(Rgb metal) {
+    auto mat_robot_metal = Arc(Material{.diffuse = metal, .specular = {0.8, 0.8, 0.8}, .shininess = 100.0,
                                         .reflectivity = 0.3, .glossy_side_length = 2.0});
     auto mat_connector = plain({0.048247, 0.048247, 0.048247});
     return SceneNode::from(std::vector<NodeRef>{
@@ -143,11 +145,11 @@ SceneNode robot() {
 }
 }  // namespace
 
-PORTRAYER_EXAMPLE(robot_alarm_clock, "robot-alarm-clock") {
+ExampleScene robot_scene(const char* name, Rgb metal) {
     ExampleScene ex;
-    ex.name = "robot-alarm-clock";
+    ex.name = name;
     ex.scene = HierScene{
-        .root = SceneNode::from(std::vector<NodeRef>{room().into(), robot().into()}).into(),
+        .root = SceneNode::from(std::vector<NodeRef>{room().into(), robot(metal).into()}).into(),
         .lights = {Light{.position = {-2.0, 15.0, 5.0}, .color = {0.9, 0.9, 0.9},
                          .area = Parallelogram{.a = {5.0, 0.0, 0.0}, .b = {0.0, 0.0, 5.0}}}},
         .ambient = {0.3, 0.3, 0.3},
@@ -159,3 +161,9 @@ PORTRAYER_EXAMPLE(robot_alarm_clock, "robot-alarm-clock") {
     ex.background = [](Uv uv) { return Rgb{0.529, 0.808, 0.922} * (1.0 - uv.v) + Rgb{0.086, 0.38, 0.745} * uv.v; };
     return ex;
 }
+
+PORTRAYER_EXAMPLE(robot_alarm_clock, "robot-alarm-clock") { return robot_scene("robot-alarm-clock", {0.006449, 0.417885, 0.025384}); }  // green, as shipped
+// the three other published colour variants (not among the reference's 28 example programs: same program, one line changed)
+PORTRAYER_EXAMPLE(robot_alarm_clock_cyan, "robot-alarm-clock-cyan") { return robot_scene("robot-alarm-clock-cyan", {0.211857, 0.772537, 0.8971}); }
+PORTRAYER_EXAMPLE(robot_alarm_clock_dark_blue, "robot-alarm-clock-dark-blue") { return robot_scene("robot-alarm-clock-dark-blue", {0.006512, 0.08022, 0.417885}); }
+PORTRAYER_EXAMPLE(robot_alarm_clock_red, "robot-alarm-clock-red") { return robot_scene("robot-alarm-clock-red", {0.417885, 0.006501, 0.006501}); }

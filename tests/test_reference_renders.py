@@ -16,7 +16,7 @@ from conftest import has_reference_assets
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_renders")
 FACTOR = 7
 TEXTURED = {"normal-mapping", "normal-mapping-left", "normal-mapping-right", "water-glass", "transmission-refraction",
-            "robot-alarm-clock"}
+            "robot-alarm-clock", "robot-alarm-clock-cyan", "robot-alarm-clock-dark-blue", "robot-alarm-clock-red"}
 # (example, samples, max mean-abs-error in LSB, min PSNR dB).  big-scene's random scene needs the re-implemented
 # rand-0.7 StdRng (host/rand07.hpp) to reproduce upstream's object placement: agreement there pins it.
 CASES = [
@@ -40,6 +40,10 @@ CASES = [
     ("transmission-refraction", 4, 0.8, 46.0),
     # area light + glossy metal / table at 2 samples against upstream's 100: noisier than the others by construction
     ("robot-alarm-clock", 2, 1.4, 42.0),
+    # the three other colour variants upstream published (the example's commented-out diffuse lines, :98-100)
+    ("robot-alarm-clock-cyan", 2, 1.45, 42.0),
+    ("robot-alarm-clock-dark-blue", 2, 1.4, 42.0),
+    ("robot-alarm-clock-red", 2, 1.4, 42.0),
 ]
 
 
@@ -74,7 +78,8 @@ GPU_CASES = [
     ("soft-shadows", 0.5, 47.0), ("normal-mapping", 0.7, 45.0), ("normal-mapping-left", 0.7, 45.0), ("normal-mapping-right", 0.7, 45.0),
     ("water-glass", 1.2, 33.0),  # coplanar cap / table patch, see above
     ("big-scene", 0.5, 46.0), ("entering-the-mirror-dimension", 0.5, 46.0), ("transmission-refraction", 0.6, 46.0),
-    ("robot-alarm-clock", 0.8, 44.0),
+    ("robot-alarm-clock", 0.8, 44.0), ("robot-alarm-clock-cyan", 0.85, 44.0), ("robot-alarm-clock-dark-blue", 0.8, 44.0),
+    ("robot-alarm-clock-red", 0.8, 44.0),
 ]
 
 

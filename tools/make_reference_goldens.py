@@ -30,6 +30,13 @@ RENDERS = {
     "entering-the-mirror-dimension.png": "entering-the-mirror-dimension",
     # upstream published four colour variants; the example source as shipped is the green one
     "10_robot-alarm-clock_green.png": "robot-alarm-clock",
+    # ... the other three are the same program with the commented-out diffuse lines (examples/robot-alarm-clock.rs:98-100)
+    "10_robot-alarm-clock.png": "robot-alarm-clock-cyan",
+    "10_robot-alarm-clock_dark_blue.png": "robot-alarm-clock-dark-blue",
+    "10_robot-alarm-clock_red.png": "robot-alarm-clock-red",
+    # (03_antialiasing.png is a hand-made 4x zoom montage of crops, not the output of examples/antialiasing.rs: mean
+    # absolute error 64 LSB against the program's 300x250 render at either of its sample counts — nothing to pin with it;
+    # 05a / 05b need the three assets missing upstream)
     "07_glossy-reflection.png": "glossy-reflection",
     "08_soft-shadows.png": "soft-shadows",
     "09a_kdtree.png": "big-scene",
