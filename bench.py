@@ -447,7 +447,13 @@ class Bench:
         rays_local = sum(st.rays for st in step_stats[0])
         launches_local = sum(st.kernel_launches for sts in step_stats for st in sts)
         r = torch.tensor([float(rays_local), float(launches_local)], dtype=torch.float64, device=self.dev)
+        # per rank: mean step time on ITS device and the rays it traced (what limits strong scaling: the slowest rank's share)
+        mine = torch.tensor([sum(step_ms) / max(len(step_ms), 1), float(rays_local)], dtype=torch.float64, device=self.dev)
+        self.by_rank = [[float(mine[0].item()), float(mine[1].item())]]
         if self.world > 1:
+            every = [torch.zeros_like(mine) for _ in range(self.world)]
+            torch.distributed.all_gather(every, mine)
+            self.by_rank = [[float(x[0].item()), float(x[1].item())] for x in every]
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)  # every step: max over ranks
             torch.distributed.all_reduce(r, op=torch.distributed.ReduceOp.SUM)  # whole-job rays
         return [float(x) for x in t.tolist()], float(r[0].item()), int(r[1].item()), step_stats
@@ -765,6 +771,10 @@ def run_ours(args, rank, world, local_rank):
                                                         "1-element all-reduce" if peer is not None else "NCCL gather + un-tiling on rank 0"),
                    "exchange_verified_against_nccl_gather": exchange_verified,
                    "node_pool_retry_rounds_in_timed_steps": int(overflow_retries),
+                   # strong scaling is limited by the slowest rank: its own device time per step and its share of the rays
+                   "ms_per_step_by_rank": [round(x[0], 3) for x in b.by_rank],
+                   "rays_per_step_by_rank": [int(x[1]) for x in b.by_rank],
+                   "rank_imbalance_max_over_mean": (max(x[0] for x in b.by_rank) / (sum(x[0] for x in b.by_rank) / len(b.by_rank))) if b.by_rank else None,
                    "reference_panics_tolerated": panics},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_fp64": roofline_fp64,
         "roofline_issue": roofline_issue, "executed_work": executed, "cpu_baseline": cpu, "other_configs": other,

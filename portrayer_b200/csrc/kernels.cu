@@ -621,28 +621,55 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(int slot_id) {
     uint32_t* __restrict__ hit_id = fs.hit_id;
     double* __restrict__ hit_t = fs.hit_t;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_slots) return;
+    const bool active = k < n_slots;  // (no early return: the warp's lanes cooperate on the image stores below)
     const uint32_t p0 = k * fp.samples;
     double total[3] = {0.0, 0.0, 0.0};
-    for (uint32_t s = 0; s < fp.samples; ++s) {
-        total[0] = total[0] + pool.cr[p0 + s];
-        total[1] = total[1] + pool.cg[p0 + s];
-        total[2] = total[2] + pool.cb[p0 + s];
+    if (active) {
+        for (uint32_t s = 0; s < fp.samples; ++s) {
+            total[0] = total[0] + pool.cr[p0 + s];
+            total[1] = total[1] + pool.cg[p0 + s];
+            total[2] = total[2] + pool.cb[p0 + s];
+        }
     }
     // compact owned-pixel order (multi-GPU gather), or the pixel's own place in a full row-major image
-    const size_t slot = fs.row_major ? (size_t)__ldg(fp.pixel_index + first_slot + k) : (size_t)first_slot + k;
-    // the exchange step of the multi-GPU path, fused: the pixel also goes to its own place in the collecting rank's
-    // full image (peer memory over NVLink for the other ranks); tiles are disjoint, so no two ranks write one byte
-    uint8_t* __restrict__ image = fs.rgb_image;
-    const size_t pixel = image ? (size_t)__ldg(fp.pixel_index + first_slot + k) : 0;
+    const size_t own_pixel = active ? (size_t)__ldg(fp.pixel_index + first_slot + k) : 0;
+    const size_t slot = fs.row_major ? own_pixel : (size_t)first_slot + k;
+    uint32_t packed = 0;  // r | g << 8 | b << 16
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         double c = total[ch] / (double)fp.samples;
         c = pow(c, 1.0 / PT_GAMMA);
         const uint8_t v = to_u8(clamp01(c));
-        rgb[slot * 3 + ch] = v;
-        if (image) image[pixel * 3 + ch] = v;
+        if (active) rgb[slot * 3 + ch] = v;
+        packed |= (uint32_t)v << (8 * ch);
     }
+    // The exchange step of the multi-GPU path, fused: the pixel also goes to its own place in the collecting device's
+    // full image (peer memory over NVLink for the other members); tiles are disjoint, so no two devices write one byte.
+    // Owned pixels are listed in 8 x 4 micro-tiles (tiles.c): 4 consecutive lanes hold 4 consecutive pixels of a row =
+    // 12 contiguous bytes, written as THREE aligned 32-bit words by three of the lanes.  Byte stores (three per pixel)
+    // cost 34 MB of NVLink traffic for the 3 MB of a 1080p half frame (ncu nvltx__bytes, profiles/r02_peer_stores.txt).
+    uint8_t* __restrict__ image = fs.rgb_image;
+    if (image) {  // uniform over the grid
+        const unsigned full = 0xFFFFFFFFu;
+        const int lane = threadIdx.x & 31, j = lane & 3, lead = lane & ~3;
+        const unsigned long long px = active ? (unsigned long long)own_pixel : ~0ull;
+        const unsigned long long px_lead = __shfl_sync(full, px, lead);
+        const unsigned ok = __ballot_sync(full, active && px == px_lead + (unsigned)j);
+        const uint32_t c0 = __shfl_sync(full, packed, lead), c1 = __shfl_sync(full, packed, lead + 1);
+        const uint32_t c2 = __shfl_sync(full, packed, lead + 2), c3 = __shfl_sync(full, packed, lead + 3);
+        const bool group = ((ok >> lead) & 0xFu) == 0xFu && (((size_t)px_lead * 3 + (size_t)image) & 3u) == 0;
+        if (group) {
+            if (j < 3) {
+                const uint32_t word = j == 0 ? (c0 | (c1 & 0xFFu) << 24) : j == 1 ? ((c1 >> 8) | (c2 & 0xFFFFu) << 16) : ((c2 >> 16) | c3 << 8);
+                *reinterpret_cast<uint32_t*>(image + (size_t)px_lead * 3 + 4 * j) = word;
+            }
+        } else if (active) {
+            image[own_pixel * 3] = (uint8_t)packed;
+            image[own_pixel * 3 + 1] = (uint8_t)(packed >> 8);
+            image[own_pixel * 3 + 2] = (uint8_t)(packed >> 16);
+        }
+    }
+    if (!active) return;
     if (hit_id) {
         hit_id[slot * 2] = pool.inst[p0];
         hit_id[slot * 2 + 1] = pool.sub[p0];
