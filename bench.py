@@ -448,7 +448,8 @@ class Bench:
         launches_local = sum(st.kernel_launches for sts in step_stats for st in sts)
         r = torch.tensor([float(rays_local), float(launches_local)], dtype=torch.float64, device=self.dev)
         # per rank: mean step time on ITS device and the rays it traced (what limits strong scaling: the slowest rank's share)
-        mine = torch.tensor([sum(step_ms) / max(len(step_ms), 1), float(rays_local)], dtype=torch.float64, device=self.dev)
+        own_ms = [sum(float(st.device_ms) for st in sts) for sts in step_stats]  # the rank's own frames (CUDA events), not the step with its completion signal
+        mine = torch.tensor([sum(own_ms) / max(len(own_ms), 1), float(rays_local)], dtype=torch.float64, device=self.dev)
         self.by_rank = [[float(mine[0].item()), float(mine[1].item())]]
         if self.world > 1:
             every = [torch.zeros_like(mine) for _ in range(self.world)]
