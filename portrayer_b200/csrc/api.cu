@@ -795,7 +795,7 @@ int run_levels_stream(int slot, uint32_t n_lights, uint64_t capacity, BatchCtl* 
             timer->end(st);
         }
         timer->begin(2, st);
-        launch_shade(slot, max_items, 0, st);
+        launch_shade(slot, max_items, shade_big_group(n_paths), 0, st);
         timer->end(st);
         *launches += n_lights ? 3 : 2;
         CUDA_TRY(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));

@@ -27,7 +27,21 @@ __constant__ FrameState c_state[kStateSlots];
 
 namespace {
 
-constexpr int kBlock = 128;
+#ifndef PT_BLOCK
+#define PT_BLOCK 128
+#endif
+constexpr int kBlock = PT_BLOCK;
+// Threads per block of the shade kernel = parents whose children are allocated together (block_alloc).  The bigger the
+// group, the longer the runs of same-kind children from neighbouring parents in the next level, and the better that
+// level's warps stay together: graphics-castle 4K x 16 renders in 324 / 304 / 291 ms with groups of 128 / 256 / 512
+// (the traversal kernels' own block size does not matter: 325 ms at 256; profiles/r02_ab_shade_group.txt).  A 512-thread
+// block leaves a small level with too few blocks to fill the machine (configs[1], 0.5 M paths per frame: -4 %), so a
+// frame picks by the size of its batches.
+#ifndef PT_SHADE_BLOCK_BIG
+#define PT_SHADE_BLOCK_BIG 512
+#endif
+constexpr int kShadeBlockSmall = kBlock, kShadeBlockBig = PT_SHADE_BLOCK_BIG;
+constexpr uint64_t kShadeBigPaths = 1ull << 21;  // batches of at least this many paths use the big group
 // minimum resident blocks per SM asked of ptxas (register budget = 65536 / (kBlock * min blocks)); tuned on B200,
 // see DESIGN.md "occupancy"
 #ifndef PT_EXTEND_MIN_BLOCKS
@@ -249,8 +263,9 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
 // launches of levels >= 1.  Grouped per block, a chunk of the next level holds children of ONE kind from neighbouring
 // parents.  (Sorting every level by (direction octant, origin cell) was measured too and lost: DESIGN.md section 10.)
 // Every thread of the block must call it (two barriers).
+template <int BLOCK>
 PT_D void block_alloc(BatchCtl* ctl, bool want0, bool want1, uint32_t& n0, uint32_t& n1) {
-    __shared__ uint32_t s_cnt[2][kBlock / 32];
+    __shared__ uint32_t s_cnt[2][BLOCK / 32];
     __shared__ uint32_t s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m0 = __ballot_sync(0xFFFFFFFFu, want0), m1 = __ballot_sync(0xFFFFFFFFu, want1);
@@ -258,7 +273,7 @@ PT_D void block_alloc(BatchCtl* ctl, bool want0, bool want1, uint32_t& n0, uint3
     __syncthreads();
     uint32_t before0 = 0, before1 = 0, total0 = 0, total1 = 0;
 #pragma unroll
-    for (int w = 0; w < kBlock / 32; ++w) {
+    for (int w = 0; w < BLOCK / 32; ++w) {
         const uint32_t c0 = s_cnt[0][w], c1 = s_cnt[1][w];
         if (w < warp) { before0 += c0; before1 += c1; }
         total0 += c0;
@@ -274,7 +289,8 @@ PT_D void block_alloc(BatchCtl* ctl, bool want0, bool want1, uint32_t& n0, uint3
 
 // `loop`: the conditional handle of the frame graph's WHILE node (0 on the stream path); the last block to
 // finish decides whether another recursion level has rays to trace.
-__global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int slot_id, cudaGraphConditionalHandle loop) {
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : PT_SHADE_MIN_BLOCKS)) shade_kernel(int slot_id, cudaGraphConditionalHandle loop) {
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
     const FrameParams& fp = fs.fp;
@@ -456,7 +472,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) shade_kernel(int 
 
         // children: reflected ray first, then refracted (material.rs:243 before :303)
         uint32_t n0, n1;
-        block_alloc(ctl, want0, want1, n0, n1);
+        block_alloc<BLOCK>(ctl, want0, want1, n0, n1);
         if (want0) {
             if (n0 < pool.capacity) {
                 pool.ox[n0] = hit_point.x; pool.oy[n0] = hit_point.y; pool.oz[n0] = hit_point.z;
@@ -848,14 +864,15 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* __restrict__ sin
     if (s == 12345.678) sink[0] = s;  // never true: keeps the chains alive
 }
 
-int g_grid_extend[3] = {0, 0, 0}, g_grid_shadow[3] = {0, 0, 0}, g_grid_shade = 0;  // [kWalkExact | kWalkCount | kWalkPrune]
+int g_grid_extend[3] = {0, 0, 0}, g_grid_shadow[3] = {0, 0, 0};  // [kWalkExact | kWalkCount | kWalkPrune]
+int g_grid_shade[2] = {0, 0};                                     // [small group | big group]
 
 template <class K>
-int persistent_grid(K kernel) {
+int persistent_grid(K kernel, int block = kBlock) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
@@ -870,12 +887,13 @@ void kernels_init() {
     g_grid_shadow[1] = persistent_grid(shadow_kernel<true>);
     g_grid_extend[2] = persistent_grid(extend_kernel<false, false, true>);
     g_grid_shadow[2] = persistent_grid(shadow_kernel<false, false, true>);
-    g_grid_shade = persistent_grid(shade_kernel);
+    g_grid_shade[0] = persistent_grid(shade_kernel<kShadeBlockSmall>, kShadeBlockSmall);
+    g_grid_shade[1] = persistent_grid(shade_kernel<kShadeBlockBig>, kShadeBlockBig);
 }
 
 static inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
-static inline int capped(int grid, uint64_t max_items) {
-    const uint64_t need = blocks_for(max_items ? max_items : 1);
+static inline int capped(int grid, uint64_t max_items, int block = kBlock) {
+    const uint64_t need = ((max_items ? max_items : 1) + block - 1) / block;
     return (uint64_t)grid > need ? (int)need : grid;
 }
 
@@ -935,8 +953,10 @@ void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, int mode, bo
     else if (mode == kWalkPrune) shadow_kernel<false, false, true><<<grid, kBlock, 0, st>>>(slot);
     else shadow_kernel<false><<<grid, kBlock, 0, st>>>(slot);
 }
-void launch_shade(int slot, uint64_t max_items, cudaGraphConditionalHandle loop, cudaStream_t st) {
-    shade_kernel<<<capped(g_grid_shade, max_items), kBlock, 0, st>>>(slot, loop);
+bool shade_big_group(uint64_t batch_paths) { return batch_paths >= kShadeBigPaths; }
+void launch_shade(int slot, uint64_t max_items, bool big, cudaGraphConditionalHandle loop, cudaStream_t st) {
+    if (big) shade_kernel<kShadeBlockBig><<<capped(g_grid_shade[1], max_items, kShadeBlockBig), kShadeBlockBig, 0, st>>>(slot, loop);
+    else shade_kernel<kShadeBlockSmall><<<capped(g_grid_shade[0], max_items, kShadeBlockSmall), kShadeBlockSmall, 0, st>>>(slot, loop);
 }
 void launch_tree_eval(int slot, uint32_t n_paths, cudaStream_t st) {
     tree_eval_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(slot);
@@ -996,9 +1016,11 @@ cudaError_t build_frame_graph(int slot, uint32_t n_slots, uint32_t samples, uint
         e = cudaGraphAddKernelNode(&n_shd, body, &n_ext, 1, &k);
         if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
         void* args2[2] = {&slot, &handle};
-        k.func = (void*)shade_kernel;
+        const bool big = shade_big_group(n_paths);
+        k.func = big ? (void*)shade_kernel<kShadeBlockBig> : (void*)shade_kernel<kShadeBlockSmall>;
         k.kernelParams = args2;
-        k.gridDim = dim3(capped(g_grid_shade, capacity));
+        k.blockDim = dim3(big ? kShadeBlockBig : kShadeBlockSmall);
+        k.gridDim = dim3(big ? capped(g_grid_shade[1], capacity, kShadeBlockBig) : capped(g_grid_shade[0], capacity, kShadeBlockSmall));
         e = cudaGraphAddKernelNode(&n_sha, body, &n_shd, 1, &k);
         if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
     }

@@ -52,7 +52,9 @@ enum { kWalkExact = 0, kWalkCount = 1, kWalkPrune = 2 };
 // linear: the PT_RENDER_LINEAR_TLAS cross-check kernels (always counting)
 void launch_extend(int slot, uint64_t max_items, int mode, bool linear, cudaStream_t st);
 void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, int mode, bool linear, cudaStream_t st);
-void launch_shade(int slot, uint64_t max_items, cudaGraphConditionalHandle loop, cudaStream_t st);
+// big: allocate the children of 512 parents together instead of 128 (frames whose batches hold >= 2 Mi paths: shade_big_group)
+bool shade_big_group(uint64_t batch_paths);
+void launch_shade(int slot, uint64_t max_items, bool big, cudaGraphConditionalHandle loop, cudaStream_t st);
 void launch_tree_eval(int slot, uint32_t n_paths, cudaStream_t st);
 void launch_resolve(int slot, uint32_t n_slots, cudaStream_t st);
 void launch_export_rays(int slot, uint32_t n_paths, cudaStream_t st);
