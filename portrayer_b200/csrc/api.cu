@@ -801,7 +801,7 @@ int run_levels_stream(int slot, uint32_t n_lights, uint64_t capacity, BatchCtl* 
         CUDA_TRY(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         if (h_ctl->error_bits & PT_DEVERR_OVERFLOW) break;
-        if (h_ctl->level_start[level + 2] <= h_ctl->level_start[level + 1]) break;  // next level is empty
+        if (h_ctl->level_start[level + 2] <= h_ctl->level_start[level + 1] && h_ctl->level_hi[level + 1] <= h_ctl->level_hi[level]) break;  // next level is empty
     }
     CUDA_TRY(cudaGetLastError());
     return PT_OK;
@@ -832,7 +832,7 @@ void accumulate_stats(PtStats* stats, const BatchCtl& c, uint32_t n_paths) {
     }
     stats->shaded_hits += c.shaded_hits;
     stats->texel_lookups += c.texel_lookups;
-    stats->nodes_total += c.pool_count;
+    stats->nodes_total += (uint64_t)c.pool_count + c.hi_count;
     stats->device_error_bits |= c.error_bits & ~PT_DEVERR_OVERFLOW;
     if (c.err_info[0] && !stats->err_bit) {
         stats->err_bit = c.err_info[0];
@@ -842,7 +842,7 @@ void accumulate_stats(PtStats* stats, const BatchCtl& c, uint32_t n_paths) {
         stats->err_where = c.err_info[4];
     }
     for (uint32_t d = 0; d + 1 < 16; ++d)
-        if (c.level_start[d + 1] > c.level_start[d] && d > stats->max_level) stats->max_level = d;
+        if ((c.level_start[d + 1] > c.level_start[d] || (d > 0 && c.level_hi[d] > c.level_hi[d - 1])) && d > stats->max_level) stats->max_level = d;
 }
 
 bool graphs_enabled() {
@@ -1053,7 +1053,7 @@ void split_range(const PtFrame* f, uint32_t first, uint32_t n, std::vector<std::
 // is a LOWER bound of the shortfall (the refused children's own children never asked): the batch is cut by twice that,
 // rounded up to a power of two, and at least halved (a tighter 1.25 x was measured: more retry rounds, slower overall).
 uint32_t overflow_divisor(const PtFrame* f, const BatchCtl& c) {
-    const double want = 2.0 * (double)c.pool_count / (double)std::max<uint32_t>(f->pool.capacity, 1);
+    const double want = 2.0 * ((double)c.pool_count + (double)c.hi_count) / (double)std::max<uint32_t>(f->pool.capacity, 1);
     uint32_t div = 2;
     while ((double)div < want && div < (1u << 16)) div *= 2;
     return div;

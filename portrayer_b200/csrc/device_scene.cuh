@@ -75,7 +75,7 @@ constexpr uint8_t kModeReflect = 1;     // colour = local + refl * C(child0)    
 constexpr uint8_t kModeDielectric = 2;  // colour = local + refl * (F*C(child0) + (1-F)*C(child1))
 
 // One batch's ray tree, structure-of-arrays, `capacity` nodes.  Level d of the
-// recursion occupies the contiguous index range [level_start[d], level_start[d+1]);
+// recursion occupies the index range [level_start[d], level_start[d+1]) plus a run at the top of the pool (BatchCtl);
 // level 0 is the batch's primary rays, node index == path index.
 struct NodePool {
     double *ox, *oy, *oz, *dx, *dy, *dz;  // ray (world space; direction not necessarily unit, material.rs:238-242)
@@ -110,6 +110,14 @@ struct BatchCtl {
     // [0] PT_DEVERR_* bit (0 = none), [1] global pixel, [2] sample, [3] path id, [4] kernel (0 extend, 1 shadow, 2 shade)
     // | level << 8 | light << 16, [5] reserved
     uint32_t err_info[6];
+    // The pool is filled from BOTH ends: primary rays and reflected children ascend from 0 (pool_count), refracted
+    // children descend from `capacity` (hi_count of them so far).  A level is then two runs — all of its reflected rays,
+    // all of its refracted rays — instead of an interleaving in units of the shade kernel's blocks:
+    //   lo run  [level_start[d], level_start[d + 1])
+    //   hi run  [capacity - level_hi[d], capacity - level_hi[d - 1])      (level_hi[-1] = 0; level 0 has none)
+    uint32_t hi_count;
+    uint32_t level_hi[16];
+    uint32_t pad2_[1];
     unsigned long long rays_shadow, rays_reflect, rays_refract, rays_depth_cut, shaded_hits, texel_lookups;
     // [0 extend | 1 shadow][kd_splits, instance_tests, triangle_tests, bbox_gates, prim_flops (the reference's work),
     //                       box tests, instance tests, triangle tests, bbox gates, prim_flops EXECUTED on the device]

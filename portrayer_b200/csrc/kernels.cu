@@ -40,7 +40,11 @@ constexpr int kBlock = PT_BLOCK;
 #ifndef PT_SHADE_BLOCK_BIG
 #define PT_SHADE_BLOCK_BIG 512
 #endif
-constexpr int kShadeBlockSmall = kBlock, kShadeBlockBig = PT_SHADE_BLOCK_BIG;
+// rounds of the big block per tile: 4 x 512 parents = 165 KB of shared memory, one block per SM
+#ifndef PT_SHADE_TILE_ROUNDS
+#define PT_SHADE_TILE_ROUNDS 4
+#endif
+constexpr int kShadeBlockSmall = kBlock, kShadeBlockBig = PT_SHADE_BLOCK_BIG, kShadeRoundsBig = PT_SHADE_TILE_ROUNDS;
 constexpr uint64_t kShadeBigPaths = 1ull << 21;  // batches of at least this many paths use the big group
 // minimum resident blocks per SM asked of ptxas (register budget = 65536 / (kBlock * min blocks)); tuned on B200,
 // see DESIGN.md "occupancy"
@@ -87,6 +91,22 @@ PT_D void record_error(const FrameParams& fp, const NodePool& pool, BatchCtl* ct
     ctl->err_info[2] = root % fp.samples;
     ctl->err_info[3] = pool.pathid[node];
     ctl->err_info[4] = where;
+}
+
+// the rays of the level the control block points at: n of them, ray j at pool index at(j)
+struct LevelRays {
+    uint32_t begin, n_lo, hi_base, n;
+    PT_D uint32_t at(uint32_t j) const { return j < n_lo ? begin + j : hi_base + (j - n_lo); }
+};
+PT_D LevelRays level_rays(const BatchCtl* ctl, const NodePool& pool) {
+    const uint32_t level = ctl->level;
+    LevelRays r;
+    r.begin = ctl->level_start[level];
+    r.n_lo = ctl->level_start[level + 1] - r.begin;
+    const uint32_t hi_now = ctl->level_hi[level], hi_prev = level ? ctl->level_hi[level - 1] : 0u;
+    r.hi_base = pool.capacity - hi_now;
+    r.n = r.n_lo + (hi_now - hi_prev);
+    return r;
 }
 
 // ------------------------------------------------------------------ camera
@@ -166,14 +186,14 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
     const NodePool& pool = fs.pool;
     BatchCtl* ctl = fs.ctl;
     const uint32_t level = ctl->level;
-    const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
+    const LevelRays rays = level_rays(ctl, pool);
     KdStack tlas_stack, blas_stack;
     WorkCounters wc;
     uint32_t err = 0;
     // Dynamic distribution: a warp claims the next 32 rays when it has finished its last 32 (one atomic per warp
     // and chunk).  Ray cost varies by orders of magnitude (sky vs. deep kd walks); a static grid-stride split leaves
     // most of the machine idle while the slowest warps finish.
-    const uint32_t n = end - begin;
+    const uint32_t n = rays.n;
     const int lane = threadIdx.x & 31;
     uint32_t next = 0;
     if (lane == 0) next = atomicAdd(&ctl->cursor[0], 32u);
@@ -182,8 +202,8 @@ __global__ void __launch_bounds__(kBlock, PT_EXTEND_MIN_BLOCKS) extend_kernel(in
         if (base >= n) break;
         // claim the following chunk now: the atomic's round trip overlaps the walk of this one
         if (lane == 0) next = atomicAdd(&ctl->cursor[0], 32u);
-        const uint32_t i = begin + base + lane;
-        if (i >= end) continue;
+        if (base + lane >= n) continue;
+        const uint32_t i = rays.at(base + lane);
         const V3 o = v3(pool.ox[i], pool.oy[i], pool.oz[i]);
         const V3 d = v3(pool.dx[i], pool.dy[i], pool.dz[i]);
         Hit hit{(double)INFINITY, kNone, 0};
@@ -209,8 +229,8 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
     BatchCtl* ctl = fs.ctl;
     const uint32_t level = ctl->level;
     const uint32_t first_slot = ctl->first_slot;
-    const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
-    const uint32_t n = end - begin;
+    const LevelRays rays = level_rays(ctl, pool);
+    const uint32_t n = rays.n;
     const unsigned long long total = (unsigned long long)n * sc.n_lights;
     KdStack tlas_stack, blas_stack;
     WorkCounters wc;
@@ -226,7 +246,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
         const unsigned long long j = (unsigned long long)base + lane;
         if (j >= total) continue;
         const uint32_t l = (uint32_t)(j / n);
-        const uint32_t i = begin + (uint32_t)(j % n);
+        const uint32_t i = rays.at((uint32_t)(j % n));
         const uint32_t inst = pool.inst[i];
         if (inst == kNone) continue;
         const V3 o = v3(pool.ox[i], pool.oy[i], pool.oz[i]);
@@ -256,41 +276,42 @@ __global__ void __launch_bounds__(kBlock, PT_SHADOW_MIN_BLOCKS) shadow_kernel(in
 }
 
 // ------------------------------------------------------------------ shade
-// Node slots for the children of one block-wide round of the shade kernel: ONE atomicAdd per block, the reflected
-// children of the block's 128 parents first (in parent order), then the refracted ones.  Allocating per warp
-// (32 parents -> up to 32 + 32 slots) made every 32-ray chunk of the next level a mixture of reflected and refracted
-// rays, and the mixture compounds level by level: on graphics-castle ncu counted 12 of 32 lanes active in the extend
-// launches of levels >= 1.  Grouped per block, a chunk of the next level holds children of ONE kind from neighbouring
-// parents.  (Sorting every level by (direction octant, origin cell) was measured too and lost: DESIGN.md section 10.)
-// Every thread of the block must call it (two barriers).
-template <int BLOCK>
-PT_D void block_alloc(BatchCtl* ctl, bool want0, bool want1, uint32_t& n0, uint32_t& n1) {
-    __shared__ uint32_t s_cnt[2][BLOCK / 32];
-    __shared__ uint32_t s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, want0), m1 = __ballot_sync(0xFFFFFFFFu, want1);
-    if (lane == 0) { s_cnt[0][warp] = (uint32_t)__popc(m0); s_cnt[1][warp] = (uint32_t)__popc(m1); }
-    __syncthreads();
-    uint32_t before0 = 0, before1 = 0, total0 = 0, total1 = 0;
-#pragma unroll
-    for (int w = 0; w < BLOCK / 32; ++w) {
-        const uint32_t c0 = s_cnt[0][w], c1 = s_cnt[1][w];
-        if (w < warp) { before0 += c0; before1 += c1; }
-        total0 += c0;
-        total1 += c1;
-    }
-    if (threadIdx.x == 0) s_base = (total0 + total1) ? atomicAdd(&ctl->pool_count, total0 + total1) : 0u;
-    __syncthreads();
-    const uint32_t base = s_base;
-    const unsigned lt = (1u << lane) - 1u;
-    n0 = want0 ? base + before0 + (uint32_t)__popc(m0 & lt) : kNone;
-    n1 = want1 ? base + total0 + before1 + (uint32_t)__popc(m1 & lt) : kNone;
-}
-
 // `loop`: the conditional handle of the frame graph's WHILE node (0 on the stream path); the last block to
 // finish decides whether another recursion level has rays to trace.
-template <int BLOCK>
+// A block shades a TILE of K * BLOCK consecutive rays of the level, K rounds of BLOCK; the children the rounds ask for are
+// kept in shared memory (ShadeTile) and allocated ONCE per tile, in parent order: reflected children to the bottom end
+// of the pool, refracted children to its top end (device_scene.cuh BatchCtl), so a level is all of its reflected rays
+// followed by all of its refracted rays.  Allocating per warp (32 parents -> up to 32 + 32 slots) made every 32-ray chunk
+// of the next level a mixture of reflected and refracted rays, and the mixture compounds level by level: on
+// graphics-castle ncu counted 12 of 32 lanes active in the extend launches of levels >= 1.  And where few parents spawn
+// children at all — the deep levels of a scene with a few dielectrics — a small group yields a run of a few dozen
+// children, so every chunk of the next level straddles runs from unrelated corners of the picture: the bigger the tile,
+// the longer the runs (graphics-castle 4K x 16: 324 / 304 / 291 ms with groups of 128 / 256 / 512 parents,
+// profiles/r02_ab_shade_group.txt).  (Sorting every level by (direction octant, origin cell) was measured too and lost:
+// DESIGN.md section 10.)
+template <int BLOCK, int K>
+struct ShadeTile {
+    static constexpr int T = BLOCK * K;  // parents per tile
+    static constexpr int W = T / 32;     // warp-rounds per tile
+    static constexpr size_t kBytes = (size_t)T * (9 * sizeof(double) + 2 * sizeof(uint32_t)) + (size_t)W * 4 * sizeof(uint32_t);
+    double* d;       // [9][T]: hit point, reflected direction, refracted direction
+    uint32_t* u;     // [2][T]: root, path id
+    uint32_t* mask;  // [2][W]: which lanes of each warp-round want a reflected / refracted child
+    uint32_t* pre;   // [2][W]: children wanted by the warp-rounds before this one
+    PT_D explicit ShadeTile(unsigned char* smem) {
+        d = reinterpret_cast<double*>(smem);
+        u = reinterpret_cast<uint32_t*>(d + 9 * T);
+        mask = u + 2 * T;
+        pre = mask + 2 * W;
+    }
+};
+
+template <int BLOCK, int K>
 __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : PT_SHADE_MIN_BLOCKS)) shade_kernel(int slot_id, cudaGraphConditionalHandle loop) {
+    extern __shared__ __align__(16) unsigned char shade_smem[];
+    using Tile = ShadeTile<BLOCK, K>;
+    const Tile tile_mem(shade_smem);
+    __shared__ uint32_t s_base[2], s_limit[2];
     const FrameState& fs = c_state[slot_id];
     const DScene& sc = fs.sc;
     const FrameParams& fp = fs.fp;
@@ -298,16 +319,19 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : PT_SHADE_MIN_BLOCKS
     BatchCtl* ctl = fs.ctl;
     const uint32_t level = ctl->level;
     const uint32_t first_slot = ctl->first_slot;
-    const uint32_t begin = ctl->level_start[level], end = ctl->level_start[level + 1];
-    const uint32_t n = end - begin;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounds = (n + stride - 1) / stride;  // every thread runs the same number of rounds (block_alloc is collective)
+    const LevelRays rays = level_rays(ctl, pool);
+    const uint32_t n = rays.n;
+    const uint32_t n_tiles = (n + Tile::T - 1) / Tile::T;  // (tiles are per block: every thread of a block runs the same loops)
+    const int lane = threadIdx.x & 31;
     uint32_t err = 0, err_seen = 0;
     unsigned long long n_shaded = 0, n_reflect = 0, n_refract = 0, n_cut = 0, n_texel = 0;
 
-    for (uint32_t r = 0; r < rounds; ++r) {
-        const uint32_t i = begin + r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool active = i < end;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int k = 0; k < K; ++k) {
+        const int slot = k * BLOCK + (int)threadIdx.x;
+        const uint32_t j = tile * (uint32_t)Tile::T + (uint32_t)slot;
+        const bool active = j < n;
+        const uint32_t i = active ? rays.at(j) : 0u;
         bool want0 = false, want1 = false;  // children to trace
         V3 hit_point = v3(0, 0, 0), dir0 = v3(0, 0, 0), dir1 = v3(0, 0, 0);
         uint32_t root = 0, pathid = 0;
@@ -470,13 +494,68 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : PT_SHADE_MIN_BLOCKS
             pool.child1[i] = c1;
         }
 
-        // children: reflected ray first, then refracted (material.rs:243 before :303)
-        uint32_t n0, n1;
-        block_alloc<BLOCK>(ctl, want0, want1, n0, n1);
+        // what this ray asks for goes into the tile (path ids: reflected = parent << 1, refracted = parent << 1 | 1,
+        // material.rs:243 before :303 — they do not depend on where the children are stored)
+        const unsigned m0 = __ballot_sync(0xFFFFFFFFu, want0), m1 = __ballot_sync(0xFFFFFFFFu, want1);
+        if (lane == 0) { tile_mem.mask[slot >> 5] = m0; tile_mem.mask[Tile::W + (slot >> 5)] = m1; }
+        if (want0 || want1) {
+            double* d = tile_mem.d + slot;
+            d[0 * Tile::T] = hit_point.x; d[1 * Tile::T] = hit_point.y; d[2 * Tile::T] = hit_point.z;
+            d[3 * Tile::T] = dir0.x; d[4 * Tile::T] = dir0.y; d[5 * Tile::T] = dir0.z;
+            d[6 * Tile::T] = dir1.x; d[7 * Tile::T] = dir1.y; d[8 * Tile::T] = dir1.z;
+            tile_mem.u[slot] = root;
+            tile_mem.u[Tile::T + slot] = pathid;
+        }
+      }
+      __syncthreads();
+      // one allocation for the tile: exclusive prefix of the warp-rounds' counts (warp 0), then the two atomics
+      if (threadIdx.x < 32) {
+          uint32_t run0 = 0, run1 = 0;
+          for (int w0 = 0; w0 < Tile::W; w0 += 32) {
+              const int w = w0 + lane;
+              const uint32_t c0 = w < Tile::W ? (uint32_t)__popc(tile_mem.mask[w]) : 0u, c1 = w < Tile::W ? (uint32_t)__popc(tile_mem.mask[Tile::W + w]) : 0u;
+              uint32_t i0 = c0, i1 = c1;  // inclusive scans over the 32 lanes
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                  const uint32_t a0 = __shfl_up_sync(0xFFFFFFFFu, i0, off), a1 = __shfl_up_sync(0xFFFFFFFFu, i1, off);
+                  if (lane >= off) { i0 += a0; i1 += a1; }
+              }
+              if (w < Tile::W) { tile_mem.pre[w] = run0 + i0 - c0; tile_mem.pre[Tile::W + w] = run1 + i1 - c1; }
+              run0 += __shfl_sync(0xFFFFFFFFu, i0, 31);
+              run1 += __shfl_sync(0xFFFFFFFFu, i1, 31);
+          }
+          if (lane == 0) {
+              // reflected children ascend from the bottom of the pool, refracted children descend from its top
+              s_base[0] = run0 ? atomicAdd(&ctl->pool_count, run0) : 0u;
+              const uint32_t hi = run1 ? atomicAdd(&ctl->hi_count, run1) : 0u;
+              // Both counters keep counting past each other when the pool is full (their sum is what the retry sizes its
+              // batches by).  A slot is usable only while the two ends have not met: each side reads the OTHER end after
+              // its own allocation — whichever of two colliding allocations comes second sees the first.
+              const uint32_t hi_now = atomicAdd(&ctl->hi_count, 0u), lo_now = atomicAdd(&ctl->pool_count, 0u);
+              s_limit[0] = pool.capacity - min(hi_now, pool.capacity);  // reflected slots must lie below this index
+              s_limit[1] = lo_now;                                      // refracted slots must lie at or above it
+              // the tile's refracted children in parent order inside its slice [capacity - (hi + run1), capacity - hi)
+              const uint64_t end_excl = (uint64_t)hi + run1;
+              s_base[1] = end_excl <= pool.capacity ? pool.capacity - (uint32_t)end_excl : kNone;
+          }
+      }
+      __syncthreads();
+      for (int k = 0; k < K; ++k) {
+        const int slot = k * BLOCK + (int)threadIdx.x;
+        const uint32_t j = tile * (uint32_t)Tile::T + (uint32_t)slot;
+        if (j >= n) continue;
+        const unsigned m0 = tile_mem.mask[slot >> 5], m1 = tile_mem.mask[Tile::W + (slot >> 5)];
+        const bool want0 = (m0 >> lane) & 1u, want1 = (m1 >> lane) & 1u;
+        if (!want0 && !want1) continue;
+        const uint32_t i = rays.at(j);
+        const unsigned lt = (1u << lane) - 1u;
+        const double* d = tile_mem.d + slot;
+        const uint32_t root = tile_mem.u[slot], pathid = tile_mem.u[Tile::T + slot];
         if (want0) {
-            if (n0 < pool.capacity) {
-                pool.ox[n0] = hit_point.x; pool.oy[n0] = hit_point.y; pool.oz[n0] = hit_point.z;
-                pool.dx[n0] = dir0.x; pool.dy[n0] = dir0.y; pool.dz[n0] = dir0.z;
+            const uint32_t n0 = s_base[0] + tile_mem.pre[slot >> 5] + (uint32_t)__popc(m0 & lt);
+            if (n0 < s_limit[0]) {
+                pool.ox[n0] = d[0 * Tile::T]; pool.oy[n0] = d[1 * Tile::T]; pool.oz[n0] = d[2 * Tile::T];
+                pool.dx[n0] = d[3 * Tile::T]; pool.dy[n0] = d[4 * Tile::T]; pool.dz[n0] = d[5 * Tile::T];
                 pool.root[n0] = root;
                 pool.pathid[n0] = pathid << 1;
                 pool.child0[i] = n0;
@@ -487,9 +566,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : PT_SHADE_MIN_BLOCKS
             }
         }
         if (want1) {
-            if (n1 < pool.capacity) {
-                pool.ox[n1] = hit_point.x; pool.oy[n1] = hit_point.y; pool.oz[n1] = hit_point.z;
-                pool.dx[n1] = dir1.x; pool.dy[n1] = dir1.y; pool.dz[n1] = dir1.z;
+            const uint32_t n1 = s_base[1] == kNone ? kNone : s_base[1] + tile_mem.pre[Tile::W + (slot >> 5)] + (uint32_t)__popc(m1 & lt);
+            if (n1 != kNone && n1 >= s_limit[1]) {
+                pool.ox[n1] = d[0 * Tile::T]; pool.oy[n1] = d[1 * Tile::T]; pool.oz[n1] = d[2 * Tile::T];
+                pool.dx[n1] = d[6 * Tile::T]; pool.dy[n1] = d[7 * Tile::T]; pool.dz[n1] = d[8 * Tile::T];
                 pool.root[n1] = root;
                 pool.pathid[n1] = (pathid << 1) | 1u;
                 pool.child1[i] = n1;
@@ -499,6 +579,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : PT_SHADE_MIN_BLOCKS
                 pool.child1[i] = kChildBg;
             }
         }
+      }
+      __syncthreads();  // the tile's shared memory is reused
     }
 
     if (err) atomicOr(&ctl->error_bits, err);
@@ -522,14 +604,24 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : PT_SHADE_MIN_BLOCKS
         __threadfence();
         const uint32_t ticket = atomicAdd(&ctl->blocks_done[level], 1u);
         if (ticket == gridDim.x - 1) {
-            const uint32_t count = atomicAdd(&ctl->pool_count, 0u);
-            const uint32_t next_end = count < pool.capacity ? count : pool.capacity;
+            const uint32_t count = atomicAdd(&ctl->pool_count, 0u), hi = atomicAdd(&ctl->hi_count, 0u);
+            uint32_t next_end = count < pool.capacity ? count : pool.capacity;
+            uint32_t next_hi = hi < pool.capacity ? hi : pool.capacity;
+            const uint32_t end = ctl->level_start[level + 1];
+            if ((uint64_t)next_end + next_hi > pool.capacity) {
+                // the two ends have met: the batch is redone with a smaller size (api.cu), its next level gets no rays
+                // (the counters above keep what was asked for)
+                atomicOr(&ctl->error_bits, PT_DEVERR_OVERFLOW);
+                next_end = end;
+                next_hi = ctl->level_hi[level];
+            }
             ctl->level_start[level + 2] = next_end;
+            ctl->level_hi[level + 1] = next_hi;
             ctl->level = level + 1;
             ctl->levels_run = level + 1;
             ctl->cursor[0] = 0u;
             ctl->cursor[1] = 0u;
-            const bool more = next_end > end && level + 1 < fs.n_levels;
+            const bool more = (next_end > end || next_hi > ctl->level_hi[level]) && level + 1 < fs.n_levels;
             if (loop) cudaGraphSetConditional(loop, more ? 1u : 0u);
         }
     }
@@ -868,11 +960,12 @@ int g_grid_extend[3] = {0, 0, 0}, g_grid_shadow[3] = {0, 0, 0};  // [kWalkExact 
 int g_grid_shade[2] = {0, 0};                                     // [small group | big group]
 
 template <class K>
-int persistent_grid(K kernel, int block = kBlock) {
+int persistent_grid(K kernel, int block = kBlock, size_t dynamic_smem = 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+    if (dynamic_smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynamic_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dynamic_smem);
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
@@ -887,8 +980,8 @@ void kernels_init() {
     g_grid_shadow[1] = persistent_grid(shadow_kernel<true>);
     g_grid_extend[2] = persistent_grid(extend_kernel<false, false, true>);
     g_grid_shadow[2] = persistent_grid(shadow_kernel<false, false, true>);
-    g_grid_shade[0] = persistent_grid(shade_kernel<kShadeBlockSmall>, kShadeBlockSmall);
-    g_grid_shade[1] = persistent_grid(shade_kernel<kShadeBlockBig>, kShadeBlockBig);
+    g_grid_shade[0] = persistent_grid(shade_kernel<kShadeBlockSmall, 1>, kShadeBlockSmall, ShadeTile<kShadeBlockSmall, 1>::kBytes);
+    g_grid_shade[1] = persistent_grid(shade_kernel<kShadeBlockBig, kShadeRoundsBig>, kShadeBlockBig, ShadeTile<kShadeBlockBig, kShadeRoundsBig>::kBytes);
 }
 
 static inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
@@ -955,8 +1048,11 @@ void launch_shadow(int slot, uint64_t max_items, uint32_t n_lights, int mode, bo
 }
 bool shade_big_group(uint64_t batch_paths) { return batch_paths >= kShadeBigPaths; }
 void launch_shade(int slot, uint64_t max_items, bool big, cudaGraphConditionalHandle loop, cudaStream_t st) {
-    if (big) shade_kernel<kShadeBlockBig><<<capped(g_grid_shade[1], max_items, kShadeBlockBig), kShadeBlockBig, 0, st>>>(slot, loop);
-    else shade_kernel<kShadeBlockSmall><<<capped(g_grid_shade[0], max_items, kShadeBlockSmall), kShadeBlockSmall, 0, st>>>(slot, loop);
+    if (big)
+        shade_kernel<kShadeBlockBig, kShadeRoundsBig><<<capped(g_grid_shade[1], max_items, kShadeBlockBig * kShadeRoundsBig), kShadeBlockBig,
+                                                        ShadeTile<kShadeBlockBig, kShadeRoundsBig>::kBytes, st>>>(slot, loop);
+    else
+        shade_kernel<kShadeBlockSmall, 1><<<capped(g_grid_shade[0], max_items, kShadeBlockSmall), kShadeBlockSmall, ShadeTile<kShadeBlockSmall, 1>::kBytes, st>>>(slot, loop);
 }
 void launch_tree_eval(int slot, uint32_t n_paths, cudaStream_t st) {
     tree_eval_kernel<<<blocks_for(n_paths), kBlock, 0, st>>>(slot);
@@ -1017,10 +1113,11 @@ cudaError_t build_frame_graph(int slot, uint32_t n_slots, uint32_t samples, uint
         if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
         void* args2[2] = {&slot, &handle};
         const bool big = shade_big_group(n_paths);
-        k.func = big ? (void*)shade_kernel<kShadeBlockBig> : (void*)shade_kernel<kShadeBlockSmall>;
+        k.func = big ? (void*)shade_kernel<kShadeBlockBig, kShadeRoundsBig> : (void*)shade_kernel<kShadeBlockSmall, 1>;
         k.kernelParams = args2;
         k.blockDim = dim3(big ? kShadeBlockBig : kShadeBlockSmall);
-        k.gridDim = dim3(big ? capped(g_grid_shade[1], capacity, kShadeBlockBig) : capped(g_grid_shade[0], capacity, kShadeBlockSmall));
+        k.gridDim = dim3(big ? capped(g_grid_shade[1], capacity, kShadeBlockBig * kShadeRoundsBig) : capped(g_grid_shade[0], capacity, kShadeBlockSmall));
+        k.sharedMemBytes = (unsigned)(big ? ShadeTile<kShadeBlockBig, kShadeRoundsBig>::kBytes : ShadeTile<kShadeBlockSmall, 1>::kBytes);
         e = cudaGraphAddKernelNode(&n_sha, body, &n_shd, 1, &k);
         if (e != cudaSuccess) { cudaGraphDestroy(graph); return e; }
     }
