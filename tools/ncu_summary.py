@@ -88,7 +88,7 @@ def traffic(path: str, source: str) -> None:
             continue
         if "_kernel<(bool)1" in r[ki] or "_kernel<1" in r[ki]:
             continue  # the counting variants of the traversal kernels (bench.py's counting pass): not what the timed region runs
-        name = r[ki].split("(")[0].replace("void ", "").replace("ptd::<unnamed>::", "").split("<")[0]
+        name = r[ki].split("(")[0].replace("void ", "").replace("ptd::<unnamed>::", "").replace("unnamed>::", "").split("<")[0]
         per[name][r[mi]] += v
         ids[name].add(r[ii])
     out = {}
