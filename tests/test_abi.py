@@ -132,3 +132,27 @@ def test_header_is_plain_c(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
     if shutil.which("g++"):
         subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
+
+
+def test_png_size_is_the_stored_deflate_layout(native_libraries):
+    """pt_png_size is pure arithmetic (no device): signature + IHDR + one IDAT of stored deflate blocks + IEND, the layout
+    tests/test_gpu_image_io.py checks byte for byte on the device"""
+    from portrayer_b200 import _ffi
+
+    for w, h in ((1, 1), (7, 5), (1456, 15), (910, 512), (3840, 2160)):
+        raw = h * (1 + 3 * w)
+        blocks = max(1, -(-raw // 65535))
+        assert _ffi.gpu.pt_png_size(w, h) == 8 + 25 + 12 + (2 + 5 * blocks + raw + 4) + 12
+    assert _ffi.gpu.pt_png_size(0, 5) == 0
+
+
+def test_integration_doc_matches_the_abi(native_libraries):
+    """INTEGRATION.md's Rust mirror states PtStats' size: keep it in step with the header"""
+    import ctypes as C
+
+    from portrayer_b200 import _ffi
+
+    n = C.sizeof(_ffi.PtStats)
+    assert _ffi.gpu.pt_abi_sizeof(2) == n
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    assert f"_opaque: [u64; {n // 8}]" in doc and f"({n} bytes" in doc
