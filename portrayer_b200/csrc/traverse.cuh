@@ -17,9 +17,6 @@
 #include "device_scene.cuh"
 
 // tuning switches (A/B'd on the box with tools/build_variants.sh + tools/ab_bench.sh)
-#ifndef PT_BLAS_TWO_PHASE
-#define PT_BLAS_TWO_PHASE 1
-#endif
 #ifndef PT_ANY_CHEAP_FIRST
 #define PT_ANY_CHEAP_FIRST 1
 #endif
