@@ -7,6 +7,6 @@ W=${1:-castle-hd}; TAG=${2:-castle}; N=${3:-12}; SKIP=${4:-0}
 mkdir -p gpurun_out
 PT_DISABLE_GRAPHS=1 timeout 1200 ncu --set full --import-source on --clock-control none \
   --kernel-name-base demangled -k regex:'(extend|shadow)_kernel<\(bool\)0, \(bool\)0, \(bool\)1>' -s $SKIP -c $N -f -o gpurun_out/prof_$TAG \
-  python bench.py --device-only --workload $W --samples 1 --steps 1 --warmup 1 --streams 1 > gpurun_out/prof_$TAG.log 2>&1
+  python bench.py --device-only --workload $W --samples ${PROFILE_SAMPLES:-1} --steps 1 --warmup 1 --streams 1 > gpurun_out/prof_$TAG.log 2>&1
 tail -3 gpurun_out/prof_$TAG.log
 ls -la gpurun_out/prof_$TAG.ncu-rep
