@@ -1113,6 +1113,10 @@ static int init_context(DeviceCtx* c, int device) {
         launch_gamma_lut(c->gamma_lut, c->stream);
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
+    // per DEVICE: the persistent grids (occupancy queries) and the kernels' function attributes — the shade kernel's
+    // 165 KB tile needs cudaFuncAttributeMaxDynamicSharedMemorySize set on every device that launches it
+    CUDA_TRY(cudaSetDevice(device));
+    kernels_init();
     CUDA_TRY(cudaGetLastError());
     c->ready = true;
     return PT_OK;
