@@ -156,3 +156,39 @@ def test_integration_doc_matches_the_abi(native_libraries):
     assert _ffi.gpu.pt_abi_sizeof(2) == n
     doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
     assert f"_opaque: [u64; {n // 8}]" in doc and f"({n} bytes" in doc
+
+
+def test_device_group_members_partition_the_callers_tiles(native_libraries):
+    """pt_render over a device group gives member i of n rank r + w*i of world w*n (api.cu render_group), r / w the
+    caller's own rank / world: the members' pixels must be exactly the caller's pixels, each once — with slices and
+    ragged image sizes.  Pure host logic (tiles.c), no device."""
+    import numpy as np
+
+    from portrayer_b200 import _ffi
+    from portrayer_b200.render import make_params
+
+    def owned(p):
+        n = _ffi.gpu.pt_owned_pixels(p, None, 0)
+        out = np.empty(n, np.uint32)
+        assert _ffi.gpu.pt_owned_pixels(p, out.ctypes.data, n) == n
+        return out
+
+    for (w, h, slice_, tile) in ((200, 120, None, 16), (333, 77, (5, 3, 300, 70), 32), (64, 64, None, 32)):
+        for world in (1, 2, 3):
+            for rank in range(world):
+                mine = owned(make_params(w, h, 1, "hash", 1, slice_, rank=rank, world=world, tile=tile))
+                for n in (2, 8):
+                    parts = [owned(make_params(w, h, 1, "hash", 1, slice_, rank=rank + world * i, world=world * n, tile=tile)) for i in range(n)]
+                    union = np.concatenate(parts)
+                    assert len(union) == len(mine) and np.array_equal(np.sort(union), np.sort(mine))
+
+
+def test_python_constants_match_the_header(native_libraries):
+    """the ctypes layer restates the header's #defines: every PT_RENDER_* / PT_PIXELS_* value must agree"""
+    from portrayer_b200 import _ffi
+
+    text = open(os.path.join(REPO, "include", "portrayer_gpu.h")).read()
+    found = dict(re.findall(r"#define\s+(PT_(?:RENDER|PIXELS)_[A-Z0-9_]+)\s+(\d+)u", text))
+    assert len(found) >= 13, found
+    for name, value in found.items():
+        assert getattr(_ffi, name) == int(value), name
